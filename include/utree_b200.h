@@ -1,0 +1,174 @@
+/* utree_b200.h -- C ABI of the B200-native SEARCH_GG hot path.
+ *
+ * The reference (knights-lab/UTree, itree.c) has no library/FFI interface
+ * ("Gutted the API because nobody (would) use(d) it", itree.c:27-29); its
+ * search binary is main() -> XT_read32() -> XT_doSearch32().  This header is
+ * the boundary a maintainer would bind instead of those two calls: plain C,
+ * pointers and sizes only, int return codes (0 = ok), no exceptions, no CPU
+ * fallback -- every entry point fails with UTB_ERR_CUDA when no sm_100 device
+ * is usable.  INTEGRATION.md shows the replacement main().
+ *
+ *   reference                                this header
+ *   ---------------------------------------  ---------------------------------
+ *   XT_read32()            itree.c:733-828   utb_ctr_open + utb_db_upload
+ *   readSamplesFPdelim()   itree.c:1202-1223 (inside utb_ctr_open)
+ *   XT_doSearch32()        itree.c:833-1108  utb_search_file / utb_search_mem
+ *     XT_INITIATE_WS       itree.c:860-901     host framer (fasta_reader.c)
+ *     XT_WORD_SEARCH       itree.c:903-933     pack + lookup kernels
+ *     XT_getIX32/xtSuffixBS itree.c:699-730    lookup kernel
+ *     full aufbau vote     itree.c:1028-1098   vote kernels
+ *     fprintf lines        itree.c:1032-1096   host formatter (formatter.c)
+ *   main() search branch   itree.c:1357-1377 utb_main
+ */
+#ifndef UTREE_B200_H
+#define UTREE_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (never exceptions) -------------------------------------- */
+enum {
+    UTB_OK = 0,
+    UTB_ERR_ARG = 1,      /* bad argument                                     */
+    UTB_ERR_IO = 2,       /* cannot open / short read                         */
+    UTB_ERR_FORMAT = 3,   /* malformed CTR or FASTA                           */
+    UTB_ERR_NOMEM = 4,
+    UTB_ERR_CUDA = 5,     /* CUDA runtime error or no usable device           */
+    UTB_ERR_LIMIT = 6     /* input exceeds a documented limit                 */
+};
+/* Thread-local message for the last failing call on this thread. */
+const char *utb_last_error(void);
+
+/* ---- CTR database on the host (App. A of SURVEY.md) ----------------------- */
+typedef struct utb_ctr utb_ctr;
+/* Parses header, BinIx, record blob and label tail (itree.c:733-828,
+ * 1154-1223).  The file stays mapped; nothing is copied until upload. */
+int utb_ctr_open(const char *path, utb_ctr **out);
+void utb_ctr_close(utb_ctr *ctr);
+uint64_t utb_ctr_num_nodes(const utb_ctr *ctr);   /* metadata[3]              */
+uint32_t utb_ctr_ix_bytes(const utb_ctr *ctr);    /* sizeof(IXTYPE): 2 or 4   */
+uint32_t utb_ctr_binix_bytes(const utb_ctr *ctr); /* on-disk entry: 4 or 8    */
+uint32_t utb_ctr_max_ix(const utb_ctr *ctr);      /* sampIX+1 (itree.c:855)   */
+uint64_t utb_ctr_last_bin(const utb_ctr *ctr);    /* BinIx[2^24] (itree.c:792)*/
+const char *utb_ctr_label(const utb_ctr *ctr, uint32_t ix);
+uint32_t utb_ctr_label_rank(const utb_ctr *ctr, uint32_t ix); /* strcmp order */
+
+/* ---- CTR resident in one GPU's HBM ---------------------------------------- */
+typedef struct utb_db utb_db;
+int utb_device_count(int *n);
+/* Copies prefix index, packed records and label table to `device`.  The host
+ * views stay caller-owned.  The returned handle is bound to that device. */
+int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out);
+void utb_db_free(utb_db *db);
+uint64_t utb_db_hbm_bytes(const utb_db *db);
+
+/* ---- per-read result record (what the vote leaves for the formatter) ------ */
+enum { UTB_NONE = 0, UTB_STAR = 1, UTB_WALK = 2 };
+#define UTB_CUT_EMPTY 0xFFFFFFFFu   /* dv == -1: empty taxonomy               */
+#define UTB_CUT_FULL  0xFFFFFFFEu   /* dv == -2: whole label                  */
+typedef struct {
+    uint32_t kind;    /* UTB_NONE: no line; STAR: "...\t*"; WALK: "...\tsl;ol" */
+    uint32_t label;   /* label id whose string / prefix is printed            */
+    uint32_t cut;     /* WALK: bytes of the label to print, or EMPTY / FULL   */
+    uint32_t found;   /* foundUniq                                            */
+    uint32_t uix;     /* distinct labels hit                                  */
+    uint32_t sl, ol;  /* WALK only                                            */
+    uint32_t _pad;
+} utb_result;
+
+/* ---- batches: one stream slot = pinned staging + device buffers ----------- */
+typedef struct utb_batch utb_batch;
+/* max_bytes: raw FASTA bytes per batch; max_reads: records per batch. */
+int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, utb_batch **out);
+void utb_batch_destroy(utb_batch *b);
+/* Pinned staging the caller fills before submit: raw bytes (sequence lines
+ * anywhere inside, headers may stay in between), and per read the byte offset
+ * and length of its trimmed sequence line.  Lengths are limited to 16777214
+ * bases (LINELEN, itree.c:836). */
+char *utb_batch_bytes(utb_batch *b);
+uint64_t *utb_batch_seq_off(utb_batch *b);
+uint32_t *utb_batch_seq_len(utb_batch *b);
+size_t utb_batch_max_bytes(const utb_batch *b);
+size_t utb_batch_max_reads(const utb_batch *b);
+/* Number of 32-base position slots a read of `len` bases occupies on the
+ * device; a batch may not exceed utb_batch_max_slots() in total. */
+uint64_t utb_read_slots(uint32_t len);
+uint64_t utb_batch_max_slots(const utb_batch *b);
+/* Asynchronous: H2D copy, pack, lookup, vote, D2H of results on the batch's
+ * stream.  The caller must not touch the pinned staging until wait returns. */
+int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
+/* Blocks until the batch is done; *results points at n_reads records in
+ * pinned memory, valid until the next submit on this batch. */
+int utb_batch_wait(utb_batch *b, const utb_result **results);
+/* Re-runs only the device stages on the inputs already resident from the last
+ * submit (no PCIe traffic) `iters` times and reports CUDA-event milliseconds
+ * per stage, summed over iters: ms[0]=pack ms[1]=lookup ms[2]=vote ms[3]=total.
+ * Also reports how many kernels were launched. */
+int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint64_t *launches);
+/* Counters of the last submit: valid 32-mer windows x strands (= lookups). */
+int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits);
+
+/* ---- stage-level entry points (parity tests call the kernels 1:1) --------- */
+/* words[n] (host) -> ix[n] (host): label id or 0xFFFFFFFF, exactly
+ * XT_getIX32 (itree.c:720-730). */
+int utb_lookup_words(utb_db *db, const uint64_t *words, size_t n, uint32_t *ix);
+/* One trimmed sequence (host) -> for every base position i the forward and
+ * reverse-complement 32-mer words and a valid flag (itree.c:906-926).
+ * fwd/rc/valid have room for len entries; entries i > len-32 are invalid. */
+int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len,
+                      uint64_t *fwd, uint64_t *rc, uint8_t *valid);
+/* hits (host; label ids, 0xFFFFFFFF = miss) of n_reads reads laid out
+ * back to back, read r owning hits[off[r] .. off[r+1]) -> vote results
+ * (itree.c:1028-1098). */
+int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off,
+                  size_t n_reads, utb_result *results);
+
+/* ---- whole search (XT_doSearch32 + output, itree.c:833-1108) -------------- */
+typedef struct {
+    uint64_t reads;        /* records parsed ("Searched N queries")            */
+    uint64_t good_finds;   /* reads with >= 1 hit ("Good finds: N")            */
+    uint64_t lookups;      /* valid windows x strands                          */
+    uint64_t hits;
+    uint64_t batches;
+    uint64_t kernel_launches;
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t out_bytes;
+    double seconds_total;  /* wall, excludes DB upload                         */
+    double seconds_device; /* sum of CUDA-event time over batches (all GPUs)   */
+} utb_stats;
+
+typedef struct utb_searcher utb_searcher;
+/* devices[n_devices]: GPUs to shard batches over (DB replicated on each).
+ * host_threads: framing/formatting workers (the CLI's [threads] argument). */
+int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
+                        int host_threads, utb_searcher **out);
+void utb_searcher_destroy(utb_searcher *s);
+/* FASTA in a file -> output file, lines in input order (== reference at
+ * threads=1).  Returns UTB_OK, or UTB_ERR_FORMAT with *ref_exit set to the
+ * reference's exit code (2) after writing every line that precedes the bad
+ * record, as the reference does. */
+int utb_search_file(utb_searcher *s, const char *fasta_path, const char *out_path,
+                    int do_rc, utb_stats *stats, int *ref_exit);
+/* Same with host buffers: fasta[n] in, malloc'ed *out (caller frees with
+ * utb_free) of *out_len bytes. */
+int utb_search_mem(utb_searcher *s, const char *fasta, size_t n, int do_rc,
+                   char **out, size_t *out_len, utb_stats *stats, int *ref_exit);
+void utb_free(void *p);
+
+/* The reference CLI contract (itree.c:1357-1377): argv parse,
+ * stdout banner, exit codes.  Returns the process exit code. */
+int utb_main(int argc, char **argv);
+
+/* ---- measurement helpers --------------------------------------------------- */
+/* Random 32-byte-sector gather bandwidth over a working set of ws_bytes on
+ * `device` (the roofline denominator of SURVEY 8d).  loads: sectors read. */
+int utb_measure_rand32(int device, uint64_t ws_bytes, uint64_t loads, int iters,
+                       double *gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

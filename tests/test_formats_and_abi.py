@@ -1,0 +1,125 @@
+"""File formats (python compress == reference compress), the host CTR loader
+against the oracle's, and the C-ABI surface.  CPU only: no compute calls."""
+import ctypes
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLD, REFDIR, ROOT, gold
+
+
+def _sha(p):
+    return hashlib.sha256(open(p, "rb").read()).hexdigest()
+
+
+@pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
+def test_python_compress_equals_reference_compress(ctrs, meta, name):
+    assert _sha(ctrs[name]) == meta[name]["ctr_sha256"]
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REFDIR, "utree-compress")), reason="oracle/_ref not built")
+def test_reference_compress_live(tmp_path, ctrs):
+    out = str(tmp_path / "q.ctr")
+    subprocess.run([os.path.join(REFDIR, "utree-compress"), gold("quirk.ubt"), out], check=True, stdout=subprocess.DEVNULL)
+    assert _sha(out) == _sha(ctrs["quirk"])
+
+
+def test_library_exports_every_declared_symbol(built):
+    from utree_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "utree_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(utb_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(capi.EXPORTS)
+    L = ctypes.CDLL(capi.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+
+
+def test_product_does_not_reference_oracle():
+    """The oracle is test infrastructure: nothing under utree_b200/csrc or include/ may name it."""
+    for d in ("utree_b200/csrc", "include"):
+        for f in os.listdir(os.path.join(ROOT, d)):
+            if f.endswith((".c", ".cu", ".h")):
+                txt = open(os.path.join(ROOT, d, f)).read()
+                assert "oracle" not in txt.lower(), f
+    so = open(os.path.join(ROOT, "utree_b200", "csrc", "libutree_b200.so"), "rb").read()
+    assert b"orc_" not in so and b"liboracle" not in so
+
+
+@pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
+def test_ctr_loader_matches_oracle_loader(built, ctrs, name):
+    from utree_b200 import capi
+    ctr, orc = capi.Ctr(ctrs[name]), capi.OracleDb(ctrs[name])
+    O = capi.oracle()
+    try:
+        assert ctr.num_nodes == O.orc_db_num_nodes(orc.h)
+        assert ctr.ix_bytes == O.orc_db_ix_bytes(orc.h) and ctr.binix_bytes == O.orc_db_binix_bytes(orc.h)
+        assert ctr.max_ix == orc.max_ix and ctr.last_bin == ctr.num_nodes
+        labels = [ctr.label(i) for i in range(ctr.max_ix)]
+        assert labels == [orc.label(i) for i in range(orc.max_ix)]
+        order = sorted(range(ctr.max_ix), key=lambda i: labels[i])       # bytes compare == strcmp
+        assert [ctr.rank(i) for i in order] == list(range(ctr.max_ix))
+    finally:
+        ctr.close(); orc.free()
+
+
+def test_ctr_loader_dedups_repeated_labels(built, tmp_path):
+    """A label string seen twice keeps its first id (addSampleUdX, itree.c:219-220)."""
+    from utree_b200 import capi, synth
+    words = np.array([5 << 40 | 7, 5 << 40 | 9, 6 << 40 | 1], dtype=np.uint64)
+    tail = b"k__A;p__B\t1\nk__A;p__C\t1\nk__A;p__B\t1\nk__A;p__D\t0\n"
+    p = str(tmp_path / "d.ctr")
+    synth.ctr_write(p, words, np.array([0, 1, 2]), tail, 2)
+    ctr, orc = capi.Ctr(p), capi.OracleDb(p)
+    try:
+        assert ctr.max_ix == orc.max_ix == 3
+        assert [ctr.label(i) for i in range(3)] == [b"k__A;p__B", b"k__A;p__C", b"k__A;p__D"]
+    finally:
+        ctr.close(); orc.free()
+
+
+def test_ctr_loader_rejects_bad_files(built, tmp_path):
+    from utree_b200 import capi
+    with pytest.raises(capi.UtbError, match="Invalid DB file"):
+        capi.Ctr(str(tmp_path / "missing.ctr"))
+    p = str(tmp_path / "zero.ctr")
+    open(p, "wb").write(np.array([8, 0, 2, 0], dtype="<u8").tobytes() + b"\0" * 64)
+    with pytest.raises(capi.UtbError, match="Tree malformatted"):
+        capi.Ctr(p)
+    open(p, "wb").write(np.array([4, 0, 2, 5], dtype="<u8").tobytes() + b"\0" * 64)
+    with pytest.raises(capi.UtbError, match="PACKSIZE"):
+        capi.Ctr(p)
+    open(p, "wb").write(np.array([8, 0, 2, 5], dtype="<u8").tobytes() + b"\0" * 64)
+    with pytest.raises(capi.UtbError, match="Error in reading tree"):
+        capi.Ctr(p)
+
+
+def test_read_slots_geometry(built):
+    from utree_b200 import capi
+    L = capi.lib()
+    assert [L.utb_read_slots(n) for n in (0, 1, 31, 32, 150, 159, 160)] == [1, 1, 1, 2, 5, 5, 6]
+
+
+def test_no_gpu_is_a_loud_error_not_a_fallback(built):
+    """Without a device every device entry point fails with UTB_ERR_CUDA."""
+    import torch
+    from utree_b200 import capi
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.UtbError) as e:
+        capi.device_count()
+    assert e.value.code == 5 and "no CPU fallback" in str(e.value)
+
+
+def test_cli_usage_and_db_errors(built, tmp_path):
+    exe = os.path.join(ROOT, "bin", "utree-search_gg")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 1 and "usage: xtree-searchGG" in p.stdout          # itree.c:1358-1360
+    p = subprocess.run([exe, str(tmp_path / "nope.ctr"), "a.fa", "o.txt", "1", "RC"], capture_output=True, text=True)
+    assert p.returncode == 0                                                    # itree.c:735: exit(0)
+    out = p.stdout.splitlines()
+    assert out[:5] == ["This is UTree [v2.0RF SigNature Edition]", "Reverse complement consideration is enabled.",
+                       "Searching at speed 0.", "Using up to 1 threads.", "Invalid DB file"]

@@ -1,0 +1,175 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the
+golden outputs of the reference binary.  Integer/byte work: bit-exact."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import BAD_CASES, CASES, ROOT, gold, read_fasta
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gpu(built, ctrs):
+    from utree_b200 import capi
+    assert capi.device_count() >= 1
+    state = {}
+    for name, path in ctrs.items():
+        ctr = capi.Ctr(path)
+        state[name] = (ctr, capi.Db(ctr, 0), capi.OracleDb(path))
+    yield state
+    for ctr, db, orc in state.values():
+        db.free(); ctr.close(); orc.free()
+
+
+def _rand_words_for(orc_path_words, rng, n_extra):
+    return orc_path_words
+
+
+@pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
+def test_lookup_words_match_oracle(gpu, name):
+    """XT_getIX32 on members, near-members, same-prefix strangers and random words."""
+    from utree_b200 import synth
+    ctr, db, orc = gpu[name]
+    words, ixs, _, _ = synth.ubt_read(gold(name + ".ubt"))
+    rng = np.random.default_rng(5)
+    w = [words, words + np.uint64(1), words - np.uint64(1),
+         (words & ~np.uint64(0xFFFFFFFFFF)) | rng.integers(0, 1 << 40, words.size, dtype=np.uint64),
+         rng.integers(0, np.iinfo(np.uint64).max, 20000, dtype=np.uint64),
+         np.array([0, np.iinfo(np.uint64).max, 0xFFFFFFFFFF, 1 << 40], dtype=np.uint64)]
+    w = np.concatenate(w)
+    if w.size > 120000:
+        w = w[rng.permutation(w.size)[:120000]]
+    got = db.lookup_words(w)
+    want = orc.lookup_many(w)
+    assert np.array_equal(got, want)
+    assert (got != 0xFFFFFFFF).sum() > 0
+
+
+def test_pack_matches_oracle_words(gpu):
+    """2-bit pack + RC: every looked-up word of the oracle's slide appears, in order."""
+    ctr, db, orc = gpu["toyA"]
+    recs = read_fasta(gold("edge_reads.fa")) + read_fasta(gold("toyA_reads.fa"))[:60] + read_fasta(gold("toyB_reads.fa"))[:20]
+    for name, seq in recs:
+        if not seq:
+            continue
+        fwd, rc, valid = db.pack_sequence(seq)
+        _, owords = orc.slide(seq, do_rc=False, want_words=True)
+        assert np.array_equal(fwd[valid == 1], owords), name
+        _, owords_rc = orc.slide(seq, do_rc=True, want_words=True)
+        # oracle order: forward windows, then windows of the RC text = rc words in reverse order
+        assert np.array_equal(np.concatenate([fwd[valid == 1], rc[valid == 1][::-1]]), owords_rc), name
+
+
+def test_vote_matches_oracle(gpu):
+    """Vote on real hit lists, on permuted hit lists and on synthetic multisets."""
+    ctr, db, orc = gpu["toyA"]
+    rng = np.random.default_rng(9)
+    lists = []
+    for name, seq in read_fasta(gold("toyA_reads.fa"))[:300] + read_fasta(gold("long_reads.fa")):
+        h, _ = orc.slide(seq, do_rc=True)
+        lists.append(h)
+        if h.size > 2:
+            lists.append(rng.permutation(h))
+    for k in range(300):      # random multisets over many labels (forces the block path too)
+        nl = int(rng.integers(1, min(ctr.max_ix, 90)))
+        labs = rng.choice(ctr.max_ix, nl, replace=False)
+        cnt = rng.integers(1, 40, nl)
+        h = np.repeat(labs, cnt).astype(np.uint32)
+        lists.append(rng.permutation(h))
+    lists.append(np.zeros(0, dtype=np.uint32))
+    off = np.zeros(len(lists) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([l.size for l in lists])
+    # sprinkle misses between the hits: they must be ignored
+    res = db.vote_hits(np.concatenate(lists), off)
+    for i, h in enumerate(lists):
+        v = orc.vote(h)
+        r = res[i]
+        assert r["kind"] == v.kind, i
+        if v.kind == 0:
+            continue
+        assert (r["label"], r["found"], r["uix"]) == (v.label, v.found, v.uix), i
+        if v.kind == 2:
+            assert (r["cut"], r["sl"], r["ol"]) == (v.cut, v.sl, v.ol), i
+
+
+@pytest.mark.parametrize("db_name,reads,out,rc", CASES)
+def test_search_file_matches_reference(gpu, tmp_path, db_name, reads, out, rc):
+    from utree_b200 import capi
+    ctr = gpu[db_name][0]
+    s = capi.Searcher(ctr, devices=(0,), host_threads=2)
+    try:
+        o = str(tmp_path / "out.txt")
+        code, ref_exit, st = s.search_file(gold(reads), o, do_rc=bool(rc))
+        assert code == 0 and ref_exit == 0
+        assert open(o, "rb").read() == open(gold(out), "rb").read()
+        assert st["kernel_launches"] >= 3
+        data = open(gold(reads), "rb").read()
+        code, ref_exit, text, st2 = s.search_mem(data, do_rc=bool(rc))
+        assert code == 0 and text == open(gold(out), "rb").read()
+        assert st2["lookups"] == st["lookups"] and st2["good_finds"] == st["good_finds"]
+    finally:
+        s.destroy()
+
+
+def test_search_counts_match_oracle(gpu, tmp_path):
+    from utree_b200 import capi
+    ctr, db, orc = gpu["toyA"]
+    s = capi.Searcher(ctr, devices=(0,), host_threads=1)
+    try:
+        o = str(tmp_path / "o.txt")
+        _, _, st = s.search_file(gold("toyA_reads.fa"), o, do_rc=True)
+        _, ost, _ = orc.search_file(gold("toyA_reads.fa"), str(tmp_path / "o2.txt"), do_rc=True)
+        assert st["lookups"] == ost["lookups"] and st["hits"] == ost["hits"]
+        assert st["good_finds"] == ost["good_finds"] and st["reads"] == ost["reads"]
+    finally:
+        s.destroy()
+
+
+def test_virtual_devices_same_output(gpu, tmp_path):
+    """Shard logic: N device slots mapped onto one GPU give the identical ordered output."""
+    from utree_b200 import capi
+    ctr = gpu["toyA"][0]
+    want = open(gold("toyA_rc.out"), "rb").read()
+    os.environ["UTB_BATCH_MB"] = "33"      # small batches -> several per device
+    try:
+        for devs in ((0, 0), (0, 0, 0, 0)):
+            s = capi.Searcher(ctr, devices=devs, host_threads=2)
+            try:
+                code, _, text, st = s.search_mem(open(gold("toyA_reads.fa"), "rb").read() * 1, do_rc=True)
+                assert code == 0 and text == want
+            finally:
+                s.destroy()
+    finally:
+        del os.environ["UTB_BATCH_MB"]
+
+
+@pytest.mark.parametrize("bad", BAD_CASES)
+def test_malformed_fasta_exit_codes(gpu, tmp_path, meta, bad):
+    from utree_b200 import capi
+    ctr = gpu["toyA"][0]
+    s = capi.Searcher(ctr, devices=(0,), host_threads=1)
+    try:
+        o = str(tmp_path / "o.txt")
+        code, ref_exit, st = s.search_file(gold(bad), o, do_rc=True)
+        assert code == 3 and ref_exit == meta[bad]["exit"] == 2
+        assert open(o, "rb").read() == open(gold(bad + ".out"), "rb").read()
+    finally:
+        s.destroy()
+
+
+@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[8]])
+def test_cli_binary_matches_reference(ctrs, tmp_path, db_name, reads, out, rc):
+    exe = os.path.join(ROOT, "bin", "utree-search_gg")
+    o = str(tmp_path / "cli.out")
+    args = [exe, ctrs[db_name], gold(reads), o, "2"] + (["RC"] if rc else [])
+    p = subprocess.run(args, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert open(o, "rb").read() == open(gold(out), "rb").read()
+    lines = p.stdout.splitlines()
+    assert lines[0] == "This is UTree [v2.0RF SigNature Edition]"
+    assert lines[-1].startswith("Searched ") and lines[-2].startswith("Good finds: ")
+    n_out = sum(1 for _ in open(gold(out), "rb"))
+    assert lines[-2] == f"Good finds: {n_out}"

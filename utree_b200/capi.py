@@ -1,0 +1,352 @@
+"""ctypes mirror of include/utree_b200.h (the product's C ABI) plus a mirror of
+oracle/oracle.h for the checker.  No compute happens in Python: every call
+below lands in libutree_b200.so, and a missing library or a missing GPU is a
+hard error -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "csrc", "libutree_b200.so")
+ORACLE_PATH = os.path.join(ROOT, "oracle", "liboracle.so")
+
+UTB_NONE, UTB_STAR, UTB_WALK = 0, 1, 2
+CUT_EMPTY, CUT_FULL = 0xFFFFFFFF, 0xFFFFFFFE
+BAD32 = 0xFFFFFFFF
+
+
+class UtbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"utb error {code}: {msg}")
+        self.code = code
+
+
+class Result(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("kind", "label", "cut", "found", "uix", "sl", "ol", "_pad")]
+
+
+RESULT_DTYPE = np.dtype([(n, "<u4") for n in ("kind", "label", "cut", "found", "uix", "sl", "ol", "_pad")])
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("reads", "good_finds", "lookups", "hits", "batches",
+                                          "kernel_launches", "h2d_bytes", "d2h_bytes", "out_bytes")] + \
+               [("seconds_total", C.c_double), ("seconds_device", C.c_double)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# every symbol include/utree_b200.h declares (tests check the .so exports all)
+EXPORTS = [
+    "utb_last_error", "utb_ctr_open", "utb_ctr_close", "utb_ctr_num_nodes", "utb_ctr_ix_bytes",
+    "utb_ctr_binix_bytes", "utb_ctr_max_ix", "utb_ctr_last_bin", "utb_ctr_label", "utb_ctr_label_rank",
+    "utb_device_count", "utb_db_upload", "utb_db_free", "utb_db_hbm_bytes",
+    "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
+    "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
+    "utb_batch_submit", "utb_batch_wait", "utb_batch_rerun_device", "utb_batch_counts",
+    "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits",
+    "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
+    "utb_main", "utb_measure_rand32",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise UtbError(-1, f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                               "there is no fallback implementation")
+        L = C.CDLL(LIB_PATH)
+        L.utb_last_error.restype = C.c_char_p
+        L.utb_ctr_num_nodes.restype = C.c_uint64
+        L.utb_ctr_last_bin.restype = C.c_uint64
+        L.utb_ctr_label.restype = C.c_char_p
+        L.utb_ctr_label.argtypes = [C.c_void_p, C.c_uint32]
+        L.utb_ctr_label_rank.argtypes = [C.c_void_p, C.c_uint32]
+        L.utb_ctr_label_rank.restype = C.c_uint32
+        for f in ("utb_ctr_num_nodes", "utb_ctr_ix_bytes", "utb_ctr_binix_bytes", "utb_ctr_max_ix", "utb_ctr_last_bin",
+                  "utb_ctr_close", "utb_db_free", "utb_db_hbm_bytes", "utb_batch_destroy", "utb_searcher_destroy",
+                  "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len", "utb_batch_max_bytes",
+                  "utb_batch_max_reads", "utb_batch_max_slots", "utb_free"):
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("utb_ctr_close", "utb_db_free", "utb_batch_destroy", "utb_searcher_destroy", "utb_free"):
+            getattr(L, f).restype = None
+        for f in ("utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len"):
+            getattr(L, f).restype = C.c_void_p
+        for f in ("utb_db_hbm_bytes", "utb_batch_max_slots", "utb_read_slots"):
+            getattr(L, f).restype = C.c_uint64
+        for f in ("utb_batch_max_bytes", "utb_batch_max_reads"):
+            getattr(L, f).restype = C.c_size_t
+        L.utb_read_slots.argtypes = [C.c_uint32]
+        L.utb_ctr_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        L.utb_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.utb_db_upload.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.utb_batch_create.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.utb_batch_submit.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int]
+        L.utb_batch_wait.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.utb_batch_rerun_device.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        L.utb_batch_counts.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.utb_lookup_words.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.utb_pack_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.utb_vote_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.utb_searcher_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.utb_search_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(Stats), C.POINTER(C.c_int)]
+        L.utb_search_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p),
+                                     C.POINTER(C.c_size_t), C.POINTER(Stats), C.POINTER(C.c_int)]
+        L.utb_main.argtypes = [C.c_int, C.POINTER(C.c_char_p)]
+        L.utb_measure_rand32.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+        _lib = L
+    return _lib
+
+
+def _ck(rc):
+    if rc:
+        raise UtbError(rc, lib().utb_last_error().decode(errors="replace"))
+
+
+class Ctr:
+    """Host view of a CTR file (utb_ctr_open)."""
+
+    def __init__(self, path):
+        self.h = C.c_void_p()
+        _ck(lib().utb_ctr_open(os.fsencode(path), C.byref(self.h)))
+        L = lib()
+        self.num_nodes = L.utb_ctr_num_nodes(self.h)
+        self.ix_bytes = L.utb_ctr_ix_bytes(self.h)
+        self.binix_bytes = L.utb_ctr_binix_bytes(self.h)
+        self.max_ix = L.utb_ctr_max_ix(self.h)
+        self.last_bin = L.utb_ctr_last_bin(self.h)
+
+    def label(self, ix):
+        return lib().utb_ctr_label(self.h, ix)
+
+    def rank(self, ix):
+        return lib().utb_ctr_label_rank(self.h, ix)
+
+    def close(self):
+        if self.h:
+            lib().utb_ctr_close(self.h)
+            self.h = C.c_void_p()
+
+
+def device_count():
+    n = C.c_int()
+    _ck(lib().utb_device_count(C.byref(n)))
+    return n.value
+
+
+class Db:
+    """CTR resident in one GPU's HBM (utb_db_upload) + stage-level calls."""
+
+    def __init__(self, ctr: Ctr, device=0):
+        self.ctr = ctr
+        self.h = C.c_void_p()
+        _ck(lib().utb_db_upload(ctr.h, device, C.byref(self.h)))
+
+    def lookup_words(self, words):
+        words = np.ascontiguousarray(words, dtype=np.uint64)
+        out = np.empty(words.size, dtype=np.uint32)
+        _ck(lib().utb_lookup_words(self.h, words.ctypes.data, words.size, out.ctypes.data))
+        return out
+
+    def pack_sequence(self, seq: bytes):
+        n = len(seq)
+        fwd = np.zeros(n, dtype=np.uint64)
+        rc = np.zeros(n, dtype=np.uint64)
+        valid = np.zeros(n, dtype=np.uint8)
+        _ck(lib().utb_pack_sequence(self.h, seq, n, fwd.ctypes.data, rc.ctypes.data, valid.ctypes.data))
+        return fwd, rc, valid
+
+    def vote_hits(self, hits, off):
+        hits = np.ascontiguousarray(hits, dtype=np.uint32)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        n = off.size - 1
+        res = np.zeros(n, dtype=RESULT_DTYPE)
+        _ck(lib().utb_vote_hits(self.h, hits.ctypes.data, off.ctypes.data, n, res.ctypes.data))
+        return res
+
+    def hbm_bytes(self):
+        return lib().utb_db_hbm_bytes(self.h)
+
+    def free(self):
+        if self.h:
+            lib().utb_db_free(self.h)
+            self.h = C.c_void_p()
+
+
+class Batch:
+    """One stream slot (utb_batch_*): pinned staging + device buffers."""
+
+    def __init__(self, db: Db, max_bytes, max_reads):
+        self.db = db
+        self.h = C.c_void_p()
+        _ck(lib().utb_batch_create(db.h, max_bytes, max_reads, C.byref(self.h)))
+        L = lib()
+        self.max_bytes, self.max_reads = max_bytes, max_reads
+        self.bytes = np.ctypeslib.as_array(C.cast(L.utb_batch_bytes(self.h), C.POINTER(C.c_uint8)), (max_bytes,))
+        self.seq_off = np.ctypeslib.as_array(C.cast(L.utb_batch_seq_off(self.h), C.POINTER(C.c_uint64)), (max_reads,))
+        self.seq_len = np.ctypeslib.as_array(C.cast(L.utb_batch_seq_len(self.h), C.POINTER(C.c_uint32)), (max_reads,))
+        self.n_reads = 0
+
+    def submit(self, n_bytes, n_reads, do_rc):
+        self.n_reads = n_reads
+        _ck(lib().utb_batch_submit(self.h, n_bytes, n_reads, int(do_rc)))
+
+    def wait(self):
+        p = C.c_void_p()
+        _ck(lib().utb_batch_wait(self.h, C.byref(p)))
+        if not self.n_reads:
+            return np.zeros(0, dtype=RESULT_DTYPE)
+        buf = (C.c_uint8 * (self.n_reads * RESULT_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, dtype=RESULT_DTYPE).copy()
+
+    def rerun_device(self, iters=1):
+        ms = (C.c_float * 4)()
+        launches = C.c_uint64()
+        _ck(lib().utb_batch_rerun_device(self.h, iters, ms, C.byref(launches)))
+        return [ms[i] for i in range(4)], launches.value
+
+    def counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        _ck(lib().utb_batch_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def destroy(self):
+        if self.h:
+            lib().utb_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Searcher:
+    """Whole search over one or more GPUs (utb_searcher_* / utb_search_*)."""
+
+    def __init__(self, ctr: Ctr, devices=(0,), host_threads=1):
+        self.ctr = ctr
+        self.h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        _ck(lib().utb_searcher_create(ctr.h, arr, len(devices), host_threads, C.byref(self.h)))
+
+    def search_file(self, fasta, out, do_rc=True):
+        st, ex = Stats(), C.c_int()
+        rc = lib().utb_search_file(self.h, os.fsencode(fasta), os.fsencode(out), int(do_rc), C.byref(st), C.byref(ex))
+        return rc, ex.value, st.as_dict()
+
+    def search_mem(self, fasta: bytes, do_rc=True, ptr=None, n=None):
+        st, ex = Stats(), C.c_int()
+        out, out_len = C.c_void_p(), C.c_size_t()
+        if ptr is None:
+            keep = C.create_string_buffer(fasta, len(fasta))
+            ptr, n = C.addressof(keep), len(fasta)
+        rc = lib().utb_search_mem(self.h, ptr, n, int(do_rc), C.byref(out), C.byref(out_len), C.byref(st), C.byref(ex))
+        data = C.string_at(out.value, out_len.value) if out.value else b""
+        if out.value:
+            lib().utb_free(out)
+        return rc, ex.value, data, st.as_dict()
+
+    def destroy(self):
+        if self.h:
+            lib().utb_searcher_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def measure_rand32(device=0, ws_bytes=8 << 30, loads=1 << 28, iters=3):
+    g = C.c_double()
+    _ck(lib().utb_measure_rand32(device, ws_bytes, loads, iters, C.byref(g)))
+    return g.value
+
+
+# ---------------------------------------------------------------------------
+# oracle mirror (checker only -- used by tests/, smoke() and bench's cpu legs)
+# ---------------------------------------------------------------------------
+class OrcStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("reads", "good_finds", "lookups", "hits", "probes",
+                                          "sect_idx", "sect_bkt", "out_bytes")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class OrcVote(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("kind", "label", "cut", "found", "uix", "sl", "ol")]
+
+
+_orc = None
+
+
+def oracle():
+    global _orc
+    if _orc is None:
+        O = C.CDLL(ORACLE_PATH)
+        O.orc_db_load.restype = C.c_void_p
+        O.orc_db_load.argtypes = [C.c_char_p, C.c_char_p, C.c_size_t]
+        O.orc_db_free.argtypes = [C.c_void_p]
+        O.orc_db_num_nodes.restype = C.c_uint64
+        for f in ("orc_db_num_nodes", "orc_db_max_ix", "orc_db_ix_bytes", "orc_db_binix_bytes"):
+            getattr(O, f).argtypes = [C.c_void_p]
+        O.orc_db_label.restype = C.c_char_p
+        O.orc_db_label.argtypes = [C.c_void_p, C.c_uint32]
+        O.orc_lookup.restype = C.c_uint32
+        O.orc_lookup.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(OrcStats)]
+        O.orc_slide.restype = C.c_uint64
+        O.orc_slide.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64,
+                                C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(OrcStats)]
+        O.orc_vote.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(OrcVote)]
+        O.orc_search_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_uint64,
+                                      C.POINTER(OrcStats), C.c_char_p, C.c_size_t]
+        O.orc_revcomp_word.restype = C.c_uint64
+        O.orc_revcomp_word.argtypes = [C.c_uint64]
+        _orc = O
+    return _orc
+
+
+class OracleDb:
+    def __init__(self, path):
+        err = C.create_string_buffer(256)
+        self.h = oracle().orc_db_load(os.fsencode(path), err, 256)
+        if not self.h:
+            raise RuntimeError("oracle: " + err.value.decode())
+        self.max_ix = oracle().orc_db_max_ix(self.h)
+
+    def lookup(self, word):
+        return oracle().orc_lookup(self.h, int(word), None)
+
+    def lookup_many(self, words):
+        return np.array([oracle().orc_lookup(self.h, int(w), None) for w in words], dtype=np.uint32)
+
+    def label(self, ix):
+        return oracle().orc_db_label(self.h, ix)
+
+    def slide(self, seq: bytes, do_rc=True, want_words=False):
+        cap = 2 * len(seq) + 2
+        hits = np.empty(cap, dtype=np.uint32)
+        words = np.empty(cap if want_words else 1, dtype=np.uint64)
+        nw = C.c_uint64()
+        nf = oracle().orc_slide(self.h, seq, len(seq), int(do_rc), hits.ctypes.data, cap,
+                                words.ctypes.data if want_words else None, cap if want_words else 0,
+                                C.byref(nw), None)
+        return hits[:nf].copy(), (words[:nw.value].copy() if want_words else None)
+
+    def vote(self, hits):
+        hits = np.ascontiguousarray(hits, dtype=np.uint32)
+        v = OrcVote()
+        oracle().orc_vote(self.h, hits.ctypes.data, hits.size, C.byref(v))
+        return v
+
+    def search_file(self, fasta, out, do_rc=True, threads=1, max_reads=0):
+        st = OrcStats()
+        err = C.create_string_buffer(256)
+        rc = oracle().orc_search_file(self.h, os.fsencode(fasta), os.fsencode(out), int(do_rc), threads,
+                                      max_reads, C.byref(st), err, 256)
+        return rc, st.as_dict(), err.value.decode()
+
+    def free(self):
+        if self.h:
+            oracle().orc_db_free(self.h)
+            self.h = None

@@ -1,0 +1,978 @@
+// kernels.cu -- sm_100a device side of the SEARCH_GG hot path + the thin C ABI
+// over it (utb_db_*, utb_batch_*, stage-level entry points).
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   binix   : the CTR prefix index exactly as on disk, (2^24+1) x 4 B
+//             (8 B when numNodes >= 2^32-1)                  itree.c:756-759
+//   recs    : the CTR record blob exactly as on disk, numNodes x SZ bytes,
+//             SZ = 5-byte suffix + IXTYPE id, + 32 B slack   itree.c:766
+//   labels  : blob of NUL-terminated strings, off[], rank[], by_rank[]
+// Per batch (one stream slot):
+//   raw     : the FASTA bytes as read from the file (headers included)
+//   seq_off/seq_len/grp_off : where each read's sequence line sits, and the
+//             first 32-base group it owns in the packed "super-sequence"
+//   pk/bad  : 2-bit codes (u64 per 32 bases, first base most significant, the
+//             k-mer word order of itree.c:924) and a bad-base bit mask.  Every
+//             read is padded to a multiple of 32 positions with >= 1 bad
+//             position, so a 32-mer window can never straddle two reads.
+//   hits    : one u32 per (position, strand): label id, MISS or NOWIN
+//   results : one utb_result per read
+//
+// Kernels: pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926),
+// lookup_kernel (XT_getIX32 + xtSuffixBS with the reference's exact probe
+// sequence, itree.c:699-730), vote_warp_kernel / vote_block_kernel (full
+// aufbau vote, itree.c:1028-1098).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "utb_internal.h"
+
+#define SUFMASK 0xFFFFFFFFFFull
+#define HIT_MISS 0xFFFFFFFFu   // looked up, not found (BAD_IX widened)
+#define HIT_NOWIN 0xFFFFFFFEu  // no valid 32-mer window here: no lookup made
+
+#define CK(call)                                                                 \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) {                                                 \
+            utb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_),   \
+                          __FILE__, __LINE__, cudaGetErrorString(e_));           \
+            return UTB_ERR_CUDA;                                                 \
+        }                                                                        \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// device-side database view (passed by value to kernels)
+// ---------------------------------------------------------------------------
+struct DevDB {
+    const uint32_t *binix32;   // one of binix32 / binix64 is non-null
+    const uint64_t *binix64;
+    const uint8_t *recs;
+    uint64_t num_nodes;
+    uint32_t sz;               // 7 or 9
+    uint32_t ix_bytes;         // 2 or 4
+    uint32_t max_ix;
+    const char *blob;
+    const uint32_t *off;
+    const uint32_t *rank;
+    const uint32_t *by_rank;
+};
+
+struct utb_db {
+    int device;
+    DevDB d;
+    void *binix, *recs, *blob, *off, *rank, *by_rank;
+    uint64_t hbm_bytes;
+    int l2_window;             // persisting-L2 window over binix configured
+    size_t l2_window_bytes;
+};
+
+// ---------------------------------------------------------------------------
+// pack: raw bytes -> 2-bit groups + bad mask
+// ---------------------------------------------------------------------------
+// One thread per 32-base group.  The 32 bytes are fetched with nine aligned
+// 32-bit loads (neighbouring threads share cache lines, so the raw bytes move
+// once from L2), classified four at a time with byte-SIMD compares.
+__device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &badbits) {
+    uint32_t u = w | 0x20202020u;                      // fold case (itree.c:114-117)
+    uint32_t isA = __vcmpeq4(u, 0x61616161u), isC = __vcmpeq4(u, 0x63636363u);
+    uint32_t isG = __vcmpeq4(u, 0x67676767u), isT = __vcmpeq4(u, 0x74747474u);
+    uint32_t code = (isC & 0x01010101u) | (isG & 0x02020202u) | (isT & 0x03030303u);
+    uint32_t inval = ~(isA | isC | isG | isT) & 0x01010101u;
+    badbits = (inval * 0x01020408u) >> 24;             // bit j = byte j is not ACGTacgt
+    // first base most significant
+    return ((code & 3u) << 6) | (((code >> 8) & 3u) << 4) | (((code >> 16) & 3u) << 2) | ((code >> 24) & 3u);
+}
+
+__global__ void __launch_bounds__(256)
+pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_off,
+            const uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ grp_off,
+            uint32_t n_reads, uint32_t n_groups,
+            uint64_t *__restrict__ pk, uint32_t *__restrict__ bad) {
+    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_groups) return;
+    if (g == n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; return; }   // guard group
+    // read owning group g: largest r with grp_off[r] <= g
+    uint32_t lo = 0, hi = n_reads;                     // invariant: grp_off[lo] <= g < grp_off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(grp_off + mid) <= g) lo = mid; else hi = mid;
+    }
+    uint32_t k = g - __ldg(grp_off + lo);
+    uint32_t len = __ldg(seq_len + lo);
+    uint32_t b0 = k * 32u;
+    uint32_t nv = len > b0 ? min(32u, len - b0) : 0u;  // real bases in this group
+    uint64_t word = 0;
+    uint32_t badm = 0;
+    if (nv) {
+        uint64_t a = __ldg(seq_off + lo) + b0;
+        const uint32_t *p = reinterpret_cast<const uint32_t *>(raw + (a & ~3ull));
+        uint32_t sh = (uint32_t)(a & 3u) * 8u;
+        uint32_t nw = (nv + 3u) >> 2;                  // 4-byte words that hold real bases
+        uint32_t prev = __ldg(p);
+#pragma unroll
+        for (uint32_t j = 0; j < 8; ++j) {
+            uint32_t cur = (j < nw) ? __ldg(p + j + 1) : 0u;   // p[j+1] only if word j is needed
+            uint32_t w = __funnelshift_r(prev, cur, sh);
+            prev = cur;
+            uint32_t bb;
+            uint32_t c = classify4(w, bb);
+            word = (word << 8) | c;
+            badm |= bb << (4u * j);
+        }
+    }
+    if (nv < 32u) badm |= 0xFFFFFFFFu << nv;           // padding positions are bad
+    pk[g] = word;
+    bad[g] = badm;
+}
+
+// ---------------------------------------------------------------------------
+// window extraction (shared by lookup and the stage-level test kernel)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool window_at(const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
+                                          uint32_t pos, uint64_t &w) {
+    uint32_t g = pos >> 5, o = pos & 31u;
+    uint64_t hi = __ldg(pk + g), lo = __ldg(pk + g + 1);
+    uint32_t bh = __ldg(bad + g), bl = __ldg(bad + g + 1);
+    uint32_t wb = o ? ((bh >> o) | (bl << (32u - o))) : bh;
+    w = o ? ((hi << (2u * o)) | (lo >> (64u - 2u * o))) : hi;
+    return wb == 0;
+}
+
+// reverse complement of a 32-mer word: reverse the 2-bit fields of ~w
+__device__ __forceinline__ uint64_t revcomp_word(uint64_t w) {
+    uint64_t x = __brevll(~w);
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+
+// ---------------------------------------------------------------------------
+// lookup: XT_getIX32 + xtSuffixBS, the reference's probe sequence verbatim
+// ---------------------------------------------------------------------------
+// Records are byte-packed (SZ = 7 or 9) so a suffix starts at any byte; its 5
+// bytes always fall inside two consecutive aligned 32-bit words, which are the
+// only bytes fetched (no sector is touched that the reference would not touch).
+__device__ __forceinline__ uint64_t load_suffix(const uint8_t *__restrict__ recs, uint64_t byte_addr) {
+    const uint32_t *p = reinterpret_cast<const uint32_t *>(recs + (byte_addr & ~3ull));
+    uint32_t w0 = __ldg(p), w1 = __ldg(p + 1);
+    uint32_t sh = (uint32_t)(byte_addr & 3u) * 8u;
+    uint64_t v = ((uint64_t)w1 << 32) | w0;
+    return (v >> sh) & SUFMASK;
+}
+
+__device__ __forceinline__ uint32_t load_ix(const DevDB &db, uint64_t rec) {
+    const uint8_t *r = db.recs + rec * db.sz + 5;
+    uint32_t v = (uint32_t)__ldg(r) | ((uint32_t)__ldg(r + 1) << 8);
+    if (db.ix_bytes == 4) v |= ((uint32_t)__ldg(r + 2) << 16) | ((uint32_t)__ldg(r + 3) << 24);
+    return v;
+}
+
+struct Probe {            // state of one in-flight xtSuffixBS
+    uint64_t pos, size, suf;
+    bool live;            // bucket non-empty
+};
+
+__device__ __forceinline__ void probe_begin(const DevDB &db, uint64_t word, Probe &q) {
+    uint64_t p = word >> 40;
+    uint64_t a, b;
+    if (db.binix32) { a = __ldg(db.binix32 + p); b = __ldg(db.binix32 + p + 1); }
+    else { a = __ldg(db.binix64 + p); b = __ldg(db.binix64 + p + 1); }
+    q.suf = word & SUFMASK;
+    q.live = a < b;                                    // itree.c:726
+    // a CTR whose index points past the blob would make the reference read
+    // out of bounds; clamp so the device never does
+    if (b > db.num_nodes) q.live = false;
+    q.pos = a;
+    q.size = q.live ? b - a - 1 : 0;                   // itree.c:728
+}
+
+template <int N>
+__device__ __forceinline__ void probe_run(const DevDB &db, Probe (&q)[N]) {
+    // Lock-step binary searches: every round issues the N independent loads
+    // first, then resolves the N compares (itree.c:701-705).
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) any |= q[i].size != 0;
+        if (!any) break;
+        uint64_t v[N], h[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            h[i] = q[i].size >> 1;
+            v[i] = q[i].size ? load_suffix(db.recs, (q[i].pos + h[i] + 1) * db.sz) : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (q[i].size) {
+                if (v[i] <= q[i].suf) { q[i].pos += h[i] + 1; q[i].size -= h[i] + 1; }
+                else q[i].size = h[i];
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t probe_end(const DevDB &db, const Probe &q) {
+    if (!q.live) return HIT_MISS;
+    if (load_suffix(db.recs, q.pos * db.sz) != q.suf) return HIT_MISS;   // itree.c:706
+    uint32_t ix = load_ix(db, q.pos);
+    return ix < db.max_ix ? ix : HIT_MISS;                                // itree.c:929
+}
+
+// One thread per position of the packed super-sequence; forward and reverse
+// complement lookups of that window run in lock-step (two independent
+// dependent-load chains per thread).
+template <int NSTR>
+__global__ void __launch_bounds__(256)
+lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
+              uint32_t n_pos, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t w = 0;
+    bool valid = pos < n_pos && window_at(pk, bad, pos, w);
+    uint32_t r[NSTR];
+#pragma unroll
+    for (int s = 0; s < NSTR; ++s) r[s] = HIT_NOWIN;
+    if (valid) {
+        Probe q[NSTR];
+        probe_begin(db, w, q[0]);
+        if (NSTR == 2) probe_begin(db, revcomp_word(w), q[NSTR - 1]);
+        probe_run<NSTR>(db, q);
+#pragma unroll
+        for (int s = 0; s < NSTR; ++s) r[s] = probe_end(db, q[s]);
+    }
+    if (pos < n_pos) {
+        if (NSTR == 2) reinterpret_cast<uint2 *>(hits)[pos] = make_uint2(r[0], r[1]);
+        else hits[pos] = r[0];
+    }
+    int nh = 0;
+#pragma unroll
+    for (int s = 0; s < NSTR; ++s) nh += r[s] < HIT_NOWIN;
+    int nvalid = __syncthreads_count(valid);
+    int nhit1 = __syncthreads_count(nh >= 1);
+    int nhit2 = __syncthreads_count(nh >= 2);
+    if (threadIdx.x == 0) {
+        if (nvalid) atomicAdd(counters + 0, (unsigned long long)nvalid * NSTR);
+        if (nhit1 + nhit2) atomicAdd(counters + 1, (unsigned long long)(nhit1 + nhit2));
+    }
+}
+
+// stage-level: words[] -> ix[] (utb_lookup_words)
+__global__ void lookup_words_kernel(DevDB db, const uint64_t *__restrict__ words, uint64_t n, uint32_t *__restrict__ ix) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Probe q[1];
+    probe_begin(db, words[i], q[0]);
+    probe_run<1>(db, q);
+    ix[i] = probe_end(db, q[0]);
+}
+
+// stage-level: expose every window of the packed stream (utb_pack_sequence)
+__global__ void expand_windows_kernel(const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
+                                      uint64_t *__restrict__ fwd, uint64_t *__restrict__ rc, uint8_t *__restrict__ valid) {
+    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= n_pos) return;
+    uint64_t w;
+    bool ok = window_at(pk, bad, pos, w);
+    fwd[pos] = ok ? w : 0;
+    rc[pos] = ok ? revcomp_word(w) : 0;
+    valid[pos] = ok;
+}
+
+// ---------------------------------------------------------------------------
+// vote (itree.c:1028-1098)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cutoff_of(uint32_t x) {   // itree.c:1044-1046
+    uint32_t c = x - x / 4u;
+    c += ((x >> 1) >= c);
+    return c;
+}
+
+// The aufbau walk, executed by one converged warp; every lane carries the same
+// scalar state, the character scans are done 32 bytes at a time with ballots.
+// T_lab/T_cnt: the distinct labels of the read in strcmp order with counts
+// (shared or global memory).
+__device__ void walk_warp(const DevDB &db, const uint32_t *T_lab, const uint32_t *T_cnt,
+                          uint32_t uix, uint32_t n, utb_result *out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t EMPTY = 0xFFFFFFFFu;
+    uint32_t cutoff = cutoff_of(n), st = 0, ed = uix, dv = EMPTY, orun = n, sl = 0, ol = 0;
+    for (;;) {                                                      // itree.c:1047
+        uint32_t run = T_cnt[st], td = dv;
+        for (uint32_t z = st + 1; z < ed; ++z) {                    // itree.c:1050
+            const char *s1 = db.blob + __ldg(db.off + T_lab[z - 1]);
+            const char *s2 = db.blob + __ldg(db.off + T_lab[z]);
+            if (!s1[dv + (dv == EMPTY)]) {                          // itree.c:1052
+                run = T_cnt[z]; st = z;
+                orun -= T_cnt[z - 1];
+                cutoff = cutoff_of(orun);
+                continue;
+            }
+            // itree.c:1060-1061: first td >= dv+1 with s1[td]==0 || s1[td]!=s2[td] || s1[td]==';'
+            uint32_t t0 = dv + 1u;
+            char a, b;
+            for (;;) {
+                char ca = s1[t0 + lane], cb = s2[t0 + lane];
+                uint32_t m = __ballot_sync(0xFFFFFFFFu, ca == 0 || ca != cb || ca == ';');
+                if (m) {
+                    int src = __ffs(m) - 1;
+                    td = t0 + (uint32_t)src;
+                    a = (char)__shfl_sync(0xFFFFFFFFu, (int)ca, src);
+                    b = (char)__shfl_sync(0xFFFFFFFFu, (int)cb, src);
+                    break;
+                }
+                t0 += 32u;
+            }
+            if (a == b) run += T_cnt[z];                            // itree.c:1062
+            else if ((!a && b == ';') ||
+                     ((a == ';' || !a) && td > 0 && s1[td - 1] == '_')) {   // itree.c:1063
+                run = T_cnt[z]; st = z;
+                orun -= T_cnt[z - 1];
+                cutoff = cutoff_of(orun);
+            }
+            else if (run >= cutoff) { ed = z; break; }              // itree.c:1068
+            else { run = T_cnt[z]; st = z; }                        // itree.c:1069
+        }
+        sl = run; ol = orun;                                        // itree.c:1071
+        if (run < cutoff) break;                                    // itree.c:1072
+        if (st + 1 >= ed) {                                         // itree.c:1073-1080
+            if (T_cnt[ed - 1] >= cutoff) dv = 0xFFFFFFFEu;
+            break;
+        }
+        orun = run; dv = td; cutoff = cutoff_of(run);               // itree.c:1082-1085
+    }
+    if (lane == 0) {
+        out->kind = UTB_WALK; out->label = T_lab[ed - 1]; out->cut = dv;
+        out->found = n; out->uix = uix; out->sl = sl; out->ol = ol; out->_pad = 0;
+    }
+}
+
+struct VoteIn {            // where a read's hit slots live
+    const uint32_t *hits;
+    const uint32_t *grp_off;   // batch mode: position space
+    const uint32_t *seq_len;
+    const uint64_t *off;       // stage-level mode: explicit ranges (overrides batch mode)
+    uint32_t nstr;
+};
+__device__ __forceinline__ void vote_range(const VoteIn &in, uint32_t r, uint64_t &start, uint64_t &count) {
+    if (in.off) { start = in.off[r]; count = in.off[r + 1] - start; return; }
+    uint32_t len = __ldg(in.seq_len + r);
+    uint64_t nwin = len >= 32u ? len - 31u : 0u;
+    start = (uint64_t)__ldg(in.grp_off + r) * 32u * in.nstr;
+    count = nwin * in.nstr;
+}
+
+#define VW_SLOTS 64u            // distinct labels a warp can hold in shared memory
+#define VW_MAXHITS 16384u       // hit slots a single warp will scan
+#define VW_WARPS 8
+
+// Warp per read: hits -> (label,count) multiset in a shared-memory hash table
+// (warp-aggregated with match_any), sorted by label rank, then the walk.
+// Reads that are too long or have too many distinct labels are queued for
+// vote_block_kernel.
+__global__ void __launch_bounds__(VW_WARPS * 32)
+vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__ results,
+                 uint32_t *__restrict__ gen_list, uint32_t *__restrict__ gen_count,
+                 unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_key[VW_WARPS][VW_SLOTS], s_cnt[VW_WARPS][VW_SLOTS];
+    __shared__ uint32_t s_rk[VW_WARPS][VW_SLOTS], s_lab[VW_WARPS][VW_SLOTS], s_tc[VW_WARPS][VW_SLOTS];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * VW_WARPS + wib;
+    if (r >= n_reads) return;
+    uint64_t start, count;
+    vote_range(in, r, start, count);
+    utb_result *out = results + r;
+    if (count > VW_MAXHITS) {
+        if (lane == 0) gen_list[atomicAdd(gen_count, 1u)] = r;
+        return;
+    }
+    uint32_t *key = s_key[wib], *cnt = s_cnt[wib];
+    key[lane] = UTB_BAD32; key[lane + 32] = UTB_BAD32;
+    cnt[lane] = 0; cnt[lane + 32] = 0;
+    __syncwarp();
+    uint32_t n = 0;
+    bool overflow = false;
+    for (uint64_t base = 0; base < count; base += 32) {
+        uint64_t i = base + lane;
+        uint32_t h = i < count ? __ldg(in.hits + start + i) : HIT_NOWIN;
+        bool ok = h < db.max_ix;
+        n += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+        uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+        if (ok && (uint32_t)(__ffs(peers) - 1) == lane) {          // one lane per distinct label
+            uint32_t c = __popc(peers), slot = (h * 2654435761u) >> 26;   // 6 bits
+            for (uint32_t tries = 0;; ++tries) {
+                if (tries == VW_SLOTS) { overflow = true; break; }
+                uint32_t old = atomicCAS(&key[slot], UTB_BAD32, h);
+                if (old == UTB_BAD32 || old == h) { atomicAdd(&cnt[slot], c); break; }
+                slot = (slot + 1) & (VW_SLOTS - 1);
+            }
+        }
+        __syncwarp();
+    }
+    if (__any_sync(0xFFFFFFFFu, overflow)) {
+        if (lane == 0) gen_list[atomicAdd(gen_count, 1u)] = r;
+        return;
+    }
+    if (n == 0) {
+        if (lane == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        return;
+    }
+    uint32_t k0 = key[lane], k1 = key[lane + 32];
+    uint32_t m0 = __ballot_sync(0xFFFFFFFFu, k0 != UTB_BAD32), m1 = __ballot_sync(0xFFFFFFFFu, k1 != UTB_BAD32);
+    uint32_t uix = __popc(m0) + __popc(m1);
+    if (lane == 0) atomicAdd(counters + 2, 1ull);                  // good finds (itree.c:1029)
+    if (uix == 1) {                                                // itree.c:1031-1032, 1039-1040
+        uint32_t lab = m0 ? __shfl_sync(0xFFFFFFFFu, k0, __ffs(m0) - 1) : __shfl_sync(0xFFFFFFFFu, k1, __ffs(m1) - 1);
+        if (lane == 0) { out->kind = UTB_STAR; out->label = lab; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        return;
+    }
+    // sort the <= 64 entries by label rank (strcmp order, itree.c:1041)
+    uint32_t *rk = s_rk[wib], *T_lab = s_lab[wib], *T_cnt = s_tc[wib];
+    uint32_t r0 = k0 != UTB_BAD32 ? __ldg(db.rank + k0) : UTB_BAD32;
+    uint32_t r1 = k1 != UTB_BAD32 ? __ldg(db.rank + k1) : UTB_BAD32;
+    rk[lane] = r0; rk[lane + 32] = r1;
+    __syncwarp();
+    uint32_t p0 = 0, p1 = 0;
+    for (uint32_t j = 0; j < VW_SLOTS; ++j) { uint32_t x = rk[j]; p0 += x < r0; p1 += x < r1; }
+    if (k0 != UTB_BAD32) { T_lab[p0] = k0; T_cnt[p0] = cnt[lane]; }
+    if (k1 != UTB_BAD32) { T_lab[p1] = k1; T_cnt[p1] = cnt[lane + 32]; }
+    __syncwarp();
+    walk_warp(db, T_lab, T_cnt, uix, n, out);
+}
+
+// Block per read for long queries / label-rich reads: global-memory histogram
+// over label ids (block-private scratch, kept zeroed), compaction in rank
+// order, then the same walk.  Persistent over the queue filled by
+// vote_warp_kernel.
+#define VB_THREADS 256
+__global__ void __launch_bounds__(VB_THREADS)
+vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
+                  const uint32_t *__restrict__ gen_list, const uint32_t *__restrict__ gen_count,
+                  uint32_t *__restrict__ hist_all, uint32_t *__restrict__ tlab_all, uint32_t *__restrict__ tcnt_all,
+                  unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_warp[VB_THREADS / 32];
+    __shared__ uint32_t s_base, s_n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    uint32_t *hist = hist_all + (size_t)blockIdx.x * db.max_ix;
+    uint32_t *T_lab = tlab_all + (size_t)blockIdx.x * db.max_ix;
+    uint32_t *T_cnt = tcnt_all + (size_t)blockIdx.x * db.max_ix;
+    const uint32_t total = *gen_count;
+    for (uint32_t qi = blockIdx.x; qi < total; qi += gridDim.x) {
+        const uint32_t r = gen_list[qi];
+        uint64_t start, count;
+        vote_range(in, r, start, count);
+        // 1. histogram (warp-aggregated global atomics) + foundUniq
+        uint32_t n_local = 0;
+        for (uint64_t base = 0; base < count; base += VB_THREADS) {
+            uint64_t i = base + tid;
+            uint32_t h = i < count ? __ldg(in.hits + start + i) : HIT_NOWIN;
+            bool ok = h < db.max_ix;
+            uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+            if (ok && (uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(&hist[h], (uint32_t)__popc(peers));
+            n_local += ok;
+        }
+        for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
+        if (tid == 0) { s_n = 0; s_base = 0; }
+        __syncthreads();
+        if (lane == 0 && n_local) atomicAdd(&s_n, n_local);
+        __threadfence();
+        __syncthreads();
+        const uint32_t n = s_n;
+        // 2. compaction in rank order (itree.c:1036-1041 produce exactly this list)
+        for (uint32_t r0 = 0; r0 < db.max_ix; r0 += VB_THREADS) {
+            uint32_t rr = r0 + tid;
+            uint32_t lab = rr < db.max_ix ? __ldg(db.by_rank + rr) : 0;
+            uint32_t c = rr < db.max_ix ? __ldcg(hist + lab) : 0;    // L2 view: the counts were made by atomics
+            uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
+            if (lane == 0) s_warp[wid] = __popc(bal);
+            __syncthreads();
+            uint32_t wbase = s_base;
+            for (uint32_t w = 0; w < wid; ++w) wbase += s_warp[w];
+            if (c) {
+                uint32_t p = wbase + __popc(bal & ((1u << lane) - 1u));
+                T_lab[p] = lab; T_cnt[p] = c;
+                hist[lab] = 0;                                     // leave the scratch clean
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < VB_THREADS / 32; ++w) t += s_warp[w]; s_base += t; }
+            __syncthreads();
+        }
+        __threadfence();
+        __syncthreads();
+        const uint32_t uix = s_base;
+        utb_result *out = results + r;
+        if (wid == 0) {
+            if (n == 0) {
+                if (lane == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
+            } else {
+                if (lane == 0) atomicAdd(counters + 2, 1ull);
+                if (uix == 1) {
+                    if (lane == 0) { out->kind = UTB_STAR; out->label = T_lab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
+                } else walk_warp(db, T_lab, T_cnt, uix, n, out);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// random-sector gather microbenchmark (roofline denominator)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rand32_kernel(const uint8_t *__restrict__ buf, uint64_t n_sectors, uint32_t per_thread, uint64_t seed,
+              unsigned long long *__restrict__ sink) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t x = (t + 1) * 0x9E3779B97F4A7C15ull + seed;
+    uint64_t acc = 0;
+    for (uint32_t k = 0; k < per_thread; k += 8) {
+        uint64_t v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            x ^= x >> 12; x ^= x << 25; x ^= x >> 27;              // xorshift64*
+            uint64_t s = __umul64hi(x * 0x2545F4914F6CDD1Dull, n_sectors);   // uniform in [0, n_sectors)
+            v[j] = __ldg(reinterpret_cast<const uint64_t *>(buf + s * 32));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += v[j];
+    }
+    if (acc == 0x123456789ull) atomicAdd(sink, 1ull);              // keep the loads alive
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: database residency
+// ---------------------------------------------------------------------------
+extern "C" int utb_device_count(int *n) {
+    if (!n) { utb_set_error("utb_device_count: null argument"); return UTB_ERR_ARG; }
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess || *n <= 0) {
+        *n = 0;
+        utb_set_error("no CUDA device available (%s); there is no CPU fallback", cudaGetErrorString(e));
+        return UTB_ERR_CUDA;
+    }
+    return UTB_OK;
+}
+
+static int check_device(int device) {
+    int n = 0;
+    int rc = utb_device_count(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) { utb_set_error("device %d out of range (have %d)", device, n); return UTB_ERR_ARG; }
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    if (p.major < 10) {
+        utb_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+        return UTB_ERR_CUDA;
+    }
+    return UTB_OK;
+}
+
+// host (pageable / mmap'ed) -> device through two pinned bounce buffers so the
+// page-cache copy of chunk i+1 overlaps the PCIe copy of chunk i
+static int upload_streamed(void *dst, const void *src, size_t n, cudaStream_t st) {
+    const size_t CH = (size_t)64 << 20;
+    void *pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    CK(cudaMallocHost(&pin[0], CH));
+    CK(cudaMallocHost(&pin[1], CH));
+    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int k = 0;
+    for (size_t o = 0; o < n; o += CH, k ^= 1) {
+        size_t c = n - o < CH ? n - o : CH;
+        CK(cudaEventSynchronize(ev[k]));
+        memcpy(pin[k], (const char *)src + o, c);
+        CK(cudaMemcpyAsync((char *)dst + o, pin[k], c, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ev[k], st));
+    }
+    CK(cudaStreamSynchronize(st));
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    cudaFreeHost(pin[0]); cudaFreeHost(pin[1]);
+    return UTB_OK;
+}
+
+extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
+    if (!ctr || !out) { utb_set_error("utb_db_upload: null argument"); return UTB_ERR_ARG; }
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    utb_db *db = (utb_db *)calloc(1, sizeof(utb_db));
+    if (!db) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    db->device = device;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    size_t nb_binix = (size_t)UTB_NUMBINS * ctr->binix_bytes;
+    size_t nb_recs = (size_t)(ctr->num_nodes * ctr->sz);
+    size_t nl = ctr->max_ix;
+    CK(cudaMalloc(&db->binix, nb_binix + 64));
+    CK(cudaMalloc(&db->recs, nb_recs + 64));                       // +slack: itree.c:766
+    CK(cudaMalloc(&db->blob, ctr->blob_len + 64));
+    CK(cudaMalloc(&db->off, (nl + 1) * 4));
+    CK(cudaMalloc(&db->rank, (nl + 1) * 4));
+    CK(cudaMalloc(&db->by_rank, (nl + 1) * 4));
+    CK(cudaMemsetAsync((char *)db->binix + nb_binix, 0, 64, st));
+    CK(cudaMemsetAsync((char *)db->recs + nb_recs, 0, 64, st));
+    CK(cudaMemsetAsync(db->blob, 0, ctr->blob_len + 64, st));
+    rc = upload_streamed(db->binix, ctr->binix_raw, nb_binix, st); if (rc) return rc;
+    rc = upload_streamed(db->recs, ctr->recs, nb_recs, st); if (rc) return rc;
+    CK(cudaMemcpyAsync(db->blob, ctr->blob, ctr->blob_len, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db->off, ctr->off, (nl + 1) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db->rank, ctr->rank, nl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(db->by_rank, ctr->by_rank, nl * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaStreamDestroy(st));
+    db->d.binix32 = ctr->binix_bytes == 4 ? (const uint32_t *)db->binix : nullptr;
+    db->d.binix64 = ctr->binix_bytes == 8 ? (const uint64_t *)db->binix : nullptr;
+    db->d.recs = (const uint8_t *)db->recs;
+    db->d.num_nodes = ctr->num_nodes;
+    db->d.sz = ctr->sz; db->d.ix_bytes = ctr->ix_bytes; db->d.max_ix = ctr->max_ix;
+    db->d.blob = (const char *)db->blob;
+    db->d.off = (const uint32_t *)db->off;
+    db->d.rank = (const uint32_t *)db->rank;
+    db->d.by_rank = (const uint32_t *)db->by_rank;
+    db->hbm_bytes = nb_binix + nb_recs + ctr->blob_len + 3 * (nl + 1) * 4;
+    // Hot prefix table pinned in L2: reserve persisting lines for the index so
+    // the streaming record traffic does not evict it (applied per stream in
+    // utb_batch_create).
+    cudaDeviceProp p;
+    CK(cudaGetDeviceProperties(&p, device));
+    const char *env = getenv("UTB_L2_PERSIST");
+    if ((!env || atoi(env) != 0) && p.persistingL2CacheMaxSize > 0 && p.accessPolicyMaxWindowSize > 0) {
+        size_t want = nb_binix < (size_t)p.persistingL2CacheMaxSize ? nb_binix : (size_t)p.persistingL2CacheMaxSize;
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+            db->l2_window = 1;
+            db->l2_window_bytes = nb_binix < (size_t)p.accessPolicyMaxWindowSize ? nb_binix : (size_t)p.accessPolicyMaxWindowSize;
+        } else cudaGetLastError();
+    }
+    *out = db;
+    return UTB_OK;
+}
+
+extern "C" void utb_db_free(utb_db *db) {
+    if (!db) return;
+    cudaSetDevice(db->device);
+    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob);
+    cudaFree(db->off); cudaFree(db->rank); cudaFree(db->by_rank);
+    free(db);
+}
+extern "C" uint64_t utb_db_hbm_bytes(const utb_db *db) { return db ? db->hbm_bytes : 0; }
+
+// ---------------------------------------------------------------------------
+// C ABI: batches
+// ---------------------------------------------------------------------------
+#define VB_BLOCKS 148
+
+struct utb_batch {
+    utb_db *db;
+    cudaStream_t st;
+    cudaEvent_t done, ev[5];
+    size_t max_bytes, max_reads;
+    uint64_t max_groups;
+    // pinned host
+    char *h_bytes; uint64_t *h_seq_off; uint32_t *h_seq_len; uint32_t *h_grp_off;
+    utb_result *h_results; unsigned long long *h_counters;
+    // device
+    uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
+    uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
+    utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count;
+    unsigned long long *d_counters;   // [0] lookups [1] hits [2] good finds
+    uint32_t *d_hist, *d_tlab, *d_tcnt;
+    // last submit
+    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight;
+    uint64_t launches;
+};
+
+extern "C" uint64_t utb_read_slots(uint32_t len) { return ((uint64_t)len + 1 + 31) / 32; }
+extern "C" uint64_t utb_batch_max_slots(const utb_batch *b) { return b->max_groups; }
+extern "C" char *utb_batch_bytes(utb_batch *b) { return b->h_bytes; }
+extern "C" uint64_t *utb_batch_seq_off(utb_batch *b) { return b->h_seq_off; }
+extern "C" uint32_t *utb_batch_seq_len(utb_batch *b) { return b->h_seq_len; }
+extern "C" size_t utb_batch_max_bytes(const utb_batch *b) { return b->max_bytes; }
+extern "C" size_t utb_batch_max_reads(const utb_batch *b) { return b->max_reads; }
+
+extern "C" void utb_batch_destroy(utb_batch *b) {
+    if (!b) return;
+    cudaSetDevice(b->db->device);
+    if (b->st) cudaStreamSynchronize(b->st);
+    cudaFreeHost(b->h_bytes); cudaFreeHost(b->h_seq_off); cudaFreeHost(b->h_seq_len); cudaFreeHost(b->h_grp_off);
+    cudaFreeHost(b->h_results); cudaFreeHost(b->h_counters);
+    cudaFree(b->d_raw); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_grp_off);
+    cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
+    cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
+    cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
+    if (b->done) cudaEventDestroy(b->done);
+    for (int i = 0; i < 5; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    if (b->st) cudaStreamDestroy(b->st);
+    free(b);
+}
+
+extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, utb_batch **out) {
+    if (!db || !out || !max_bytes || !max_reads) { utb_set_error("utb_batch_create: bad argument"); return UTB_ERR_ARG; }
+    *out = nullptr;
+    if (max_bytes + 32 * max_reads >= ((uint64_t)1 << 32) - 4096) {
+        utb_set_error("batch too large: positions must fit 32 bits"); return UTB_ERR_LIMIT;
+    }
+    CK(cudaSetDevice(db->device));
+    utb_batch *b = (utb_batch *)calloc(1, sizeof(utb_batch));
+    if (!b) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    b->db = db; b->max_bytes = max_bytes; b->max_reads = max_reads;
+    // every read owns ceil((len+1)/32) <= len/32 + 1 groups
+    b->max_groups = max_bytes / 32 + max_reads + 1;
+    size_t npos = (size_t)b->max_groups * 32;
+    size_t nl = db->d.max_ix ? db->d.max_ix : 1;
+#define BK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { utb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); utb_batch_destroy(b); return UTB_ERR_CUDA; } } while (0)
+    BK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
+    BK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+    for (int i = 0; i < 5; ++i) BK(cudaEventCreate(&b->ev[i]));
+    BK(cudaMallocHost(&b->h_bytes, max_bytes + 64));
+    BK(cudaMallocHost(&b->h_seq_off, max_reads * 8));
+    BK(cudaMallocHost(&b->h_seq_len, max_reads * 4));
+    BK(cudaMallocHost(&b->h_grp_off, (max_reads + 1) * 4));
+    BK(cudaMallocHost(&b->h_results, max_reads * sizeof(utb_result)));
+    BK(cudaMallocHost(&b->h_counters, 4 * 8));
+    BK(cudaMalloc(&b->d_raw, max_bytes + 128));
+    BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
+    BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
+    BK(cudaMalloc(&b->d_grp_off, (max_reads + 1) * 4));
+    BK(cudaMalloc(&b->d_pk, (b->max_groups + 2) * 8));
+    BK(cudaMalloc(&b->d_bad, (b->max_groups + 2) * 4));
+    BK(cudaMalloc(&b->d_hits, npos * 2 * 4));
+    BK(cudaMalloc(&b->d_results, max_reads * sizeof(utb_result)));
+    BK(cudaMalloc(&b->d_gen_list, max_reads * 4));
+    BK(cudaMalloc(&b->d_gen_count, 4));
+    BK(cudaMalloc(&b->d_counters, 4 * 8));
+    BK(cudaMalloc(&b->d_hist, (size_t)VB_BLOCKS * nl * 4));
+    BK(cudaMalloc(&b->d_tlab, (size_t)VB_BLOCKS * nl * 4));
+    BK(cudaMalloc(&b->d_tcnt, (size_t)VB_BLOCKS * nl * 4));
+    BK(cudaMemset(b->d_hist, 0, (size_t)VB_BLOCKS * nl * 4));
+    BK(cudaMemset(b->d_raw, 0, max_bytes + 128));
+    if (db->l2_window) {
+        cudaStreamAttrValue a;
+        memset(&a, 0, sizeof a);
+        a.accessPolicyWindow.base_ptr = db->binix;
+        a.accessPolicyWindow.num_bytes = db->l2_window_bytes;
+        a.accessPolicyWindow.hitRatio = 1.0f;
+        a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(b->st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
+    }
+#undef BK
+    *out = b;
+    return UTB_OK;
+}
+
+// launches the device stages on b->st; if timed, records ev[0..4] around them
+static int launch_stages(utb_batch *b, bool timed) {
+    const DevDB &d = b->db->d;
+    const uint32_t n_reads = (uint32_t)b->n_reads, n_groups = b->n_groups;
+    const uint32_t n_pos = n_groups * 32u;
+    const uint32_t nstr = b->do_rc ? 2u : 1u;
+    CK(cudaMemsetAsync(b->d_gen_count, 0, 4, b->st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 4 * 8, b->st));
+    if (timed) CK(cudaEventRecord(b->ev[0], b->st));
+    if (n_reads) {
+        pack_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
+                                                                   n_reads, n_groups, b->d_pk, b->d_bad);
+        b->launches++;
+    }
+    if (timed) CK(cudaEventRecord(b->ev[1], b->st));
+    if (n_pos) {
+        if (nstr == 2) lookup_kernel<2><<<(n_pos + 255) / 256, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+        else lookup_kernel<1><<<(n_pos + 255) / 256, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+        b->launches++;
+    }
+    if (timed) CK(cudaEventRecord(b->ev[2], b->st));
+    if (n_reads) {
+        VoteIn in;
+        in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
+        vote_warp_kernel<<<(n_reads + VW_WARPS - 1) / VW_WARPS, VW_WARPS * 32, 0, b->st>>>(
+            d, in, n_reads, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
+        vote_block_kernel<<<VB_BLOCKS, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
+                                                               b->d_hist, b->d_tlab, b->d_tcnt, b->d_counters);
+        b->launches += 2;
+    }
+    if (timed) CK(cudaEventRecord(b->ev[3], b->st));
+    CK(cudaGetLastError());
+    return UTB_OK;
+}
+
+extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
+    if (!b) { utb_set_error("utb_batch_submit: null batch"); return UTB_ERR_ARG; }
+    if (n_bytes > b->max_bytes || n_reads > b->max_reads) { utb_set_error("utb_batch_submit: batch over capacity"); return UTB_ERR_LIMIT; }
+    CK(cudaSetDevice(b->db->device));
+    // position space: read r owns groups [grp_off[r], grp_off[r+1])
+    uint64_t g = 0;
+    for (size_t r = 0; r < n_reads; ++r) {
+        uint32_t len = b->h_seq_len[r];
+        if (len > UTB_MAXSEQ) { utb_set_error("read %zu: %u bases exceeds the 16777214-base limit", r, len); return UTB_ERR_LIMIT; }
+        if (b->h_seq_off[r] + len > n_bytes) { utb_set_error("read %zu: sequence outside the batch bytes", r); return UTB_ERR_ARG; }
+        b->h_grp_off[r] = (uint32_t)g;
+        g += utb_read_slots(len);
+    }
+    if (g > b->max_groups) { utb_set_error("utb_batch_submit: %llu position groups exceed capacity %llu", (unsigned long long)g, (unsigned long long)b->max_groups); return UTB_ERR_LIMIT; }
+    b->h_grp_off[n_reads] = (uint32_t)g;
+    b->n_reads = n_reads; b->n_groups = (uint32_t)g; b->do_rc = do_rc ? 1 : 0;
+    if (n_reads) {
+        CK(cudaMemcpyAsync(b->d_raw, b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
+        CK(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, n_reads * 8, cudaMemcpyHostToDevice, b->st));
+        CK(cudaMemcpyAsync(b->d_seq_len, b->h_seq_len, n_reads * 4, cudaMemcpyHostToDevice, b->st));
+        CK(cudaMemcpyAsync(b->d_grp_off, b->h_grp_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, b->st));
+    }
+    int rc = launch_stages(b, true);
+    if (rc) return rc;
+    if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
+    CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * 8, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaEventRecord(b->done, b->st));
+    b->in_flight = 1;
+    return UTB_OK;
+}
+
+extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
+    if (!b) { utb_set_error("utb_batch_wait: null batch"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    CK(cudaEventSynchronize(b->done));
+    b->in_flight = 0;
+    if (results) *results = b->h_results;
+    return UTB_OK;
+}
+
+extern "C" int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits) {
+    if (!b) { utb_set_error("utb_batch_counts: null batch"); return UTB_ERR_ARG; }
+    if (lookups) *lookups = b->h_counters[0];
+    if (hits) *hits = b->h_counters[1];
+    return UTB_OK;
+}
+
+// device-stage milliseconds of the LAST submit (valid after wait): pack, lookup, vote, total
+extern "C" int utb_batch_last_ms(utb_batch *b, float ms[4]) {
+    if (!b || !ms) { utb_set_error("utb_batch_last_ms: null argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&ms[i], b->ev[i], b->ev[i + 1]));
+    CK(cudaEventElapsedTime(&ms[3], b->ev[0], b->ev[3]));
+    return UTB_OK;
+}
+extern "C" uint64_t utb_batch_launches(const utb_batch *b) { return b ? b->launches : 0; }
+
+extern "C" int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint64_t *launches) {
+    if (!b || iters < 1) { utb_set_error("utb_batch_rerun_device: bad argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    CK(cudaStreamSynchronize(b->st));
+    float acc[4] = {0, 0, 0, 0};
+    uint64_t l0 = b->launches;
+    for (int it = 0; it < iters; ++it) {
+        int rc = launch_stages(b, true);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(b->st));
+        float t[4];
+        rc = utb_batch_last_ms(b, t);
+        if (rc) return rc;
+        for (int i = 0; i < 4; ++i) acc[i] += t[i];
+    }
+    if (ms) for (int i = 0; i < 4; ++i) ms[i] = acc[i];
+    if (launches) *launches = b->launches - l0;
+    return UTB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: stage-level entry points for parity tests
+// ---------------------------------------------------------------------------
+extern "C" int utb_lookup_words(utb_db *db, const uint64_t *words, size_t n, uint32_t *ix) {
+    if (!db || (!words && n) || (!ix && n)) { utb_set_error("utb_lookup_words: null argument"); return UTB_ERR_ARG; }
+    if (!n) return UTB_OK;
+    CK(cudaSetDevice(db->device));
+    uint64_t *dw = nullptr; uint32_t *di = nullptr;
+    CK(cudaMalloc(&dw, n * 8));
+    CK(cudaMalloc(&di, n * 4));
+    CK(cudaMemcpy(dw, words, n * 8, cudaMemcpyHostToDevice));
+    lookup_words_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(ix, di, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dw); cudaFree(di);
+    return UTB_OK;
+}
+
+extern "C" int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len, uint64_t *fwd, uint64_t *rc, uint8_t *valid) {
+    if (!db || !seq || !fwd || !rc || !valid) { utb_set_error("utb_pack_sequence: null argument"); return UTB_ERR_ARG; }
+    if (len > UTB_MAXSEQ) { utb_set_error("sequence too long"); return UTB_ERR_LIMIT; }
+    if (!len) return UTB_OK;
+    CK(cudaSetDevice(db->device));
+    // deliberately misaligned by 1 byte, as sequences are inside a FASTA chunk
+    uint32_t n_groups = (uint32_t)utb_read_slots(len), n_pos = n_groups * 32;
+    uint8_t *d_raw; uint64_t *d_off, *d_pk, *d_f, *d_r; uint32_t *d_len, *d_grp, *d_bad; uint8_t *d_v;
+    CK(cudaMalloc(&d_raw, (size_t)len + 128)); CK(cudaMemset(d_raw, 0, (size_t)len + 128));
+    CK(cudaMalloc(&d_off, 8)); CK(cudaMalloc(&d_len, 4)); CK(cudaMalloc(&d_grp, 8));
+    CK(cudaMalloc(&d_pk, (size_t)(n_groups + 2) * 8)); CK(cudaMalloc(&d_bad, (size_t)(n_groups + 2) * 4));
+    CK(cudaMalloc(&d_f, (size_t)n_pos * 8)); CK(cudaMalloc(&d_r, (size_t)n_pos * 8)); CK(cudaMalloc(&d_v, n_pos));
+    uint64_t off = 1; uint32_t grp[2] = {0, n_groups};
+    CK(cudaMemcpy(d_raw + 1, seq, len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_len, &len, 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_grp, grp, 8, cudaMemcpyHostToDevice));
+    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, d_pk, d_bad);
+    expand_windows_kernel<<<(n_pos + 255) / 256, 256>>>(d_pk, d_bad, n_pos, d_f, d_r, d_v);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(fwd, d_f, (size_t)len * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rc, d_r, (size_t)len * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(valid, d_v, len, cudaMemcpyDeviceToHost));
+    cudaFree(d_raw); cudaFree(d_off); cudaFree(d_len); cudaFree(d_grp); cudaFree(d_pk); cudaFree(d_bad);
+    cudaFree(d_f); cudaFree(d_r); cudaFree(d_v);
+    return UTB_OK;
+}
+
+extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off, size_t n_reads, utb_result *results) {
+    if (!db || !off || !results || (!hits && n_reads && off[n_reads])) { utb_set_error("utb_vote_hits: null argument"); return UTB_ERR_ARG; }
+    if (!n_reads) return UTB_OK;
+    CK(cudaSetDevice(db->device));
+    size_t nh = off[n_reads], nl = db->d.max_ix ? db->d.max_ix : 1;
+    uint32_t *d_hits, *d_gl, *d_gc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
+    CK(cudaMalloc(&d_hits, (nh + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
+    CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
+    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 32));
+    CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
+    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 32));
+    if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1;
+    vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, d_res, d_gl, d_gc, d_cnt);
+    vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
+    cudaFree(d_hits); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_cnt);
+    cudaFree(d_hist); cudaFree(d_tl); cudaFree(d_tc);
+    return UTB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: roofline denominator
+// ---------------------------------------------------------------------------
+extern "C" int utb_measure_rand32(int device, uint64_t ws_bytes, uint64_t loads, int iters, double *gbs) {
+    if (!gbs || ws_bytes < 4096 || iters < 1) { utb_set_error("utb_measure_rand32: bad argument"); return UTB_ERR_ARG; }
+    int rc = check_device(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    uint8_t *buf; unsigned long long *sink;
+    CK(cudaMalloc(&buf, ws_bytes));
+    CK(cudaMalloc(&sink, 8));
+    CK(cudaMemset(buf, 1, ws_bytes));
+    CK(cudaMemset(sink, 0, 8));
+    const uint32_t per_thread = 64;
+    uint64_t threads = (loads + per_thread - 1) / per_thread;
+    uint32_t blocks = (uint32_t)((threads + 255) / 256);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int it = 0; it < iters + 1; ++it) {
+        CK(cudaEventRecord(e0));
+        rand32_kernel<<<blocks, 256>>>(buf, ws_bytes / 32, per_thread, 0x1234 + it, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        double g = (double)blocks * 256 * per_thread * 32.0 / (ms * 1e-3) / 1e9;
+        if (it > 0 && g > best) best = g;                          // first pass is warm-up
+    }
+    *gbs = best;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf); cudaFree(sink);
+    return UTB_OK;
+}
