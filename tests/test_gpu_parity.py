@@ -173,3 +173,41 @@ def test_cli_binary_matches_reference(ctrs, tmp_path, db_name, reads, out, rc):
     assert lines[-1].startswith("Searched ") and lines[-2].startswith("Good finds: ")
     n_out = sum(1 for _ in open(gold(out), "rb"))
     assert lines[-2] == f"Good finds: {n_out}"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "utree-build_gg")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("complevel", [0, 2])
+def test_synthetic_ctr_equals_reference_built_tree(built, tmp_path, complevel):
+    """The GPU CTR synthesiser (bench input generator) against the REAL builder:
+    same universe through utree-build_gg + utree-compress and through
+    uts_build_ctr must classify identically (reference search on both trees),
+    and the product must match the reference on the synthesised tree."""
+    from utree_b200 import build, capi, synthgpu
+    build.build_synth()
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    uni = synthgpu.Universe(seed=99, n_phyla=2, n_genera=2, n_species=2, n_strains=3, genome_len=30000)
+    fa, mp = str(tmp_path / "g.fa"), str(tmp_path / "g.map")
+    with open(fa, "wb") as f, open(mp, "wb") as m:
+        for g in range(uni.n_genomes):
+            f.write(b">gen%d\n" % g + uni.genome_ascii(g) + b"\n")
+            m.write(b"gen%d\t" % g + uni.genome_tax(g) + b"\n")
+    ubt, ctr_ref, ctr_syn = str(tmp_path / "t.ubt"), str(tmp_path / "ref.ctr"), str(tmp_path / "syn.ctr")
+    subprocess.run([os.path.join(ref, "utree-build_gg"), fa, mp, ubt, "1", str(complevel)], check=True, stdout=subprocess.DEVNULL)
+    subprocess.run([os.path.join(ref, "utree-compress"), ubt, ctr_ref], check=True, stdout=subprocess.DEVNULL)
+    n, nl = uni.build_ctr(ctr_syn, complevel=complevel)
+    assert n == np.frombuffer(open(ctr_ref, "rb").read(32), dtype="<u8")[3]
+    reads = str(tmp_path / "r.fa")
+    uni.make_reads(20000, read_len=150).tofile(reads)
+    outs = []
+    for c in (ctr_ref, ctr_syn):
+        o = c + ".out"
+        subprocess.run([os.path.join(ref, "utree-search_gg"), c, reads, o, "1", "RC"], check=True, stdout=subprocess.DEVNULL)
+        outs.append(open(o, "rb").read())
+    assert outs[0] == outs[1] and outs[0].count(b"\n") > 15000
+    ctr = capi.Ctr(ctr_syn)
+    s = capi.Searcher(ctr, devices=(0,), host_threads=2)
+    try:
+        code, _, text, st = s.search_mem(open(reads, "rb").read(), do_rc=True)
+        assert code == 0 and text == outs[1]
+    finally:
+        s.destroy(); ctr.close()

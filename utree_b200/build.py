@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libutree_b200.so")
+SYNTH_LIB = os.path.join(CSRC, "libutb_synth.so")   # bench/test input generator, not the product
 BIN = os.path.join(ROOT, "bin")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "gcc"   # PATH gcc: $CC in this image points at a gcc without libgomp specs
@@ -54,7 +55,8 @@ def build(force=False, verbose=False):
         o = os.path.join(CSRC, f[:-2] + ".o")
         _run([GCC] + C_FLAGS + ["-c", os.path.join(CSRC, f), "-o", o], log)
         objs.append(o)
-    _run([NVCC, "-shared", "-o", LIB] + objs + ["-Xcompiler", "-pthread", "-lpthread"], log)
+    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
+         ["-Xcompiler", "-pthread", "-lpthread"], log)
     os.makedirs(BIN, exist_ok=True)
     _run([GCC] + C_FLAGS + [os.path.join(CSRC, "main.c"), "-o", exe, "-L" + CSRC, "-lutree_b200",
                             "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
@@ -67,6 +69,16 @@ def build(force=False, verbose=False):
     return LIB
 
 
+def build_synth(force=False):
+    """libutb_synth.so: synthetic CTR / reads generator (CUB sort).  Inputs only."""
+    src = os.path.join(CSRC, "synth.cu")
+    if not force and _newer(SYNTH_LIB, [src]):
+        return SYNTH_LIB
+    _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-Xcompiler", "-fPIC", "-shared", src, "-o", SYNTH_LIB])
+    return SYNTH_LIB
+
+
 def build_oracle():
     """Builds the CPU checker (and oracle/_ref when /root/reference exists)."""
     _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
@@ -74,4 +86,5 @@ def build_oracle():
 
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
+    build_synth(force="--force" in sys.argv)
     build_oracle()

@@ -1,0 +1,75 @@
+"""ctypes wrapper of libutb_synth.so (utree_b200/csrc/synth.cu): GPU-side
+generator of bench / large-test INPUTS (a CTR file and FASTA reads of a seeded
+synthetic universe).  Not on the search path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libutb_synth.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(LIB_PATH)
+        L.uts_last_error.restype = C.c_char_p
+        L.uts_build_ctr.argtypes = [C.c_int, C.c_uint64] + [C.c_uint32] * 7 + [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+        L.uts_reads_bytes.restype = C.c_uint64
+        L.uts_reads_bytes.argtypes = [C.c_uint64, C.c_uint32]
+        L.uts_make_reads.argtypes = [C.c_int, C.c_uint64] + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_uint32] * 4 + [C.c_void_p]
+        L.uts_genome_ascii.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.c_void_p]
+        L.uts_genome_ascii.restype = None
+        L.uts_genome_tax.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.c_char_p, C.c_size_t]
+        L.uts_genome_tax.restype = None
+        _lib = L
+    return _lib
+
+
+class Universe:
+    """n_phyla x n_genera x n_species x n_strains genomes of genome_len bases."""
+
+    def __init__(self, seed, n_phyla, n_genera, n_species, n_strains, genome_len):
+        self.seed, self.shape, self.genome_len = seed, (n_phyla, n_genera, n_species, n_strains), genome_len
+        self.n_genomes = n_phyla * n_genera * n_species * n_strains
+
+    def _args(self):
+        return [self.seed, *self.shape, self.genome_len]
+
+    def build_ctr(self, path, complevel=2, ix_bytes=2, device=0):
+        n, nl = C.c_uint64(), C.c_uint32()
+        rc = lib().uts_build_ctr(device, *self._args(), complevel, ix_bytes, os.fsencode(path), C.byref(n), C.byref(nl))
+        if rc:
+            raise RuntimeError("uts_build_ctr: " + lib().uts_last_error().decode())
+        return n.value, nl.value
+
+    def record_bytes(self, read_len):
+        return 12 + read_len + 1
+
+    def make_reads(self, n_reads, read_len=150, read_seed=7, first=0, sub_permille=10, n_permille=20,
+                   random_permille=20, device=0, out=None):
+        """Returns a uint8 array holding fixed-width FASTA records
+        '>r%09u\\n' + bases + '\\n' for reads [first, first + n_reads)."""
+        nb = lib().uts_reads_bytes(n_reads, read_len)
+        if out is None:
+            out = np.empty(nb, dtype=np.uint8)
+        assert out.size >= nb
+        rc = lib().uts_make_reads(device, *self._args(), read_seed, first, n_reads, read_len, sub_permille,
+                                  n_permille, random_permille, out.ctypes.data)
+        if rc:
+            raise RuntimeError("uts_make_reads: " + lib().uts_last_error().decode())
+        return out[:nb]
+
+    def genome_ascii(self, g):
+        buf = np.empty(self.genome_len, dtype=np.uint8)
+        lib().uts_genome_ascii(*self._args(), g, buf.ctypes.data)
+        return buf.tobytes()
+
+    def genome_tax(self, g):
+        buf = C.create_string_buffer(512)
+        lib().uts_genome_tax(*self._args(), g, buf, 512)
+        return buf.value
