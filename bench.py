@@ -38,9 +38,11 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: universe (phyla, genera, species, strains, genome_len), complevel, ix_bytes, reads/GPU, read_len
-    "l2s": dict(universe=(50, 5, 5, 4, 4_000_000), complevel=2, ix_bytes=2, reads=10_000_000, read_len=150,
+    # one strain per species, like a RefSeq-representative set: little k-mer sharing, so the
+    # 20 Gb of genome sampled 1/16 (complevel 2) keeps ~1.1 G records (~8 GB), README.md:2
+    "l2s": dict(universe=(50, 20, 5, 1, 4_000_000), complevel=2, ix_bytes=2, reads=10_000_000, read_len=150,
                 desc="L2-scale synthetic CTR (5000 genomes x 4 Mb, complevel 2) vs 10M x 150bp reads, RC"),
-    "l4": dict(universe=(50, 5, 5, 4, 4_000_000), complevel=4, ix_bytes=2, reads=10_000_000, read_len=150,
+    "l4": dict(universe=(50, 20, 5, 1, 4_000_000), complevel=4, ix_bytes=2, reads=10_000_000, read_len=150,
                desc="L4 synthetic CTR (5000 genomes x 4 Mb, complevel 4) vs 10M x 150bp reads, RC"),
     "small": dict(universe=(4, 3, 3, 3, 400_000), complevel=2, ix_bytes=2, reads=400_000, read_len=150,
                   desc="small synthetic CTR (108 genomes x 0.4 Mb, complevel 2) vs 400k x 150bp reads, RC"),

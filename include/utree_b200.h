@@ -13,11 +13,11 @@
  *   XT_read32()            itree.c:733-828   utb_ctr_open + utb_db_upload
  *   readSamplesFPdelim()   itree.c:1202-1223 (inside utb_ctr_open)
  *   XT_doSearch32()        itree.c:833-1108  utb_search_file / utb_search_mem
- *     XT_INITIATE_WS       itree.c:860-901     host framer (fasta_reader.c)
+ *     XT_INITIATE_WS       itree.c:860-901     host framer (pipeline.c)
  *     XT_WORD_SEARCH       itree.c:903-933     pack + lookup kernels
  *     XT_getIX32/xtSuffixBS itree.c:699-730    lookup kernel
  *     full aufbau vote     itree.c:1028-1098   vote kernels
- *     fprintf lines        itree.c:1032-1096   host formatter (formatter.c)
+ *     fprintf lines        itree.c:1032-1096   host formatter (pipeline.c)
  *   main() search branch   itree.c:1357-1377 utb_main
  */
 #ifndef UTREE_B200_H
@@ -125,6 +125,21 @@ int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len,
  * (itree.c:1028-1098). */
 int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off,
                   size_t n_reads, utb_result *results);
+
+/* ---- host stages (no GPU involved; CPU tests drive them directly) --------- */
+/* The reference's record reader (itree.c:866-890) over a byte buffer: lines
+ * are taken strictly in pairs, name = bytes after '>' up to the first ' ',
+ * '\n' or NUL, sequence = the line cut at a NUL, minus one '\n' and one '\r'.
+ * Fills one entry per complete record (at most max_reads), *used = byte after
+ * the last framed record.  A malformed record stops the framing: the records
+ * before it are valid, the call returns UTB_ERR_FORMAT and *ref_exit = 2. */
+int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t max_reads,
+                      uint64_t *seq_off, uint32_t *seq_len, uint32_t *name_off, uint32_t *name_len,
+                      size_t *n_reads, size_t *used, int *ref_exit);
+/* The reference's output lines (itree.c:1032, 1040, 1096) for n_reads result
+ * records; names are taken from bytes[name_off[r] .. +name_len[r]). */
+int utb_format_results(const utb_ctr *ctr, const char *bytes, const uint32_t *name_off, const uint32_t *name_len,
+                       const utb_result *results, size_t n_reads, char *out, size_t out_cap, size_t *out_len);
 
 /* ---- whole search (XT_doSearch32 + output, itree.c:833-1108) -------------- */
 typedef struct {

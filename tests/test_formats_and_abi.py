@@ -123,3 +123,91 @@ def test_cli_usage_and_db_errors(built, tmp_path):
     out = p.stdout.splitlines()
     assert out[:5] == ["This is UTree [v2.0RF SigNature Edition]", "Reverse complement consideration is enabled.",
                        "Searching at speed 0.", "Using up to 1 threads.", "Invalid DB file"]
+
+
+# ---- host logic: framer and formatter (no GPU) --------------------------------
+def _py_frame(data):
+    """Reference reader restated in Python (itree.c:866-890); returns (records, error?)."""
+    if not data:
+        return [], False
+    lines = data.split(b"\n")
+    if data.endswith(b"\n"):
+        lines = lines[:-1]
+        ends = [b"\n"] * len(lines)
+    else:
+        ends = [b"\n"] * (len(lines) - 1) + [b""]
+    recs = []
+    for i in range(0, len(lines), 2):
+        if i + 1 >= len(lines):
+            return recs, True                       # can't read sequence
+        h, s = lines[i] + ends[i], lines[i + 1] + ends[i + 1]
+        if h[:1] != b">" or s[:1] == b">":
+            return recs, True
+        s = s.split(b"\0")[0]
+        if not s:
+            return recs, True
+        if s.endswith(b"\n"):
+            s = s[:-1]
+        if s.endswith(b"\r"):
+            s = s[:-1]
+        name = h[1:]
+        for stop in (b"\0", b" ", b"\n"):
+            name = name.split(stop)[0]
+        recs.append((name, s))
+    return recs, False
+
+
+@pytest.mark.parametrize("fasta", ["toyA_reads.fa", "toyB_reads.fa", "edge_reads.fa", "long_reads.fa", "quirk_reads.fa",
+                                   "bad_noheader.fa", "bad_seq_is_header.fa", "bad_truncated.fa"])
+@pytest.mark.parametrize("threads", [1, 2, 5, 16])
+def test_framer_matches_reference_reader(built, fasta, threads):
+    from utree_b200 import capi
+    data = open(gold(fasta), "rb").read()
+    want, bad = _py_frame(data)
+    rc, ex, used, recs, _ = capi.frame_records(data, eof=True, threads=threads)
+    assert recs == want
+    assert (rc, ex) == ((3, 2) if bad else (0, 0))
+    if not bad:
+        assert used == len(data)
+
+
+def test_framer_odd_inputs(built):
+    from utree_b200 import capi
+    cases = [b"", b">a\nACGT", b">a\nACGT\n", b">a\r\nACGT\r\n", b">a b c\nAC\0GT\n", b">\nA\n", b">x\n\n>y\nAC\n",
+             b">a\nACGT\n\n", b"\n", b">a\n", b">a", b">n\0ame z\nACGT\n>b\n\0\n", b">a\nAC\n>b\nGT\n>c\n>d\n"]
+    for data in cases:
+        want, bad = _py_frame(data)
+        for t in (1, 3, 8):
+            rc, ex, used, recs, _ = capi.frame_records(data, eof=True, threads=t)
+            assert recs == want, (data, t)
+            assert (rc != 0) == bad, (data, t)
+
+
+def test_framer_partial_buffer_carries_the_tail(built):
+    """Without EOF an incomplete last record is left for the next buffer."""
+    from utree_b200 import capi
+    data = b">a\nACGT\n>b\nGGTT\n>c\nAC"
+    rc, ex, used, recs, _ = capi.frame_records(data, eof=False, threads=4)
+    assert rc == 0 and recs == [(b"a", b"ACGT"), (b"b", b"GGTT")] and data[used:] == b">c\nAC"
+    rc, ex, used, recs, _ = capi.frame_records(data + b"\n", eof=False, threads=4)
+    assert [r[0] for r in recs] == [b"a", b"b", b"c"] and used == len(data) + 1
+    rc, ex, used, recs, _ = capi.frame_records(data, eof=False, threads=2, max_reads=1)
+    assert recs == [(b"a", b"ACGT")] and data[used:].startswith(b">b\n")
+
+
+def test_formatter_matches_oracle_lines(built, ctrs):
+    """utb_format_results on oracle votes == the golden output of the reference."""
+    from utree_b200 import capi
+    ctr, orc = capi.Ctr(ctrs["toyA"]), capi.OracleDb(ctrs["toyA"])
+    try:
+        data = open(gold("toyA_reads.fa"), "rb").read()
+        rc, ex, used, recs, (name_off, name_len) = capi.frame_records(data, threads=3)
+        res = np.zeros(len(recs), dtype=capi.RESULT_DTYPE)
+        for i, (_, seq) in enumerate(recs):
+            hits, _ = orc.slide(seq, do_rc=True)
+            v = orc.vote(hits)
+            res[i] = (v.kind, v.label, v.cut, v.found, v.uix, v.sl, v.ol, 0)
+        text = capi.format_results(ctr, data, name_off, name_len, res)
+        assert text == open(gold("toyA_rc.out"), "rb").read()
+    finally:
+        ctr.close(); orc.free()

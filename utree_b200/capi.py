@@ -49,7 +49,7 @@ EXPORTS = [
     "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
     "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
     "utb_batch_submit", "utb_batch_wait", "utb_batch_rerun_device", "utb_batch_counts",
-    "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits",
+    "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_frame_records", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
     "utb_main", "utb_measure_rand32",
 ]
@@ -96,6 +96,10 @@ def lib():
         L.utb_lookup_words.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.utb_pack_sequence.argtypes = [C.c_void_p, C.c_char_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.utb_vote_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.utb_frame_records.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 4 + \
+            [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+        L.utb_format_results.argtypes = [C.c_void_p, C.c_char_p] + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p, C.c_size_t,
+                                                                                       C.POINTER(C.c_size_t)]
         L.utb_searcher_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.utb_search_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(Stats), C.POINTER(C.c_int)]
         L.utb_search_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p),
@@ -134,6 +138,33 @@ class Ctr:
         if self.h:
             lib().utb_ctr_close(self.h)
             self.h = C.c_void_p()
+
+
+def frame_records(buf: bytes, eof=True, threads=1, max_reads=None):
+    """Host framer (utb_frame_records).  Returns (rc, ref_exit, used, [(name, seq)])."""
+    cap = max_reads if max_reads is not None else len(buf) // 2 + 2
+    seq_off = np.zeros(cap, dtype=np.uint64)
+    seq_len = np.zeros(cap, dtype=np.uint32)
+    name_off = np.zeros(cap, dtype=np.uint32)
+    name_len = np.zeros(cap, dtype=np.uint32)
+    n, used, ex = C.c_size_t(), C.c_size_t(), C.c_int()
+    rc = lib().utb_frame_records(buf, len(buf), int(eof), threads, cap, seq_off.ctypes.data, seq_len.ctypes.data,
+                                 name_off.ctypes.data, name_len.ctypes.data, C.byref(n), C.byref(used), C.byref(ex))
+    recs = [(buf[name_off[i]:name_off[i] + name_len[i]], buf[seq_off[i]:seq_off[i] + seq_len[i]]) for i in range(n.value)]
+    return rc, ex.value, used.value, recs, (name_off[:n.value].copy(), name_len[:n.value].copy())
+
+
+def format_results(ctr, buf: bytes, name_off, name_len, results):
+    """Host formatter (utb_format_results) -> bytes."""
+    results = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
+    name_off = np.ascontiguousarray(name_off, dtype=np.uint32)
+    name_len = np.ascontiguousarray(name_len, dtype=np.uint32)
+    cap = len(buf) + results.size * 1024 + 64
+    out = C.create_string_buffer(cap)
+    n = C.c_size_t()
+    _ck(lib().utb_format_results(ctr.h, buf, name_off.ctypes.data, name_len.ctypes.data, results.ctypes.data,
+                                 results.size, out, cap, C.byref(n)))
+    return out.raw[:n.value]
 
 
 def device_count():

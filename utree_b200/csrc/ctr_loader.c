@@ -32,7 +32,6 @@ void utb_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 const char *utb_last_error(void) { return g_err; }
-void utb_free(void *p) { free(p); }
 
 static uint64_t fnv1a(const char *s, size_t n) {
     uint64_t h = 1469598103934665603ull;

@@ -3,13 +3,19 @@
  * GPUs, and the ordered output formatter (the fprintf lines of itree.c:1032,
  * 1040, 1096).
  *
- * Threads: the calling thread reads the input straight into the pinned
- * staging buffer of the next free batch slot, frames the records in place
- * (no per-read copies: the device receives the file bytes as they are, plus
- * one (offset,length) pair per read) and submits the batch; one formatter
- * thread waits for batches in sequence order and emits the text.  Slots are
- * dealt round-robin over the devices, the database being replicated on each,
- * so multi-GPU needs no collective: the ordered merge below is the only
+ * Two thread teams share the [threads] the CLI is given:
+ *   reader team    -- fills the pinned staging buffer of the next free batch
+ *                     slot straight from the input (parallel pread / memcpy),
+ *                     frames the records in place (parallel newline count,
+ *                     then parallel record parse keyed by line parity), and
+ *                     submits the batch.  No per-read copies: the device gets
+ *                     the file bytes as they are plus one (offset, length)
+ *                     pair per read.
+ *   formatter team -- waits for batches in sequence order, formats the lines
+ *                     of a batch in parallel, and emits them in order
+ *                     (parallel pwrite / memcpy at prefix-summed offsets).
+ * Slots are dealt round-robin over the devices, the database being replicated
+ * on each, so multi-GPU needs no collective: the ordered merge is the only
  * cross-device step.
  */
 #define _GNU_SOURCE
@@ -21,6 +27,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -29,15 +37,69 @@ uint64_t utb_batch_launches(const utb_batch *b);
 
 #define SLOTS_PER_DEVICE 3
 #define DEFAULT_BATCH_BYTES ((size_t)64 << 20)
+#define MAX_TEAM 64
 
+/* ---- thread team: leader + helpers, fork/join with barriers ----------------- */
+typedef void (*team_fn)(void *ctx, int part, int nparts);
+typedef struct {
+    int n;                      /* members including the leader */
+    pthread_t th[MAX_TEAM];
+    pthread_barrier_t start, end;
+    team_fn fn;
+    void *ctx;
+    volatile int quit;
+    struct team_arg { void *team; int id; } arg[MAX_TEAM];
+} team_t;
+
+static void *team_helper(void *a_) {
+    struct team_arg *a = (struct team_arg *)a_;
+    team_t *t = (team_t *)a->team;
+    int id = a->id;
+    for (;;) {
+        pthread_barrier_wait(&t->start);
+        if (t->quit) break;
+        t->fn(t->ctx, id, t->n);
+        pthread_barrier_wait(&t->end);
+    }
+    return NULL;
+}
+static int team_init(team_t *t, int n) {
+    memset(t, 0, sizeof *t);
+    if (n < 1) n = 1;
+    if (n > MAX_TEAM) n = MAX_TEAM;
+    t->n = n;
+    if (n == 1) return 0;
+    pthread_barrier_init(&t->start, NULL, (unsigned)n);
+    pthread_barrier_init(&t->end, NULL, (unsigned)n);
+    for (int i = 1; i < n; ++i) {
+        t->arg[i].team = t; t->arg[i].id = i;
+        if (pthread_create(&t->th[i], NULL, team_helper, &t->arg[i])) return -1;
+    }
+    return 0;
+}
+static void team_run(team_t *t, team_fn fn, void *ctx) {
+    if (t->n == 1) { fn(ctx, 0, 1); return; }
+    t->fn = fn; t->ctx = ctx;
+    pthread_barrier_wait(&t->start);
+    fn(ctx, 0, t->n);
+    pthread_barrier_wait(&t->end);
+}
+static void team_destroy(team_t *t) {
+    if (t->n <= 1) return;
+    t->quit = 1;
+    pthread_barrier_wait(&t->start);
+    for (int i = 1; i < t->n; ++i) pthread_join(t->th[i], NULL);
+    pthread_barrier_destroy(&t->start);
+    pthread_barrier_destroy(&t->end);
+}
+
+/* ---- searcher ----------------------------------------------------------------- */
 typedef struct {
     utb_batch *b;
     int dev_index;
-    /* filled by the framer */
     size_t n_bytes, n_reads;
     uint32_t *name_off, *name_len;
     uint64_t first_read;           /* global index of the slot's first read */
-    /* hand-over */
     int state;                     /* 0 free, 1 submitted */
 } slot_t;
 
@@ -50,6 +112,7 @@ struct utb_searcher {
     slot_t *slots;
     int host_threads;
     size_t batch_bytes, batch_reads;
+    size_t max_label;              /* longest label incl. NUL */
     int verbose;                   /* CLI: progress lines on stdout */
 };
 
@@ -70,6 +133,10 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->batch_bytes = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : DEFAULT_BATCH_BYTES;
     if (s->batch_bytes < 2 * (size_t)UTB_LINELEN + 4096) s->batch_bytes = 2 * (size_t)UTB_LINELEN + 4096; /* one max record must fit */
     s->batch_reads = s->batch_bytes / 64;
+    for (uint32_t i = 0; i < ctr->max_ix; ++i) {
+        size_t l = ctr->off[i + 1] - ctr->off[i];
+        if (l > s->max_label) s->max_label = l;
+    }
     s->devices = (int *)malloc(sizeof(int) * (size_t)n_devices);
     s->dbs = (utb_db **)calloc((size_t)n_devices, sizeof(utb_db *));
     s->n_slots = n_devices * SLOTS_PER_DEVICE;
@@ -85,8 +152,8 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
         sl->dev_index = i % n_devices;
         int rc = utb_batch_create(s->dbs[sl->dev_index], s->batch_bytes, s->batch_reads, &sl->b);
         if (rc) { utb_searcher_destroy(s); return rc; }
-        sl->name_off = (uint32_t *)malloc(s->batch_reads * 4);
-        sl->name_len = (uint32_t *)malloc(s->batch_reads * 4);
+        sl->name_off = (uint32_t *)malloc((s->batch_reads + 1) * 4);
+        sl->name_len = (uint32_t *)malloc((s->batch_reads + 1) * 4);
         if (!sl->name_off || !sl->name_len) { utb_searcher_destroy(s); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     }
     *out = s;
@@ -103,18 +170,32 @@ void utb_searcher_destroy(utb_searcher *s) {
     free(s->slots); free(s->dbs); free(s->devices); free(s);
 }
 
-void utb_searcher_set_verbose(utb_searcher *s, int v) { if (s) s->verbose = v; }
-
-/* ---- input source / output sink ------------------------------------------ */
+/* ---- input source ---------------------------------------------------------------- */
 typedef struct {
     int fd;                 /* >= 0: file */
+    int seekable;           /* regular file: parallel pread */
+    off_t file_off, file_size;
     const char *mem;        /* else memory */
     size_t mem_len, mem_pos;
     int eof;
 } source_t;
 
-static ssize_t src_read(source_t *s, char *dst, size_t cap) {
-    if (s->fd >= 0) {
+typedef struct { source_t *src; char *dst; size_t n; int failed; } fill_ctx;
+static void fill_part(void *c_, int part, int nparts) {
+    fill_ctx *c = (fill_ctx *)c_;
+    size_t a = c->n * (size_t)part / (size_t)nparts, b = c->n * (size_t)(part + 1) / (size_t)nparts;
+    if (c->src->fd < 0) { memcpy(c->dst + a, c->src->mem + c->src->mem_pos + a, b - a); return; }
+    while (a < b) {
+        ssize_t k = pread(c->src->fd, c->dst + a, b - a, c->src->file_off + (off_t)a);
+        if (k < 0) { if (errno == EINTR) continue; c->failed = 1; return; }
+        if (k == 0) { c->failed = 1; return; }
+        a += (size_t)k;
+    }
+}
+/* Reads up to cap bytes into dst; returns bytes read or -1. */
+static ssize_t src_fill(source_t *s, team_t *team, char *dst, size_t cap) {
+    if (s->eof || !cap) return 0;
+    if (s->fd >= 0 && !s->seekable) {                 /* pipe / fifo: plain reads */
         size_t got = 0;
         while (got < cap) {
             ssize_t k = read(s->fd, dst + got, cap - got);
@@ -124,37 +205,53 @@ static ssize_t src_read(source_t *s, char *dst, size_t cap) {
         }
         return (ssize_t)got;
     }
-    size_t left = s->mem_len - s->mem_pos, k = left < cap ? left : cap;
-    memcpy(dst, s->mem + s->mem_pos, k);
-    s->mem_pos += k;
-    if (s->mem_pos == s->mem_len) s->eof = 1;
-    return (ssize_t)k;
+    size_t left = s->fd >= 0 ? (size_t)(s->file_size - s->file_off) : s->mem_len - s->mem_pos;
+    size_t n = left < cap ? left : cap;
+    fill_ctx c = {s, dst, n, 0};
+    if (n) team_run(team, fill_part, &c);
+    if (c.failed) return -1;
+    if (s->fd >= 0) s->file_off += (off_t)n; else s->mem_pos += n;
+    if (n == left) s->eof = 1;
+    return (ssize_t)n;
 }
 
+/* ---- output sink -------------------------------------------------------------------- */
+/* memory sink: an anonymous mapping grown with mremap (no data copies); the
+ * caller's pointer sits 64 bytes into the mapping, utb_free() unmaps it. */
+#define SINK_MAGIC 0x55544253494e4b31ull
+typedef struct { uint64_t magic, map_len; } sink_hdr;
 typedef struct {
-    FILE *fp;               /* file sink, or */
-    char *mem; size_t len, cap;   /* growing memory sink */
+    int fd;                 /* file sink (pwrite at off), or */
+    char *map; size_t cap;  /* memory sink */
+    size_t off;             /* bytes emitted so far */
     int failed;
 } sink_t;
 
-static void sink_write(sink_t *k, const char *p, size_t n) {
-    if (!n) return;
-    if (k->fp) { if (fwrite(p, 1, n, k->fp) != n) k->failed = 1; return; }
-    if (k->len + n > k->cap) {
-        size_t nc = k->cap ? k->cap : (size_t)1 << 20;
-        while (nc < k->len + n) nc <<= 1;
-        char *q = (char *)realloc(k->mem, nc);
-        if (!q) { k->failed = 1; return; }
-        k->mem = q; k->cap = nc;
-    }
-    memcpy(k->mem + k->len, p, n);
-    k->len += n;
+static int sink_reserve(sink_t *k, size_t upto) {
+    if (k->fd >= 0) return 0;
+    size_t need = upto + 64;
+    if (need <= k->cap) return 0;
+    size_t nc = k->cap ? k->cap : (size_t)1 << 24;
+    while (nc < need) nc <<= 1;
+    void *m = k->map ? mremap(k->map, k->cap, nc, MREMAP_MAYMOVE)
+                     : mmap(NULL, nc, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (m == MAP_FAILED) { k->failed = 1; return -1; }
+    k->map = (char *)m; k->cap = nc;
+    ((sink_hdr *)k->map)->magic = SINK_MAGIC;
+    ((sink_hdr *)k->map)->map_len = nc;
+    return 0;
+}
+void utb_free(void *p) {
+    if (!p) return;
+    sink_hdr *h = (sink_hdr *)((char *)p - 64);
+    if (h->magic == SINK_MAGIC) munmap(h, h->map_len);
 }
 
-/* ---- formatter ------------------------------------------------------------ */
+/* ---- shared run state ------------------------------------------------------------------ */
 typedef struct {
     utb_searcher *s;
     sink_t *sink;
+    team_t fmt_team;
     pthread_mutex_t mu;
     pthread_cond_t cv;
     uint64_t submitted;     /* batches handed to the devices */
@@ -164,6 +261,7 @@ typedef struct {
     utb_stats st;
 } run_t;
 
+/* ---- formatter ----------------------------------------------------------------------------- */
 static inline char *put_u32(char *p, uint32_t v) {
     char t[10]; int n = 0;
     do { t[n++] = (char)('0' + v % 10u); v /= 10u; } while (v);
@@ -171,13 +269,35 @@ static inline char *put_u32(char *p, uint32_t v) {
     return p;
 }
 
+typedef struct {
+    const utb_ctr *c; const slot_t *sl; const utb_result *res; const char *bytes;
+    size_t max_label;
+    char *buf[MAX_TEAM]; size_t cap[MAX_TEAM], len[MAX_TEAM], off[MAX_TEAM];
+    uint64_t good[MAX_TEAM];
+    int nomem;
+    sink_t *sink;
+} fmt_ctx;
+
 /* One line per read with >= 1 hit; shapes of itree.c:1032, 1040, 1096. */
-static size_t format_batch(const utb_ctr *c, const slot_t *sl, const utb_result *res, char *out, uint64_t *good) {
-    const char *bytes = utb_batch_bytes(sl->b);
-    char *p = out;
+static void fmt_part(void *c_, int part, int nparts) {
+    fmt_ctx *f = (fmt_ctx *)c_;
+    const slot_t *sl = f->sl;
+    size_t r0 = sl->n_reads * (size_t)part / (size_t)nparts, r1 = sl->n_reads * (size_t)(part + 1) / (size_t)nparts;
+    size_t need = 0;
+    for (size_t r = r0; r < r1; ++r) need += sl->name_len[r];
+    need += (r1 - r0) * (f->max_label + 64) + 64;   /* name + label + 4 tabs + 4 numbers + newline */
+    if (need > f->cap[part]) {
+        free(f->buf[part]);
+        f->cap[part] = need + (need >> 2);
+        f->buf[part] = (char *)malloc(f->cap[part]);
+        if (!f->buf[part]) { f->cap[part] = 0; f->len[part] = 0; f->nomem = 1; return; }
+    }
+    const utb_ctr *c = f->c;
+    const char *bytes = f->bytes;
+    char *p = f->buf[part];
     uint64_t g = 0;
-    for (size_t r = 0; r < sl->n_reads; ++r) {
-        const utb_result *v = &res[r];
+    for (size_t r = r0; r < r1; ++r) {
+        const utb_result *v = &f->res[r];
         if (v->kind == UTB_NONE) continue;
         ++g;
         memcpy(p, bytes + sl->name_off[r], sl->name_len[r]); p += sl->name_len[r];
@@ -196,19 +316,30 @@ static size_t format_batch(const utb_ctr *c, const slot_t *sl, const utb_result 
         else { p = put_u32(p, v->sl); *p++ = ';'; p = put_u32(p, v->ol); }
         *p++ = '\n';
     }
-    *good += g;
-    return (size_t)(p - out);
+    f->len[part] = (size_t)(p - f->buf[part]);
+    f->good[part] = g;
+}
+static void emit_part(void *c_, int part, int nparts) {
+    fmt_ctx *f = (fmt_ctx *)c_;
+    (void)nparts;
+    size_t n = f->len[part];
+    if (!n) return;
+    if (f->sink->fd < 0) { memcpy(f->sink->map + 64 + f->off[part], f->buf[part], n); return; }
+    const char *p = f->buf[part];
+    off_t o = (off_t)f->off[part];
+    while (n) {
+        ssize_t k = pwrite(f->sink->fd, p, n, o);
+        if (k < 0) { if (errno == EINTR) continue; f->sink->failed = 1; return; }
+        p += k; o += k; n -= (size_t)k;
+    }
 }
 
 static void *formatter_main(void *arg) {
     run_t *R = (run_t *)arg;
     utb_searcher *s = R->s;
-    size_t max_label = 0;
-    for (uint32_t i = 0; i < s->ctr->max_ix; ++i) {
-        size_t l = s->ctr->off[i + 1] - s->ctr->off[i];
-        if (l > max_label) max_label = l;
-    }
-    char *obuf = NULL; size_t ocap = 0;
+    fmt_ctx F;
+    memset(&F, 0, sizeof F);
+    F.c = s->ctr; F.max_label = s->max_label; F.sink = R->sink;
     for (uint64_t seq = 0;; ++seq) {
         pthread_mutex_lock(&R->mu);
         while (R->submitted <= seq && !R->done_reading) pthread_cond_wait(&R->cv, &R->mu);
@@ -220,15 +351,17 @@ static void *formatter_main(void *arg) {
         int rc = utb_batch_wait(sl->b, &res);
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
         if (!rc) {
-            /* worst case per line: name + label + 4 tabs + 4 numbers + newline */
-            size_t need = sl->n_bytes + sl->n_reads * (max_label + 64);
-            if (need > ocap) { free(obuf); ocap = need + (need >> 2); obuf = (char *)malloc(ocap); }
-            if (!obuf) { R->error = UTB_ERR_NOMEM; snprintf(R->errmsg, sizeof R->errmsg, "out of memory (formatter)"); ocap = 0; }
-            else {
-                size_t n = format_batch(s->ctr, sl, res, obuf, &R->st.good_finds);
-                sink_write(R->sink, obuf, n);
-                R->st.out_bytes += n;
+            F.sl = sl; F.res = res; F.bytes = utb_batch_bytes(sl->b);
+            team_run(&R->fmt_team, fmt_part, &F);
+            size_t tot = 0;
+            for (int p = 0; p < R->fmt_team.n; ++p) { F.off[p] = R->sink->off + tot; tot += F.len[p]; R->st.good_finds += F.good[p]; F.good[p] = 0; }
+            if (F.nomem) { R->error = UTB_ERR_NOMEM; snprintf(R->errmsg, sizeof R->errmsg, "out of memory (formatter)"); }
+            else if (!sink_reserve(R->sink, R->sink->off + tot)) {
+                team_run(&R->fmt_team, emit_part, &F);
+                R->sink->off += tot;
+                R->st.out_bytes += tot;
             }
+            for (int p = 0; p < R->fmt_team.n; ++p) F.len[p] = 0;
             uint64_t lk = 0, ht = 0; float ms[4] = {0, 0, 0, 0};
             utb_batch_counts(sl->b, &lk, &ht);
             utb_batch_last_ms(sl->b, ms);
@@ -246,77 +379,174 @@ static void *formatter_main(void *arg) {
         pthread_cond_broadcast(&R->cv);
         pthread_mutex_unlock(&R->mu);
     }
-    free(obuf);
+    for (int p = 0; p < MAX_TEAM; ++p) free(F.buf[p]);
     return NULL;
 }
 
-/* ---- framer ---------------------------------------------------------------- */
-/* Frames complete records of buf[0..fill) into the slot's tables, following
- * the reference reader (itree.c:866-890).  Returns the number of bytes
- * consumed; *fmt_err is set (with a message) when the record at the returned
- * position is malformed -- the records before it are still valid. */
-static size_t frame_records(slot_t *sl, size_t fill, int eof, size_t max_reads, uint64_t max_slots,
-                            uint64_t first_read, int *fmt_err, char *msg, size_t msglen, int *full) {
-    char *buf = utb_batch_bytes(sl->b);
-    uint64_t *seq_off = utb_batch_seq_off(sl->b);
-    uint32_t *seq_len = utb_batch_seq_len(sl->b);
-    size_t pos = 0, n = 0;
-    uint64_t groups = 0;
-    *fmt_err = 0; *full = 0;
-    while (pos < fill) {
-        char *h = buf + pos;
-        char *hnl = (char *)memchr(h, '\n', fill - pos);
-        if (!hnl && !eof) break;                                   /* header line incomplete */
-        size_t sstart = hnl ? (size_t)(hnl - buf) + 1 : fill;
-        if (sstart >= fill) {
-            if (!eof) break;
-            /* fgets for the sequence line fails: itree.c:871-872 */
-            snprintf(msg, msglen, "ERROR: can't read sequence L %llu", (unsigned long long)(first_read + n));
-            *fmt_err = 1; break;
-        }
-        char *sq = buf + sstart;
-        char *snl = (char *)memchr(sq, '\n', fill - sstart);
-        if (!snl && !eof) break;                                   /* sequence line incomplete */
-        size_t send = snl ? (size_t)(snl - buf) + 1 : fill;        /* one past the line incl. '\n' */
-        if ((size_t)(sstart - pos) >= UTB_LINELEN || send - sstart >= UTB_LINELEN) {
-            snprintf(msg, msglen, "ERROR: line longer than %u bytes near query %llu (limit of the reference reader)",
-                     UTB_LINELEN - 1, (unsigned long long)(first_read + n + 1));
-            *fmt_err = 1; break;
-        }
-        if (*h != '>') {                                           /* itree.c:880 */
-            snprintf(msg, msglen, "ERROR: no header '>' [L %llu]", (unsigned long long)(first_read + n + 1));
-            *fmt_err = 1; break;
-        }
-        if (*sq == '>') {                                          /* itree.c:886 */
-            snprintf(msg, msglen, "ERROR: sequence begins '>' [L %llu]", (unsigned long long)(first_read + n + 1));
-            *fmt_err = 1; break;
-        }
-        /* strlen(): an embedded NUL ends the line (itree.c:887) */
-        size_t length = send - sstart;
-        char *nul = (char *)memchr(sq, 0, length);
-        if (nul) length = (size_t)(nul - sq);
-        if (!length) {                                             /* itree.c:888 */
-            snprintf(msg, msglen, "ERROR: empty query line %llu", (unsigned long long)(first_read + n + 1));
-            *fmt_err = 1; break;
-        }
-        if (sq[length - 1] == '\n') --length;                      /* itree.c:889 */
-        if (length && sq[length - 1] == '\r') --length;            /* itree.c:890 */
-        uint64_t g = utb_read_slots((uint32_t)length);
-        if (n == max_reads || groups + g > max_slots) { *full = 1; break; }
-        /* name: after '>' up to the first ' ', '\n' or NUL (itree.c:881-882) */
-        size_t hl = (size_t)(sstart - pos);                        /* header line incl. '\n' if any */
-        size_t nl = 1;
-        while (nl < hl && h[nl] && h[nl] != ' ' && h[nl] != '\n') ++nl;
-        sl->name_off[n] = (uint32_t)(pos + 1);
-        sl->name_len[n] = (uint32_t)(nl - 1);
-        seq_off[n] = sstart;
-        seq_len[n] = (uint32_t)length;
-        groups += g;
-        ++n;
-        pos = send;
+/* ---- framer ----------------------------------------------------------------------------------- */
+/* The reference reads lines strictly in pairs (itree.c:869-871): line 2r is
+ * the header of record r, line 2r+1 its sequence, whatever they contain.  So
+ * a line's role follows from its index, which a parallel newline count gives:
+ * pass 1 counts '\n' per segment, pass 2 lets every worker parse the records
+ * whose header line starts right after a newline of its own segment. */
+enum { FE_NONE = 0, FE_NOHEADER, FE_SEQ_GT, FE_EMPTY, FE_TOOLONG };
+typedef struct {
+    const char *buf; size_t fill; int eof;
+    uint64_t *seq_off; uint32_t *seq_len; uint32_t *name_off, *name_len;
+    size_t cnt[MAX_TEAM];          /* newlines per segment */
+    size_t base[MAX_TEAM];         /* newlines before the segment */
+    size_t n_rec;                  /* complete records in the buffer (clamped to max_rec) */
+    size_t max_rec;                /* capacity of the per-read arrays */
+    size_t err_rec[MAX_TEAM]; int err_code[MAX_TEAM];
+    size_t end_of_records;         /* byte after the last complete record */
+} frame_ctx;
+
+static void count_part(void *c_, int part, int nparts) {
+    frame_ctx *c = (frame_ctx *)c_;
+    size_t a = c->fill * (size_t)part / (size_t)nparts, b = c->fill * (size_t)(part + 1) / (size_t)nparts;
+    size_t n = 0;
+    const char *p = c->buf + a, *e = c->buf + b;
+    while (p < e) {
+        const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        ++n; p = q + 1;
     }
-    sl->n_reads = n;
-    return pos;
+    c->cnt[part] = n;
+}
+
+/* Parses record r whose header line starts at s (itree.c:879-890). */
+static inline size_t parse_record(frame_ctx *c, size_t r, size_t s, int *err) {
+    const char *buf = c->buf;
+    size_t fill = c->fill;
+    const char *h = buf + s;
+    const char *hnl = (const char *)memchr(h, '\n', fill - s);
+    size_t sstart = (size_t)(hnl - buf) + 1;                       /* r < n_rec guarantees both lines exist */
+    const char *sq = buf + sstart;
+    const char *snl = sstart < fill ? (const char *)memchr(sq, '\n', fill - sstart) : NULL;
+    size_t send = snl ? (size_t)(snl - buf) + 1 : fill;            /* one past the line incl. '\n' */
+    *err = FE_NONE;
+    if (sstart - s >= UTB_LINELEN || send - sstart >= UTB_LINELEN) { *err = FE_TOOLONG; return send; }
+    if (*h != '>') { *err = FE_NOHEADER; return send; }            /* itree.c:880 */
+    if (*sq == '>') { *err = FE_SEQ_GT; return send; }             /* itree.c:886 */
+    size_t length = send - sstart;
+    const char *nul = (const char *)memchr(sq, 0, length);                     /* strlen(): itree.c:887 */
+    if (nul) length = (size_t)(nul - sq);
+    if (!length) { *err = FE_EMPTY; return send; }                 /* itree.c:888 */
+    if (sq[length - 1] == '\n') --length;                          /* itree.c:889 */
+    if (length && sq[length - 1] == '\r') --length;                /* itree.c:890 */
+    /* name: after '>' up to the first ' ', '\n' or NUL (itree.c:881-882) */
+    size_t hl = sstart - s, nl = 1;
+    while (nl < hl && h[nl] && h[nl] != ' ' && h[nl] != '\n') ++nl;
+    c->name_off[r] = (uint32_t)(s + 1);
+    c->name_len[r] = (uint32_t)(nl - 1);
+    c->seq_off[r] = sstart;
+    c->seq_len[r] = (uint32_t)length;
+    return send;
+}
+
+static void frame_part(void *c_, int part, int nparts) {
+    frame_ctx *c = (frame_ctx *)c_;
+    size_t a = c->fill * (size_t)part / (size_t)nparts, b = c->fill * (size_t)(part + 1) / (size_t)nparts;
+    c->err_rec[part] = (size_t)-1; c->err_code[part] = FE_NONE;
+    /* first line start owned by this segment, and its line index */
+    size_t s, L;
+    if (part == 0) { s = 0; L = 0; }
+    else {
+        const char *q = a < b ? (const char *)memchr(c->buf + a, '\n', b - a) : NULL;
+        if (!q) return;
+        s = (size_t)(q - c->buf) + 1; L = c->base[part] + 1;
+    }
+    for (;;) {
+        if (L & 1) {                                               /* a sequence line: its record belongs to whoever owns the header */
+            if (s >= b) return;
+            const char *q = (const char *)memchr(c->buf + s, '\n', b - s);
+            if (!q) return;
+            s = (size_t)(q - c->buf) + 1; ++L;
+            continue;
+        }
+        size_t r = L >> 1;
+        if (r >= c->n_rec) return;
+        int err;
+        size_t send = parse_record(c, r, s, &err);
+        if (err) { if (r < c->err_rec[part]) { c->err_rec[part] = r; c->err_code[part] = err; } }
+        if (r == c->n_rec - 1) c->end_of_records = send;
+        /* the next header starts after the sequence line's newline: ours iff that newline is in [a, b) */
+        if (send > b || send == 0 || c->buf[send - 1] != '\n') return;
+        if (send - 1 < a) return;
+        s = send; L += 2;
+        if (s > c->fill) return;
+    }
+}
+
+static const char *fe_text(int code) {
+    switch (code) {
+    case FE_NOHEADER: return "ERROR: no header '>'";
+    case FE_SEQ_GT: return "ERROR: sequence begins '>'";
+    case FE_EMPTY: return "ERROR: empty query line";
+    default: return "ERROR: line longer than the reference reader's 16777215-byte limit";
+    }
+}
+
+
+/* Frames buf[0..fill): on return *n_out records are valid (those before the
+ * first malformed one), *used is the byte after the last complete record,
+ * *err is FE_* of the record at index *n_out (or FE_NONE), *dangling tells
+ * that at EOF a header line is left without its sequence line. */
+static void frame_buffer(team_t *team, frame_ctx *F, size_t *n_out, size_t *n_complete, size_t *used, int *err, int *dangling) {
+    team_run(team, count_part, F);
+    size_t nl_total = 0;
+    for (int p = 0; p < team->n; ++p) { F->base[p] = nl_total; nl_total += F->cnt[p]; }
+    size_t n_lines = nl_total + ((F->eof && F->fill && F->buf[F->fill - 1] != '\n') ? 1 : 0);   /* a last line without '\n' counts at EOF */
+    F->n_rec = n_lines / 2;
+    *dangling = F->eof && (n_lines & 1);                       /* header whose sequence fgets fails (itree.c:871-872) */
+    if (F->n_rec > F->max_rec) { F->n_rec = F->max_rec; *dangling = 0; }   /* the rest comes back with the carry */
+    F->end_of_records = 0;
+    for (int p = 0; p < team->n; ++p) { F->err_rec[p] = (size_t)-1; F->err_code[p] = FE_NONE; }
+    if (F->n_rec) team_run(team, frame_part, F);
+    size_t n = F->n_rec; *err = FE_NONE;
+    for (int p = 0; p < team->n; ++p) if (F->err_rec[p] < n) { n = F->err_rec[p]; *err = F->err_code[p]; }
+    *n_out = n; *n_complete = F->n_rec; *used = F->end_of_records;
+}
+
+/* Host-stage entry points (CPU-only tests drive the framer and the formatter through these). */
+int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t max_reads,
+                      uint64_t *seq_off, uint32_t *seq_len, uint32_t *name_off, uint32_t *name_len,
+                      size_t *n_reads, size_t *used, int *ref_exit) {
+    if ((!buf && n) || !seq_off || !seq_len || !name_off || !name_len || !n_reads || !used) { utb_set_error("utb_frame_records: null argument"); return UTB_ERR_ARG; }
+    if (ref_exit) *ref_exit = 0;
+    *n_reads = 0; *used = 0;
+    if (!n) return UTB_OK;
+    team_t team;
+    if (team_init(&team, threads)) { utb_set_error("cannot start worker threads"); return UTB_ERR_NOMEM; }
+    frame_ctx F;
+    memset(&F, 0, sizeof F);
+    F.buf = buf; F.fill = n; F.eof = eof; F.max_rec = max_reads;
+    F.seq_off = seq_off; F.seq_len = seq_len; F.name_off = name_off; F.name_len = name_len;
+    size_t nr, nc, u; int err, dangling;
+    frame_buffer(&team, &F, &nr, &nc, &u, &err, &dangling);
+    team_destroy(&team);
+    *n_reads = nr; *used = u;
+    if (err) { utb_set_error("%s [L %zu]", fe_text(err), nr + 1); if (ref_exit) *ref_exit = 2; return UTB_ERR_FORMAT; }
+    if (dangling) { utb_set_error("ERROR: can't read sequence L %zu", nr); if (ref_exit) *ref_exit = 2; return UTB_ERR_FORMAT; }
+    return UTB_OK;
+}
+
+int utb_format_results(const utb_ctr *ctr, const char *bytes, const uint32_t *name_off, const uint32_t *name_len,
+                       const utb_result *results, size_t n_reads, char *out, size_t out_cap, size_t *out_len) {
+    if (!ctr || !bytes || !name_off || !name_len || !results || !out || !out_len) { utb_set_error("utb_format_results: null argument"); return UTB_ERR_ARG; }
+    slot_t sl; memset(&sl, 0, sizeof sl);
+    sl.n_reads = n_reads; sl.name_off = (uint32_t *)name_off; sl.name_len = (uint32_t *)name_len;
+    fmt_ctx F; memset(&F, 0, sizeof F);
+    F.c = ctr; F.sl = &sl; F.res = results; F.bytes = bytes;
+    for (uint32_t i = 0; i < ctr->max_ix; ++i) { size_t l = ctr->off[i + 1] - ctr->off[i]; if (l > F.max_label) F.max_label = l; }
+    fmt_part(&F, 0, 1);
+    if (F.nomem) { utb_set_error("out of memory (formatter)"); return UTB_ERR_NOMEM; }
+    int rc = UTB_OK;
+    if (F.len[0] > out_cap) { utb_set_error("utb_format_results: output needs %zu bytes", F.len[0]); rc = UTB_ERR_LIMIT; }
+    else memcpy(out, F.buf[0], F.len[0]);
+    *out_len = F.len[0];
+    free(F.buf[0]);
+    return rc;
 }
 
 static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, utb_stats *stats, int *ref_exit) {
@@ -329,6 +559,10 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     double t0 = now_s();
     uint64_t launches0 = 0;
     for (int i = 0; i < s->n_slots; ++i) { s->slots[i].state = 0; launches0 += utb_batch_launches(s->slots[i].b); }
+    /* split the host threads between the two teams */
+    int T = s->host_threads, n_rd = T >= 4 ? T / 2 : 1, n_fm = T >= 4 ? T - n_rd : 1;
+    team_t rd_team;
+    if (team_init(&rd_team, n_rd) || team_init(&R.fmt_team, n_fm)) { utb_set_error("cannot start worker threads"); return UTB_ERR_NOMEM; }
     pthread_t fmt;
     if (pthread_create(&fmt, NULL, formatter_main, &R)) { utb_set_error("cannot start formatter thread"); return UTB_ERR_NOMEM; }
 
@@ -349,27 +583,49 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         size_t cap = utb_batch_max_bytes(sl->b), fill = carry_len;
         if (carry_len) memcpy(buf, carry, carry_len);
         carry_len = 0;
-        if (!src->eof) {
-            ssize_t k = src_read(src, buf + fill, cap - fill);
-            if (k < 0) { rc = UTB_ERR_IO; utb_set_error("read error on input: %s", strerror(errno)); break; }
-            fill += (size_t)k;
-        }
+        ssize_t k = src_fill(src, &rd_team, buf + fill, cap - fill);
+        if (k < 0) { rc = UTB_ERR_IO; utb_set_error("read error on input: %s", strerror(errno)); break; }
+        fill += (size_t)k;
         if (!fill) break;                                          /* clean EOF */
-        int full = 0;
-        size_t used = frame_records(sl, fill, src->eof, utb_batch_max_reads(sl->b), utb_batch_max_slots(sl->b),
-                                    n_reads_total, &fmt_err, fmt_msg, sizeof fmt_msg, &full);
-        if (!fmt_err && used == 0 && !full && fill == cap) {
+
+        frame_ctx F;
+        memset(&F, 0, sizeof F);
+        F.buf = buf; F.fill = fill; F.eof = src->eof; F.max_rec = utb_batch_max_reads(sl->b);
+        F.seq_off = utb_batch_seq_off(sl->b); F.seq_len = utb_batch_seq_len(sl->b);
+        F.name_off = sl->name_off; F.name_len = sl->name_len;
+        size_t n, n_complete, end_of_records; int err_code, dangling;
+        frame_buffer(&rd_team, &F, &n, &n_complete, &end_of_records, &err_code, &dangling);
+        if (err_code) { fmt_err = 1; snprintf(fmt_msg, sizeof fmt_msg, "%s [L %llu]", fe_text(err_code), (unsigned long long)(n_reads_total + n + 1)); }
+        /* capacity: reads and 32-base position groups */
+        size_t max_reads = utb_batch_max_reads(sl->b);
+        uint64_t max_slots = utb_batch_max_slots(sl->b), groups = 0;
+        int cut = 0;
+        if (n > max_reads) { n = max_reads; cut = 1; }
+        for (size_t r = 0; r < n; ++r) {
+            uint64_t g = utb_read_slots(F.seq_len[r]);
+            if (groups + g > max_slots) { n = r; cut = 1; break; }
+            groups += g;
+        }
+        if (cut) fmt_err = 0;                                      /* the bad record, if any, comes back with the carry */
+        size_t used = (n == n_complete) ? end_of_records : (size_t)sl->name_off[n] - 1;
+        if (!fmt_err && !cut && dangling && n == n_complete) {
+            fmt_err = 1;
+            snprintf(fmt_msg, sizeof fmt_msg, "ERROR: can't read sequence L %llu", (unsigned long long)(n_reads_total + n));
+        }
+        if (!fmt_err && n == 0 && !cut && !src->eof && fill == cap) {
             fmt_err = 1;
             snprintf(fmt_msg, sizeof fmt_msg, "ERROR: record larger than the %zu-byte batch buffer", cap);
         }
-        sl->n_bytes = used;
+        sl->n_reads = n;
+        sl->n_bytes = fmt_err ? fill : used;
         sl->first_read = n_reads_total;
-        n_reads_total += sl->n_reads;
+        n_reads_total += n;
         if (!fmt_err && used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
-        if (sl->n_reads) {
-            int r2 = utb_batch_submit(sl->b, used, sl->n_reads, do_rc);
+        if (n) {
+            /* every sequence lies inside the first n_bytes of the buffer */
+            int r2 = utb_batch_submit(sl->b, fmt_err ? fill : used, n, do_rc);
             if (r2) { rc = r2; break; }
-            R.st.h2d_bytes += used + sl->n_reads * 16 + 4;
+            R.st.h2d_bytes += (fmt_err ? fill : used) + n * 16 + 4;
             pthread_mutex_lock(&R.mu);
             sl->state = 1;
             R.submitted = ++seq;
@@ -384,12 +640,14 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     pthread_cond_broadcast(&R.cv);
     pthread_mutex_unlock(&R.mu);
     pthread_join(fmt, NULL);
+    team_destroy(&rd_team);
+    team_destroy(&R.fmt_team);
     free(carry);
     pthread_mutex_destroy(&R.mu);
     pthread_cond_destroy(&R.cv);
     if (!rc && R.error) { rc = R.error; utb_set_error("%s", R.errmsg); }
     if (!rc && sink->failed) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
-    R.st.reads = n_reads_total + (fmt_err ? 1 : 0);                /* the reference counts the bad record too */
+    R.st.reads = n_reads_total;
     R.st.batches = seq;
     for (int i = 0; i < s->n_slots; ++i) R.st.kernel_launches += utb_batch_launches(s->slots[i].b);
     R.st.kernel_launches -= launches0;
@@ -409,16 +667,14 @@ int utb_search_file(utb_searcher *s, const char *fasta_path, const char *out_pat
     if (ref_exit) *ref_exit = 0;
     int fd = open(fasta_path, O_RDONLY);
     if (fd < 0) { utb_set_error("Invalid input files"); if (ref_exit) *ref_exit = 1; return UTB_ERR_IO; }   /* itree.c:835 */
-#ifdef POSIX_FADV_SEQUENTIAL
-    posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-#endif
-    FILE *fo = fopen(out_path, "wb");
-    if (!fo) { close(fd); utb_set_error("cannot open output file %s", out_path); if (ref_exit) *ref_exit = 1; return UTB_ERR_IO; }
-    setvbuf(fo, NULL, _IOFBF, (size_t)4 << 20);
+    int fo = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fo < 0) { close(fd); utb_set_error("cannot open output file %s", out_path); if (ref_exit) *ref_exit = 1; return UTB_ERR_IO; }
     source_t src; memset(&src, 0, sizeof src); src.fd = fd;
-    sink_t sink; memset(&sink, 0, sizeof sink); sink.fp = fo;
+    struct stat st;
+    if (!fstat(fd, &st) && S_ISREG(st.st_mode)) { src.seekable = 1; src.file_size = st.st_size; if (!st.st_size) src.eof = 1; }
+    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = fo;
     int rc = run_search(s, &src, &sink, do_rc, stats, ref_exit);
-    if (fclose(fo) && !rc) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
+    if (close(fo) && !rc) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
     close(fd);
     return rc;
 }
@@ -427,13 +683,13 @@ int utb_search_mem(utb_searcher *s, const char *fasta, size_t n, int do_rc,
                    char **out, size_t *out_len, utb_stats *stats, int *ref_exit) {
     if (!s || (!fasta && n) || !out || !out_len) { utb_set_error("utb_search_mem: null argument"); return UTB_ERR_ARG; }
     source_t src; memset(&src, 0, sizeof src); src.fd = -1; src.mem = fasta; src.mem_len = n; src.eof = n == 0;
-    sink_t sink; memset(&sink, 0, sizeof sink);
+    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = -1;
     int rc = run_search(s, &src, &sink, do_rc, stats, ref_exit);
-    *out = sink.mem; *out_len = sink.len;
+    *out = sink.map ? sink.map + 64 : NULL; *out_len = sink.off;
     return rc;
 }
 
-/* ---- CLI (itree.c:1357-1377; stdout lines of SURVEY App. C) ---------------- */
+/* ---- CLI (itree.c:1357-1377; stdout lines of SURVEY App. C) -------------------------------------- */
 static const char *TYPEARR[9] = {"NA", "uint8_t", "uint16_t", "NA", "uint32_t", "NA", "NA", "NA", "uint64_t"};
 
 int utb_main(int argc, char **argv) {
@@ -484,7 +740,7 @@ int utb_main(int argc, char **argv) {
     int ref_exit = 0;
     rc = utb_search_file(s, argv[2], argv[3], do_rc, &st, &ref_exit);
     if (rc == UTB_ERR_IO && ref_exit == 1) { puts(utb_last_error()); utb_searcher_destroy(s); utb_ctr_close(ctr); return 1; }
-    if (rc == UTB_ERR_FORMAT && ref_exit) {                        /* output so far is flushed, as exit() does */
+    if (rc == UTB_ERR_FORMAT && ref_exit) {                        /* output so far is on disk, as after the reference's exit() */
         fflush(stdout);
         fprintf(stderr, "%s\n", utb_last_error());
         utb_searcher_destroy(s); utb_ctr_close(ctr);
