@@ -282,8 +282,8 @@ def main():
     t0 = time.time()
     e2e_stats = []
     for _ in range(args.steps):
-        rc_, ex, text, st = searcher.search_mem(None, do_rc=True, ptr=ptr, n=reads_np.size)
-        assert rc_ == 0
+        rc_, ex, nbytes, st = searcher.search_mem(None, do_rc=True, ptr=ptr, n=reads_np.size, copy=False)
+        assert rc_ == 0 and nbytes == len(out_text)
         e2e_stats.append(st)
     barrier()
     e2e_s = time.time() - t0
@@ -320,7 +320,8 @@ def main():
         lookup_ms = ms_sum[1] / args.steps
         alg_bytes = sect["bytes_per_lookup"] * lookups
         achieved = alg_bytes / (lookup_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "lookup_kernel<2>", "achieved": round(achieved, 1), "peak": round(rand32, 1),
+        mode = "interpolation-start (regular CTR)" if db.lookup_mode() else "reference probe sequence"
+        roofline = {"bound": "hbm", "kernel": f"lookup_kernel<2,{'true' if db.lookup_mode() else 'false'}> ({mode})", "achieved": round(achieved, 1), "peak": round(rand32, 1),
                     "unit": "GB/s", "frac": round(achieved / rand32, 4), "traffic": None,
                     "peak_kind": "measured random 32B-sector gather, 8 GiB working set (utb_measure_rand32)",
                     "stream_peak": stream_peak, "stream_peak_kind": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
@@ -351,7 +352,9 @@ def main():
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload,
             "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]),
                     "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": round(e2e_s_max * 1e3 / args.steps, 1),
-                    "api": "utb_search_mem (host FASTA buffer -> host text)", "out_bytes_per_step": int(st["out_bytes"])},
+                    "api": "utb_search_mem (host FASTA buffer -> host text)", "out_bytes_per_step": int(st["out_bytes"]),
+                    "host_phase_s": {k: round(st[k], 3) for k in ("rd_wait_slot", "rd_fill", "rd_frame", "rd_submit",
+                                                                 "fm_wait_gpu", "fm_format", "fm_emit", "seconds_device")}},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "db": {"records": int(ctr.num_nodes), "labels": int(ctr.max_ix), "file_bytes": ctr_meta["bytes"],
                    "hbm_bytes": int(db.hbm_bytes()), "load_s": round(db_load_s, 1)},

@@ -64,6 +64,10 @@ int utb_device_count(int *n);
 int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out);
 void utb_db_free(utb_db *db);
 uint64_t utb_db_hbm_bytes(const utb_db *db);
+/* 1 when every bucket of the CTR is strictly sorted (what utree-compress
+ * emits; the first-bin quirk is handled) and the interpolation-start lookup
+ * is in use, 0 when the reference's probe sequence is emulated verbatim. */
+int utb_db_lookup_mode(const utb_db *db);
 
 /* ---- per-read result record (what the vote leaves for the formatter) ------ */
 enum { UTB_NONE = 0, UTB_STAR = 1, UTB_WALK = 2 };
@@ -153,6 +157,9 @@ typedef struct {
     uint64_t out_bytes;
     double seconds_total;  /* wall, excludes DB upload                         */
     double seconds_device; /* sum of CUDA-event time over batches (all GPUs)   */
+    /* where the two host threads' wall time went (seconds) */
+    double rd_wait_slot, rd_fill, rd_frame, rd_submit;   /* reader team leader   */
+    double fm_wait_gpu, fm_format, fm_emit;              /* formatter team leader */
 } utb_stats;
 
 typedef struct utb_searcher utb_searcher;

@@ -211,3 +211,66 @@ def test_synthetic_ctr_equals_reference_built_tree(built, tmp_path, complevel):
         assert code == 0 and text == outs[1]
     finally:
         s.destroy(); ctr.close()
+
+
+def _lookup_probe_words(words, rng):
+    w = np.concatenate([words, words + np.uint64(1), words - np.uint64(1),
+                        (words & ~np.uint64(0xFFFFFFFFFF)) | rng.integers(0, 1 << 40, words.size, dtype=np.uint64),
+                        (words & ~np.uint64(0xFFFFFFFFFF)), (words | np.uint64(0xFFFFFFFFFF)),
+                        rng.integers(0, np.iinfo(np.uint64).max, 5000, dtype=np.uint64)])
+    return w[rng.permutation(w.size)[:60000]]
+
+
+@pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
+def test_both_lookup_variants_match_oracle(built, ctrs, name):
+    """Interpolation-start search (regular CTRs) and the exact-probe kernel give XT_getIX32's answer."""
+    from utree_b200 import capi, synth
+    words, _, _, _ = synth.ubt_read(gold(name + ".ubt"))
+    w = _lookup_probe_words(words, np.random.default_rng(17))
+    orc = capi.OracleDb(ctrs[name])
+    want = orc.lookup_many(w)
+    orc.free()
+    ctr = capi.Ctr(ctrs[name])
+    try:
+        for env, mode in ((None, 1), ("exact", 0)):
+            if env:
+                os.environ["UTB_LOOKUP"] = env
+            try:
+                db = capi.Db(ctr, 0)
+            finally:
+                os.environ.pop("UTB_LOOKUP", None)
+            assert db.lookup_mode() == mode          # every reference-compressed tree is regular
+            assert np.array_equal(db.lookup_words(w), want), (name, env)
+            db.free()
+    finally:
+        ctr.close()
+
+
+def test_irregular_ctr_takes_the_exact_probe_path(built, tmp_path):
+    """A CTR with an unsorted bucket (never produced by utree-compress): the loader detects it
+    and the device emulates xtSuffixBS's probe sequence, matching the oracle hit for hit."""
+    from utree_b200 import capi, synth
+    rng = np.random.default_rng(23)
+    words, ixs, tail, _ = synth.ubt_read(gold("dense.ubt"))
+    binix = synth.binix_like_reference(words)
+    shuffled = words.copy()
+    pre = words >> np.uint64(40)
+    for p in np.unique(pre)[3::4]:                      # shuffle every 4th bucket in place
+        idx = np.flatnonzero(pre == p)
+        shuffled[idx] = shuffled[rng.permutation(idx)]
+    path = str(tmp_path / "irregular.ctr")
+    synth.ctr_write(path, shuffled, ixs, tail, 2, binix=binix)
+    ctr, orc = capi.Ctr(path), capi.OracleDb(path)
+    db = capi.Db(ctr, 0)
+    try:
+        assert db.lookup_mode() == 0
+        w = _lookup_probe_words(words, rng)
+        assert np.array_equal(db.lookup_words(w), orc.lookup_many(w))
+        s = capi.Searcher(ctr, devices=(0,), host_threads=2)
+        o1, o2 = str(tmp_path / "a.out"), str(tmp_path / "b.out")
+        code, _, _ = s.search_file(gold("dense_reads.fa"), o1, do_rc=True)
+        orc.search_file(gold("dense_reads.fa"), o2, do_rc=True)
+        assert code == 0 and open(o1, "rb").read() == open(o2, "rb").read()
+        s.destroy()
+    finally:
+        db.free(); ctr.close(); orc.free()

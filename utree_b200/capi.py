@@ -35,7 +35,8 @@ RESULT_DTYPE = np.dtype([(n, "<u4") for n in ("kind", "label", "cut", "found", "
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("reads", "good_finds", "lookups", "hits", "batches",
                                           "kernel_launches", "h2d_bytes", "d2h_bytes", "out_bytes")] + \
-               [("seconds_total", C.c_double), ("seconds_device", C.c_double)]
+               [(n, C.c_double) for n in ("seconds_total", "seconds_device", "rd_wait_slot", "rd_fill", "rd_frame",
+                                          "rd_submit", "fm_wait_gpu", "fm_format", "fm_emit")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -45,7 +46,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "utb_last_error", "utb_ctr_open", "utb_ctr_close", "utb_ctr_num_nodes", "utb_ctr_ix_bytes",
     "utb_ctr_binix_bytes", "utb_ctr_max_ix", "utb_ctr_last_bin", "utb_ctr_label", "utb_ctr_label_rank",
-    "utb_device_count", "utb_db_upload", "utb_db_free", "utb_db_hbm_bytes",
+    "utb_device_count", "utb_db_upload", "utb_db_free", "utb_db_hbm_bytes", "utb_db_lookup_mode",
     "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
     "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
     "utb_batch_submit", "utb_batch_wait", "utb_batch_rerun_device", "utb_batch_counts",
@@ -206,6 +207,11 @@ class Db:
     def hbm_bytes(self):
         return lib().utb_db_hbm_bytes(self.h)
 
+    def lookup_mode(self):
+        """1: interpolation-start search (regular CTR); 0: reference probe sequence."""
+        lib().utb_db_lookup_mode.argtypes = [C.c_void_p]
+        return lib().utb_db_lookup_mode(self.h)
+
     def free(self):
         if self.h:
             lib().utb_db_free(self.h)
@@ -269,14 +275,17 @@ class Searcher:
         rc = lib().utb_search_file(self.h, os.fsencode(fasta), os.fsencode(out), int(do_rc), C.byref(st), C.byref(ex))
         return rc, ex.value, st.as_dict()
 
-    def search_mem(self, fasta: bytes, do_rc=True, ptr=None, n=None):
+    def search_mem(self, fasta: bytes, do_rc=True, ptr=None, n=None, copy=True):
+        """copy=False: the output text is not copied into Python (returns its length instead)."""
         st, ex = Stats(), C.c_int()
         out, out_len = C.c_void_p(), C.c_size_t()
         if ptr is None:
             keep = C.create_string_buffer(fasta, len(fasta))
             ptr, n = C.addressof(keep), len(fasta)
         rc = lib().utb_search_mem(self.h, ptr, n, int(do_rc), C.byref(out), C.byref(out_len), C.byref(st), C.byref(ex))
-        data = C.string_at(out.value, out_len.value) if out.value else b""
+        data = out_len.value
+        if copy:
+            data = C.string_at(out.value, out_len.value) if out.value else b""
         if out.value:
             lib().utb_free(out)
         return rc, ex.value, data, st.as_dict()

@@ -58,15 +58,28 @@ struct DevDB {
     const uint32_t *off;
     const uint32_t *rank;
     const uint32_t *by_rank;
+    uint32_t quirk_bin;        // bucket whose record 0 is the folded foreign record, else 0xFFFFFFFF
+    // regular CTRs only: structure-of-arrays copy of the records (recs is then freed)
+    const uint32_t *keys;      // suffix >> 8
+    const uint32_t *aux32;     // suffix & 0xFF | id << 8   (IXTYPE uint16_t)
+    const uint64_t *aux64;     // same, IXTYPE uint32_t
+    // membership pre-filter over all record words (register-blocked Bloom, 16-byte blocks)
+    const uint4 *bloom;
+    uint64_t bloom_blocks;
 };
 
 struct utb_db {
     int device;
     DevDB d;
-    void *binix, *recs, *blob, *off, *rank, *by_rank;
+    int regular;               // every bucket strictly sorted (modulo quirk_bin): interpolation search is exact
+    int use_interp;            // lookup kernel variant in use
+    void *binix, *recs, *blob, *off, *rank, *by_rank, *keys, *aux, *bloom;
+    int bloom_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
+    double ema_hit_rate;       // of the batches seen so far
     uint64_t hbm_bytes;
     int l2_window;             // persisting-L2 window over binix configured
     size_t l2_window_bytes;
+    float l2_hit_ratio;
 };
 
 // ---------------------------------------------------------------------------
@@ -219,47 +232,345 @@ __device__ __forceinline__ uint32_t probe_end(const DevDB &db, const Probe &q) {
     return ix < db.max_ix ? ix : HIT_MISS;                                // itree.c:929
 }
 
-// One thread per position of the packed super-sequence; forward and reverse
-// complement lookups of that window run in lock-step (two independent
-// dependent-load chains per thread).
-template <int NSTR>
-__global__ void __launch_bounds__(256)
-lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
-              uint32_t n_pos, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
-    uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
-    uint64_t w = 0;
-    bool valid = pos < n_pos && window_at(pk, bad, pos, w);
-    uint32_t r[NSTR];
+
+// ---- key-window search (regular CTRs only) -----------------------------------
+// What bounds the exact-probe kernel is not bytes but the chain of dependent
+// loads a warp has to wait for (profiles/r01_*: DRAM ~35 % busy, all warps
+// resident, ~8 serialized round trips per lookup).  For a regular CTR (every
+// bucket strictly sorted -- verified on the device at upload) the records are
+// therefore re-laid out once, at load time, as structure-of-arrays:
+//     keys[i] = suffix >> 8   (u32, 16 keys per 64-byte line)
+//     aux[i]  = suffix & 0xFF | id << 8
+// Suffixes are close to uniform inside a bucket, so record a + n*s/2^40 is
+// within a few slots of the answer: ONE aligned 64-byte vector load around it
+// holds the 16 candidate keys, which are ranked branch-free in registers.  A
+// lookup is then index -> key line -> (hits only) aux: 2-3 dependent steps
+// instead of ~8, and ~1.3 random DRAM fetches instead of ~5.  On a strictly
+// sorted bucket any exact membership test returns what xtSuffixBS returns, so
+// the result is identical; CTRs that are not regular keep the exact kernel.
+enum { FW_MISS = 0, FW_FOUND = 1, FW_LEFT = 2, FW_RIGHT = 3, FW_SLOW = 4 };
+#define KW 8u                   // keys per window = one 32-byte sector
+struct FastProbe {
+    uint64_t a, b;      // bucket [a,b), quirk-adjusted
+    uint64_t ws;        // first key of the current window (multiple of KW)
+    uint64_t pos;       // FW_FOUND: index of the only key equal to t in the window
+    uint32_t t, lo8;    // target key and the suffix's low byte
+    int st;
+};
+__device__ __forceinline__ void fast_begin(const DevDB &db, uint64_t word, FastProbe &q) {
+    uint64_t p = word >> 40;
+    uint64_t a, b;
+    if (db.binix32) { a = __ldg(db.binix32 + p); b = __ldg(db.binix32 + p + 1); }
+    else { a = __ldg(db.binix64 + p); b = __ldg(db.binix64 + p + 1); }
+    uint64_t suf = word & SUFMASK;
+    q.t = (uint32_t)(suf >> 8); q.lo8 = (uint32_t)(suf & 0xFFu);
+    bool live = a < b && b <= db.num_nodes;                        // itree.c:726 (+ bounds guard)
+    if (live && (uint32_t)p == db.quirk_bin) { a += 1; live = a < b; }   // record 0 is unreachable for xtSuffixBS
+    q.a = a; q.b = b; q.pos = 0;
+    q.st = live ? FW_LEFT : FW_MISS;                               // any non-final state: "window pending"
+    q.ws = live ? ((a + __umul64hi(suf << 24, b - a)) & ~(uint64_t)(KW - 1)) : 0;   // a + floor(n*s/2^40) < b
+}
+// One sector of keys around the estimate.  The miss fills the whole 128-byte
+// line in L2, so the neighbouring sectors a later step may need are L2 hits;
+// asking for them up front would cost as much as further misses
+// (profiles/r01_membench_ncu.txt).
+__device__ __forceinline__ void window_step(const DevDB &db, FastProbe &q) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(db.keys + q.ws);
+    const uint4 k0 = __ldg(p), k1 = __ldg(p + 1);
+    const uint32_t kk[KW] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+    const uint64_t wa = q.ws > q.a ? q.ws : q.a, wb = q.ws + KW < q.b ? q.ws + KW : q.b;
+    const uint32_t j0 = (uint32_t)(wa - q.ws), j1 = (uint32_t)(wb - q.ws);   // in-bucket slots [j0, j1)
+    uint32_t lt = 0, eq = 0;
 #pragma unroll
-    for (int s = 0; s < NSTR; ++s) r[s] = HIT_NOWIN;
-    if (valid) {
-        Probe q[NSTR];
-        probe_begin(db, w, q[0]);
-        if (NSTR == 2) probe_begin(db, revcomp_word(w), q[NSTR - 1]);
-        probe_run<NSTR>(db, q);
-#pragma unroll
-        for (int s = 0; s < NSTR; ++s) r[s] = probe_end(db, q[s]);
+    for (uint32_t j = 0; j < KW; ++j) {
+        bool in = j >= j0 && j < j1;
+        lt += in && kk[j] < q.t;
+        eq += in && kk[j] == q.t;
     }
-    if (pos < n_pos) {
-        if (NSTR == 2) reinterpret_cast<uint2 *>(hits)[pos] = make_uint2(r[0], r[1]);
-        else hits[pos] = r[0];
+    const bool left_open = wa > q.a, right_open = wb < q.b;
+    if (eq == 0) {
+        if (lt == 0 && left_open) { q.st = FW_LEFT; q.ws -= KW; }             // every key here is larger
+        else if (lt == j1 - j0 && right_open) { q.st = FW_RIGHT; q.ws += KW; } // every key here is smaller
+        else q.st = FW_MISS;
+    } else if (eq == 1) { q.st = FW_FOUND; q.pos = wa + lt; }
+    else q.st = FW_SLOW;                                           // equal 32-bit keys: needs the low byte to order
+}
+__device__ __forceinline__ uint64_t load_aux(const DevDB &db, uint64_t i) {
+    return db.aux32 ? (uint64_t)__ldg(db.aux32 + i) : __ldg(db.aux64 + i);
+}
+// rare: exact lower bound over the whole bucket on the full 40-bit suffix
+__device__ __noinline__ uint32_t fast_slow(const DevDB &db, uint64_t a, uint64_t b, uint32_t t, uint32_t lo8) {
+    const uint64_t s = ((uint64_t)t << 8) | lo8;
+    uint64_t lo = a, hi = b;
+    while (lo < hi) {
+        uint64_t mid = (lo + hi) >> 1;
+        uint64_t c = ((uint64_t)__ldg(db.keys + mid) << 8) | (load_aux(db, mid) & 0xFFu);
+        if (c < s) lo = mid + 1; else hi = mid;
     }
-    int nh = 0;
+    if (lo >= b) return HIT_MISS;
+    uint64_t ax = load_aux(db, lo);
+    if ((((uint64_t)__ldg(db.keys + lo) << 8) | (ax & 0xFFu)) != s) return HIT_MISS;
+    uint32_t ix = (uint32_t)(ax >> 8);
+    return ix < db.max_ix ? ix : HIT_MISS;
+}
+#define FW_MAX_STEPS 4          // sectors inspected before giving up on the estimate
+template <int N>
+__device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)[N], uint32_t (&r)[N]) {
+    FastProbe q[N];
 #pragma unroll
-    for (int s = 0; s < NSTR; ++s) nh += r[s] < HIT_NOWIN;
-    int nvalid = __syncthreads_count(valid);
-    int nhit1 = __syncthreads_count(nh >= 1);
-    int nhit2 = __syncthreads_count(nh >= 2);
-    if (threadIdx.x == 0) {
-        if (nvalid) atomicAdd(counters + 0, (unsigned long long)nvalid * NSTR);
-        if (nhit1 + nhit2) atomicAdd(counters + 1, (unsigned long long)(nhit1 + nhit2));
+    for (int i = 0; i < N; ++i) fast_begin(db, w[i], q[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if (q[i].st == FW_MISS) continue;                          // empty bucket
+        int dir = 0;                                               // direction of the last move
+        for (int step = 0; step < FW_MAX_STEPS; ++step) {
+            window_step(db, q[i]);
+            if (q[i].st != FW_LEFT && q[i].st != FW_RIGHT) break;
+            if (dir && q[i].st != dir) { q[i].st = FW_MISS; break; }   // turned around: the target falls between two adjacent windows
+            dir = q[i].st;
+        }
+        if (q[i].st == FW_LEFT || q[i].st == FW_RIGHT) q[i].st = FW_SLOW;   // estimate off by several sectors
+    }
+    // hits fetch low byte + id; a neighbour key is checked when the match sits on a window edge
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        r[i] = HIT_MISS;
+        if (q[i].st == FW_FOUND) {
+            const uint64_t ax = load_aux(db, q[i].pos);
+            uint32_t nb = ~q[i].t;
+            const uint64_t wa = q[i].ws > q[i].a ? q[i].ws : q[i].a, wb = q[i].ws + KW < q[i].b ? q[i].ws + KW : q[i].b;
+            if (q[i].pos == wa && wa > q[i].a) nb = __ldg(db.keys + q[i].pos - 1);
+            else if (q[i].pos == wb - 1 && wb < q[i].b) nb = __ldg(db.keys + q[i].pos + 1);
+            if (nb == q[i].t) q[i].st = FW_SLOW;                   // the run of equal keys crosses the window
+            else if ((uint32_t)(ax & 0xFFu) == q[i].lo8) { uint32_t ix = (uint32_t)(ax >> 8); r[i] = ix < db.max_ix ? ix : HIT_MISS; }
+        }
+        if (q[i].st == FW_SLOW) r[i] = fast_slow(db, q[i].a, q[i].b, q[i].t, q[i].lo8);
     }
 }
 
+// raw CTR records -> SoA (runs once at upload, only for regular CTRs)
+__global__ void __launch_bounds__(256)
+relayout_kernel(DevDB db, uint32_t *__restrict__ keys, uint32_t *__restrict__ aux32, uint64_t *__restrict__ aux64) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= db.num_nodes) return;
+    uint64_t suf = load_suffix(db.recs, i * db.sz);
+    uint32_t ix = load_ix(db, i);
+    keys[i] = (uint32_t)(suf >> 8);
+    if (aux32) aux32[i] = (uint32_t)(suf & 0xFFu) | (ix << 8);
+    else aux64[i] = (suf & 0xFFu) | ((uint64_t)ix << 8);
+}
+
+// Load-time check of the invariant the interpolation search relies on.
+// out[0] buckets with a disorder past their first pair (or an index beyond the blob)
+// out[1] buckets whose only disorder is record0 >= record1   out[2] smallest such bin
+// out[3] first non-empty bin
+__global__ void __launch_bounds__(256)
+verify_kernel(DevDB db, unsigned long long *__restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= UTB_NUMBINS - 1) return;
+    uint64_t a, b;
+    if (db.binix32) { a = db.binix32[p]; b = db.binix32[p + 1]; }
+    else { a = db.binix64[p]; b = db.binix64[p + 1]; }
+    if (a >= b) return;                                            // empty for XT_getIX32 (itree.c:726)
+    if (b > db.num_nodes) { atomicAdd(out + 0, 1ull); return; }
+    atomicMin(out + 3, (unsigned long long)p);
+    uint64_t prev = load_suffix(db.recs, a * db.sz);
+    bool first_bad = false, rest_bad = false;
+    for (uint64_t i = a + 1; i < b; ++i) {
+        uint64_t cur = load_suffix(db.recs, i * db.sz);
+        if (cur <= prev) { if (i == a + 1) first_bad = true; else rest_bad = true; }
+        prev = cur;
+    }
+    if (rest_bad) atomicAdd(out + 0, 1ull);
+    else if (first_bad) { atomicAdd(out + 1, 1ull); atomicMin(out + 2, (unsigned long long)p); }
+}
+
+// ---- membership pre-filter ----------------------------------------------------
+// Most 32-mers of a read are not in a sampled tree (complevel 2 keeps 1/16 of
+// the k-mers), and every miss costs the exact path ~2.6 random DRAM fetches.
+// A register-blocked Bloom filter over the record words, built on the device
+// at upload, answers "certainly absent" with ONE 16-byte load: block =
+// 4 x u32, two bits per word, all eight tests on registers.  No false negatives,
+// so a filtered miss is a miss of XT_getIX32 too; positives take the exact path.
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
+    return x ^ (x >> 33);
+}
+__device__ __forceinline__ uint4 bloom_masks(uint64_t h) {
+    const uint64_t g = h * 0x9E3779B97F4A7C15ull;                  // 8 x 5 bits: two bits in each of the 4 words
+    return make_uint4((1u << (g & 31)) | (1u << ((g >> 5) & 31)), (1u << ((g >> 10) & 31)) | (1u << ((g >> 15) & 31)),
+                      (1u << ((g >> 20) & 31)) | (1u << ((g >> 25) & 31)), (1u << ((g >> 30) & 31)) | (1u << ((g >> 35) & 31)));
+}
+__device__ __forceinline__ bool bloom_maybe(const DevDB &db, uint64_t word) {
+    const uint64_t h = mix64(word);
+    const uint4 v = __ldg(db.bloom + __umul64hi(h, db.bloom_blocks));   // ONE request for ONE line (profiles/r01_membench*)
+    const uint4 m = bloom_masks(h);
+    return ((v.x & m.x) == m.x) & ((v.y & m.y) == m.y) & ((v.z & m.z) == m.z) & ((v.w & m.w) == m.w);
+}
+// one thread per prefix bin: inserts the words of the bin's records
+__global__ void __launch_bounds__(256)
+bloom_build_kernel(DevDB db, uint32_t *__restrict__ bloom) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= UTB_NUMBINS - 1) return;
+    uint64_t a, b;
+    if (db.binix32) { a = db.binix32[p]; b = db.binix32[p + 1]; }
+    else { a = db.binix64[p]; b = db.binix64[p + 1]; }
+    if (a >= b || b > db.num_nodes) return;
+    if (p == db.quirk_bin) ++a;                                    // the folded record is unreachable anyway
+    for (uint64_t i = a; i < b; ++i) {
+        const uint64_t word = ((uint64_t)p << 40) | ((uint64_t)db.keys[i] << 8) | (load_aux(db, i) & 0xFFu);
+        const uint64_t h = mix64(word);
+        uint32_t *blk = bloom + 4 * __umul64hi(h, db.bloom_blocks);
+        const uint4 m = bloom_masks(h);
+        atomicOr(blk + 0, m.x); atomicOr(blk + 1, m.y); atomicOr(blk + 2, m.z); atomicOr(blk + 3, m.w);
+    }
+}
+
+// One thread per (position, strand) of the packed super-sequence: lanes 2k and
+// 2k+1 look up the forward and the reverse-complement word of window k, so the
+// hit slots of a warp are 32 consecutive u32.  No block-level synchronisation:
+// a warp that is done leaves (the profile of the first version showed a third
+// of the resident warps parked on a bookkeeping barrier); lookups and hits are
+// counted per warp into COUNTER_SLOTS spread counters that the host sums.
+#define COUNTER_SLOTS 1024
+template <int NSTR, bool FAST, bool BLOOM>
+__global__ void __launch_bounds__(256, 6)
+lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
+              uint32_t n_pos, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+    uint64_t w = 0;
+    const bool valid = pos < n_pos && window_at(pk, bad, pos, w);
+    uint32_t r = HIT_NOWIN;
+    if (valid) {
+        if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
+        if (BLOOM && !bloom_maybe(db, w)) r = HIT_MISS;
+        else if (FAST) {
+            uint64_t ww[1] = {w};
+            uint32_t rr[1];
+            fast_lookup<1>(db, ww, rr);
+            r = rr[0];
+        } else {
+            Probe q[1];
+            probe_begin(db, w, q[0]);
+            probe_run<1>(db, q);
+            r = probe_end(db, q[0]);
+        }
+    }
+    if (pos < n_pos) hits[slot] = r;
+    const uint32_t nv = __popc(__ballot_sync(0xFFFFFFFFu, valid));
+    const uint32_t nh = __popc(__ballot_sync(0xFFFFFFFFu, r < HIT_NOWIN));
+    if ((threadIdx.x & 31u) == 0) {
+        const uint32_t c = blockIdx.x & (COUNTER_SLOTS - 1);
+        if (nv) atomicAdd(counters + c, (unsigned long long)nv);
+        if (nh) atomicAdd(counters + COUNTER_SLOTS + c, (unsigned long long)nh);
+    }
+}
+
+// ---- two-phase lookup (pre-filter on) -------------------------------------------
+// In one fused kernel every warp waits for its slowest lane, i.e. for the one
+// or two lanes per warp whose word passes the filter and walks the whole
+// index -> key line -> aux chain, while the other ~30 lanes idle: the kernel
+// is bound by warp latency, not by DRAM.  So the work is split into two dense
+// passes: phase A tests every window against the filter (one fetch, no chain)
+// and appends the survivors to a queue with a warp-aggregated atomic; phase B
+// runs the exact search over the queue with every lane busy.
+__device__ __noinline__ uint32_t fast_lookup_cold(const DevDB &db, uint64_t w) {
+    uint64_t ww[1] = {w};
+    uint32_t rr[1];
+    fast_lookup<1>(db, ww, rr);
+    return rr[0];
+}
+#define Q_CHUNK 128u              // queue slots a warp reserves per atomic
+#define Q_INVALID 0xFFFFFFFFu
+template <int NSTR>
+__global__ void __launch_bounds__(256, 6)
+filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
+              uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
+              uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
+              uint64_t q_cap) {
+    // persistent warps: each owns a private chunk of the queue, so the global
+    // counter sees one atomic per Q_CHUNK survivors instead of one per warp-step
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t n_slots = (uint64_t)n_pos * NSTR;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t chunk_base = 0;
+    uint32_t chunk_used = Q_CHUNK;                                 // "no chunk yet"
+    bool have_chunk = false;
+    uint32_t nv = 0, nh = 0;
+    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_slots; base += stride) {
+        const uint64_t slot = base + lane;
+        const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+        uint64_t w = 0;
+        const bool valid = slot < n_slots && window_at(pk, bad, pos, w);
+        if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
+        const bool pass = valid && bloom_maybe(db, w);
+        uint32_t r = valid ? HIT_MISS : HIT_NOWIN;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+        const uint32_t c = __popc(m);
+        if (c) {
+            if (chunk_used + c > Q_CHUNK) {                        // retire the chunk (pad its tail) and take a new one
+                if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
+                unsigned long long nb = 0;
+                if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
+                chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                chunk_used = 0;
+                have_chunk = chunk_base + Q_CHUNK <= q_cap;        // beyond capacity: resolve inline from here on
+            }
+            if (pass) {
+                if (have_chunk) {
+                    const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
+                    q_words[idx] = w; q_slots[idx] = (uint32_t)slot;
+                } else r = fast_lookup_cold(db, w);
+            }
+            chunk_used += c;
+        }
+        if (slot < n_slots) hits[slot] = r;
+        nv += valid; nh += r < HIT_NOWIN;
+    }
+    if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
+    for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xFFFFFFFFu, nv, o); nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); }
+    if (lane == 0) {
+        const uint32_t cs = (blockIdx.x * 8 + (threadIdx.x >> 5)) & (COUNTER_SLOTS - 1);
+        if (nv) atomicAdd(counters + cs, (unsigned long long)nv);
+        if (nh) atomicAdd(counters + COUNTER_SLOTS + cs, (unsigned long long)nh);
+    }
+}
+
+__global__ void __launch_bounds__(256, 6)
+queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32_t *__restrict__ q_slots,
+                    const unsigned long long *__restrict__ q_count, uint64_t q_cap,
+                    uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+    const uint64_t n = *q_count < q_cap ? *q_count : q_cap;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t nh = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t slot = q_slots[i];
+        if (slot == Q_INVALID) continue;                           // padding of a retired chunk
+        uint64_t ww[1] = {q_words[i]};
+        uint32_t rr[1];
+        fast_lookup<1>(db, ww, rr);
+        if (rr[0] != HIT_MISS) { hits[slot] = rr[0]; ++nh; }
+    }
+    for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
+    if ((threadIdx.x & 31u) == 0 && nh)
+        atomicAdd(counters + COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)nh);
+}
+
 // stage-level: words[] -> ix[] (utb_lookup_words)
+template <bool FAST>
 __global__ void lookup_words_kernel(DevDB db, const uint64_t *__restrict__ words, uint64_t n, uint32_t *__restrict__ ix) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (FAST) {
+        if (db.bloom && !bloom_maybe(db, words[i])) { ix[i] = HIT_MISS; return; }
+        uint64_t ww[1] = {words[i]};
+        uint32_t rr[1];
+        fast_lookup<1>(db, ww, rr);
+        ix[i] = rr[0];
+        return;
+    }
     Probe q[1];
     probe_begin(db, words[i], q[0]);
     probe_run<1>(db, q);
@@ -419,7 +730,7 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
     uint32_t k0 = key[lane], k1 = key[lane + 32];
     uint32_t m0 = __ballot_sync(0xFFFFFFFFu, k0 != UTB_BAD32), m1 = __ballot_sync(0xFFFFFFFFu, k1 != UTB_BAD32);
     uint32_t uix = __popc(m0) + __popc(m1);
-    if (lane == 0) atomicAdd(counters + 2, 1ull);                  // good finds (itree.c:1029)
+    if (lane == 0) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), 1ull);   // good finds (itree.c:1029)
     if (uix == 1) {                                                // itree.c:1031-1032, 1039-1040
         uint32_t lab = m0 ? __shfl_sync(0xFFFFFFFFu, k0, __ffs(m0) - 1) : __shfl_sync(0xFFFFFFFFu, k1, __ffs(m1) - 1);
         if (lane == 0) { out->kind = UTB_STAR; out->label = lab; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
@@ -504,7 +815,7 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
             if (n == 0) {
                 if (lane == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
             } else {
-                if (lane == 0) atomicAdd(counters + 2, 1ull);
+                if (lane == 0) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), 1ull);
                 if (uix == 1) {
                     if (lane == 0) { out->kind = UTB_STAR; out->label = T_lab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
                 } else walk_warp(db, T_lab, T_cnt, uix, n, out);
@@ -631,6 +942,55 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
     db->d.rank = (const uint32_t *)db->rank;
     db->d.by_rank = (const uint32_t *)db->by_rank;
     db->hbm_bytes = nb_binix + nb_recs + ctr->blob_len + 3 * (nl + 1) * 4;
+    // Is the CTR regular (what utree-compress emits: every bucket strictly
+    // sorted, at most the first-bin quirk)?  Then the interpolation search is
+    // exact; otherwise keep the reference's probe sequence.
+    {
+        db->d.quirk_bin = 0xFFFFFFFFu;
+        unsigned long long *d_out, h_out[4] = {0, 0, ~0ull, ~0ull};
+        CK(cudaMalloc(&d_out, 32));
+        CK(cudaMemcpy(d_out, h_out, 32, cudaMemcpyHostToDevice));
+        verify_kernel<<<(UTB_NUMBINS - 1 + 255) / 256, 256>>>(db->d, d_out);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(h_out, d_out, 32, cudaMemcpyDeviceToHost));
+        cudaFree(d_out);
+        db->regular = h_out[0] == 0 && (h_out[1] == 0 || (h_out[1] == 1 && h_out[2] == h_out[3]));
+        if (db->regular && h_out[1] == 1) db->d.quirk_bin = (uint32_t)h_out[2];
+        const char *lk = getenv("UTB_LOOKUP");                      // "exact" forces the reference probe sequence
+        db->use_interp = db->regular && !(lk && !strcmp(lk, "exact"));
+    }
+    if (db->use_interp) {
+        // one-time re-layout into key / aux arrays (16 keys of slack: the window load may overrun)
+        const size_t n = (size_t)ctr->num_nodes, aux_sz = ctr->ix_bytes == 2 ? 4 : 8;
+        CK(cudaMalloc(&db->keys, (n + 32) * 4));
+        CK(cudaMalloc(&db->aux, (n + 32) * aux_sz));
+        CK(cudaMemset((char *)db->keys + n * 4, 0xFF, 32 * 4));
+        relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, (uint32_t *)db->keys,
+                                                               ctr->ix_bytes == 2 ? (uint32_t *)db->aux : nullptr,
+                                                               ctr->ix_bytes == 2 ? nullptr : (uint64_t *)db->aux);
+        CK(cudaGetLastError());
+        CK(cudaDeviceSynchronize());
+        db->d.keys = (const uint32_t *)db->keys;
+        db->d.aux32 = ctr->ix_bytes == 2 ? (const uint32_t *)db->aux : nullptr;
+        db->d.aux64 = ctr->ix_bytes == 2 ? nullptr : (const uint64_t *)db->aux;
+        CK(cudaFree(db->recs));                                    // the byte-packed blob is no longer needed
+        db->recs = nullptr; db->d.recs = nullptr;
+        db->hbm_bytes = nb_binix + (n + 32) * (4 + aux_sz) + ctr->blob_len + 3 * (nl + 1) * 4;
+        const char *bm = getenv("UTB_BLOOM");                      // 0 off, 1 always, default auto
+        db->bloom_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
+        if (db->bloom_mode) {
+            // 16 bits per record: 8 records per 128-bit block -> ~0.1 % false positives
+            uint64_t blocks = n / 8 + 1024;
+            CK(cudaMalloc(&db->bloom, blocks * 16));
+            CK(cudaMemset(db->bloom, 0, blocks * 16));
+            db->d.bloom_blocks = blocks;
+            bloom_build_kernel<<<(UTB_NUMBINS - 1 + 255) / 256, 256>>>(db->d, (uint32_t *)db->bloom);
+            CK(cudaGetLastError());
+            CK(cudaDeviceSynchronize());
+            db->d.bloom = (const uint4 *)db->bloom;
+            db->hbm_bytes += blocks * 16;
+        }
+    }
     // Hot prefix table pinned in L2: reserve persisting lines for the index so
     // the streaming record traffic does not evict it (applied per stream in
     // utb_batch_create).
@@ -642,7 +1002,22 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
             db->l2_window = 1;
             db->l2_window_bytes = nb_binix < (size_t)p.accessPolicyMaxWindowSize ? nb_binix : (size_t)p.accessPolicyMaxWindowSize;
+            // a window larger than the set-aside would thrash it: persist only the fraction that fits
+            db->l2_hit_ratio = want >= db->l2_window_bytes ? 1.0f : (float)((double)want / (double)db->l2_window_bytes);
+            const char *hr = getenv("UTB_L2_HITRATIO");
+            if (hr) db->l2_hit_ratio = (float)atof(hr);
         } else cudaGetLastError();
+    }
+    const char *fg = getenv("UTB_L2_FETCH");                        // DRAM->L2 fetch granularity hint: 32 / 64 / 128
+    if (fg && atoi(fg) > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)) != cudaSuccess) cudaGetLastError();
+    if (getenv("UTB_STATS")) {
+        size_t fgv = 0, pl = 0;
+        cudaDeviceGetLimit(&fgv, cudaLimitMaxL2FetchGranularity);
+        cudaDeviceGetLimit(&pl, cudaLimitPersistingL2CacheSize);
+        fprintf(stderr, "utree-b200: device %d %s: L2 %d MiB, persisting max %d MiB (set %zu MiB), window max %d MiB, "
+                "fetch granularity %zu B, binix window %zu MiB hitRatio %.2f\n", device, p.name, p.l2CacheSize >> 20,
+                p.persistingL2CacheMaxSize >> 20, pl >> 20, p.accessPolicyMaxWindowSize >> 20, fgv,
+                db->l2_window_bytes >> 20, db->l2_hit_ratio);
     }
     *out = db;
     return UTB_OK;
@@ -651,11 +1026,12 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
 extern "C" void utb_db_free(utb_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob);
+    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob); cudaFree(db->keys); cudaFree(db->aux); cudaFree(db->bloom);
     cudaFree(db->off); cudaFree(db->rank); cudaFree(db->by_rank);
     free(db);
 }
 extern "C" uint64_t utb_db_hbm_bytes(const utb_db *db) { return db ? db->hbm_bytes : 0; }
+extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_interp : 0; }
 
 // ---------------------------------------------------------------------------
 // C ABI: batches
@@ -675,10 +1051,11 @@ struct utb_batch {
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
     uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
     utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count;
-    unsigned long long *d_counters;   // [0] lookups [1] hits [2] good finds
+    unsigned long long *d_counters;   // [3][COUNTER_SLOTS]: lookups, hits, good finds (summed on the host)
     uint32_t *d_hist, *d_tlab, *d_tcnt;
+    uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     // last submit
-    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight;
+    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom;
     uint64_t launches;
 };
 
@@ -700,6 +1077,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
+    cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 5; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -729,7 +1107,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMallocHost(&b->h_seq_len, max_reads * 4));
     BK(cudaMallocHost(&b->h_grp_off, (max_reads + 1) * 4));
     BK(cudaMallocHost(&b->h_results, max_reads * sizeof(utb_result)));
-    BK(cudaMallocHost(&b->h_counters, 4 * 8));
+    BK(cudaMallocHost(&b->h_counters, 3 * COUNTER_SLOTS * 8));
     BK(cudaMalloc(&b->d_raw, max_bytes + 128));
     BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
     BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
@@ -740,18 +1118,24 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_results, max_reads * sizeof(utb_result)));
     BK(cudaMalloc(&b->d_gen_list, max_reads * 4));
     BK(cudaMalloc(&b->d_gen_count, 4));
-    BK(cudaMalloc(&b->d_counters, 4 * 8));
+    BK(cudaMalloc(&b->d_counters, 3 * COUNTER_SLOTS * 8));
     BK(cudaMalloc(&b->d_hist, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMalloc(&b->d_tlab, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMalloc(&b->d_tcnt, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMemset(b->d_hist, 0, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMemset(b->d_raw, 0, max_bytes + 128));
+    if (db->bloom) {                                               // queue for a quarter of the lookup slots; overflow resolves inline
+        b->q_cap = npos * 2 / 4 + 4096;
+        BK(cudaMalloc(&b->d_qwords, b->q_cap * 8));
+        BK(cudaMalloc(&b->d_qslots, b->q_cap * 4));
+        BK(cudaMalloc(&b->d_qcount, 8));
+    }
     if (db->l2_window) {
         cudaStreamAttrValue a;
         memset(&a, 0, sizeof a);
         a.accessPolicyWindow.base_ptr = db->binix;
         a.accessPolicyWindow.num_bytes = db->l2_window_bytes;
-        a.accessPolicyWindow.hitRatio = 1.0f;
+        a.accessPolicyWindow.hitRatio = db->l2_hit_ratio;
         a.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         if (cudaStreamSetAttribute(b->st, cudaStreamAttributeAccessPolicyWindow, &a) != cudaSuccess) cudaGetLastError();
@@ -768,7 +1152,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     const uint32_t n_pos = n_groups * 32u;
     const uint32_t nstr = b->do_rc ? 2u : 1u;
     CK(cudaMemsetAsync(b->d_gen_count, 0, 4, b->st));
-    CK(cudaMemsetAsync(b->d_counters, 0, 4 * 8, b->st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 3 * COUNTER_SLOTS * 8, b->st));
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
         pack_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
@@ -777,8 +1161,24 @@ static int launch_stages(utb_batch *b, bool timed) {
     }
     if (timed) CK(cudaEventRecord(b->ev[1], b->st));
     if (n_pos) {
-        if (nstr == 2) lookup_kernel<2><<<(n_pos + 255) / 256, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
-        else lookup_kernel<1><<<(n_pos + 255) / 256, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+        const unsigned nb = (unsigned)(((uint64_t)n_pos * nstr + 255) / 256);
+        // pre-filter on while misses dominate (it only adds a fetch to lookups that hit)
+        const bool bloom = b->db->bloom && (b->db->bloom_mode == 1 || (b->db->bloom_mode == 2 && b->db->ema_hit_rate < 0.40));
+        b->used_bloom = bloom;
+        if (b->db->use_interp && bloom) {
+            CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
+            const unsigned pb = nb < 148u * 6u ? nb : 148u * 6u;   // persistent: 6 CTAs per SM
+            if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_counters);
+            b->launches++;
+        } else if (b->db->use_interp) {
+            if (nstr == 2) lookup_kernel<2, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+            else lookup_kernel<1, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+        } else {
+            if (nstr == 2) lookup_kernel<2, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+            else lookup_kernel<1, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+        }
         b->launches++;
     }
     if (timed) CK(cudaEventRecord(b->ev[2], b->st));
@@ -821,7 +1221,7 @@ extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, in
     int rc = launch_stages(b, true);
     if (rc) return rc;
     if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
-    CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * 8, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 3 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
     CK(cudaEventRecord(b->done, b->st));
     b->in_flight = 1;
     return UTB_OK;
@@ -831,6 +1231,14 @@ extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
     if (!b) { utb_set_error("utb_batch_wait: null batch"); return UTB_ERR_ARG; }
     CK(cudaSetDevice(b->db->device));
     CK(cudaEventSynchronize(b->done));
+    if (b->in_flight) {
+        uint64_t l = 0, h = 0;
+        for (int i = 0; i < COUNTER_SLOTS; ++i) { l += b->h_counters[i]; h += b->h_counters[COUNTER_SLOTS + i]; }
+        if (l >= 4096) {                                            // steer the pre-filter: hit rate seen so far
+            double r = (double)h / (double)l;
+            b->db->ema_hit_rate = b->db->ema_hit_rate < 0 ? r : 0.5 * b->db->ema_hit_rate + 0.5 * r;
+        }
+    }
     b->in_flight = 0;
     if (results) *results = b->h_results;
     return UTB_OK;
@@ -838,8 +1246,10 @@ extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
 
 extern "C" int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits) {
     if (!b) { utb_set_error("utb_batch_counts: null batch"); return UTB_ERR_ARG; }
-    if (lookups) *lookups = b->h_counters[0];
-    if (hits) *hits = b->h_counters[1];
+    uint64_t l = 0, h = 0;
+    for (int i = 0; i < COUNTER_SLOTS; ++i) { l += b->h_counters[i]; h += b->h_counters[COUNTER_SLOTS + i]; }
+    if (lookups) *lookups = l;
+    if (hits) *hits = h;
     return UTB_OK;
 }
 
@@ -884,7 +1294,8 @@ extern "C" int utb_lookup_words(utb_db *db, const uint64_t *words, size_t n, uin
     CK(cudaMalloc(&dw, n * 8));
     CK(cudaMalloc(&di, n * 4));
     CK(cudaMemcpy(dw, words, n * 8, cudaMemcpyHostToDevice));
-    lookup_words_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
+    if (db->use_interp) lookup_words_kernel<true><<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
+    else lookup_words_kernel<false><<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
     CK(cudaGetLastError());
     CK(cudaMemcpy(ix, di, n * 4, cudaMemcpyDeviceToHost));
     cudaFree(dw); cudaFree(di);
@@ -927,9 +1338,9 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     uint32_t *d_hits, *d_gl, *d_gc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
     CK(cudaMalloc(&d_hits, (nh + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
-    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 32));
+    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 3 * COUNTER_SLOTS * 8));
     CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 32));
+    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 3 * COUNTER_SLOTS * 8));
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1;
