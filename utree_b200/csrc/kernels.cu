@@ -314,16 +314,20 @@ __device__ __noinline__ uint32_t fast_slow(const DevDB &db, uint64_t a, uint64_t
     return ix < db.max_ix ? ix : HIT_MISS;
 }
 #define FW_MAX_STEPS 4          // sectors inspected before giving up on the estimate
+// sect: 32-byte sectors this lookup had to touch (index pair, key windows, aux)
 template <int N>
-__device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)[N], uint32_t (&r)[N]) {
+__device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)[N], uint32_t (&r)[N], uint32_t *sect = nullptr) {
     FastProbe q[N];
+    uint32_t ns = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) fast_begin(db, w[i], q[i]);
 #pragma unroll
     for (int i = 0; i < N; ++i) {
+        ns += ((w[i] >> 40) & 7u) == 7u ? 2u : 1u;                 // BinIx[p], BinIx[p+1]: 4-byte entries, 8 per sector
         if (q[i].st == FW_MISS) continue;                          // empty bucket
         int dir = 0;                                               // direction of the last move
         for (int step = 0; step < FW_MAX_STEPS; ++step) {
+            ++ns;
             window_step(db, q[i]);
             if (q[i].st != FW_LEFT && q[i].st != FW_RIGHT) break;
             if (dir && q[i].st != dir) { q[i].st = FW_MISS; break; }   // turned around: the target falls between two adjacent windows
@@ -336,6 +340,7 @@ __device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)
     for (int i = 0; i < N; ++i) {
         r[i] = HIT_MISS;
         if (q[i].st == FW_FOUND) {
+            ++ns;
             const uint64_t ax = load_aux(db, q[i].pos);
             uint32_t nb = ~q[i].t;
             const uint64_t wa = q[i].ws > q[i].a ? q[i].ws : q[i].a, wb = q[i].ws + KW < q[i].b ? q[i].ws + KW : q[i].b;
@@ -344,8 +349,9 @@ __device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)
             if (nb == q[i].t) q[i].st = FW_SLOW;                   // the run of equal keys crosses the window
             else if ((uint32_t)(ax & 0xFFu) == q[i].lo8) { uint32_t ix = (uint32_t)(ax >> 8); r[i] = ix < db.max_ix ? ix : HIT_MISS; }
         }
-        if (q[i].st == FW_SLOW) r[i] = fast_slow(db, q[i].a, q[i].b, q[i].t, q[i].lo8);
+        if (q[i].st == FW_SLOW) { r[i] = fast_slow(db, q[i].a, q[i].b, q[i].t, q[i].lo8); ns += 8; }
     }
+    if (sect) *sect = ns;
 }
 
 // raw CTR records -> SoA (runs once at upload, only for regular CTRs)
@@ -544,18 +550,22 @@ queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32
                     uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
     const uint64_t n = *q_count < q_cap ? *q_count : q_cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint32_t nh = 0;
+    uint32_t nh = 0, nsect = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t slot = q_slots[i];
         if (slot == Q_INVALID) continue;                           // padding of a retired chunk
         uint64_t ww[1] = {q_words[i]};
-        uint32_t rr[1];
-        fast_lookup<1>(db, ww, rr);
+        uint32_t rr[1], sc;
+        fast_lookup<1>(db, ww, rr, &sc);
+        nsect += sc;
         if (rr[0] != HIT_MISS) { hits[slot] = rr[0]; ++nh; }
     }
-    for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
-    if ((threadIdx.x & 31u) == 0 && nh)
-        atomicAdd(counters + COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)nh);
+    for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); nsect += __shfl_xor_sync(0xFFFFFFFFu, nsect, o); }
+    if ((threadIdx.x & 31u) == 0) {
+        const uint32_t c = blockIdx.x & (COUNTER_SLOTS - 1);
+        if (nh) atomicAdd(counters + COUNTER_SLOTS + c, (unsigned long long)nh);
+        if (nsect) atomicAdd(counters + 3 * COUNTER_SLOTS + c, (unsigned long long)nsect);
+    }
 }
 
 // stage-level: words[] -> ix[] (utb_lookup_words)
@@ -1041,7 +1051,7 @@ extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_interp
 struct utb_batch {
     utb_db *db;
     cudaStream_t st;
-    cudaEvent_t done, ev[5];
+    cudaEvent_t done, ev[6];
     size_t max_bytes, max_reads;
     uint64_t max_groups;
     // pinned host
@@ -1051,7 +1061,7 @@ struct utb_batch {
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
     uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
     utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count;
-    unsigned long long *d_counters;   // [3][COUNTER_SLOTS]: lookups, hits, good finds (summed on the host)
+    unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     // last submit
@@ -1079,7 +1089,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount);
     if (b->done) cudaEventDestroy(b->done);
-    for (int i = 0; i < 5; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
     free(b);
 }
@@ -1101,13 +1111,13 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
 #define BK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { utb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); utb_batch_destroy(b); return UTB_ERR_CUDA; } } while (0)
     BK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
     BK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
-    for (int i = 0; i < 5; ++i) BK(cudaEventCreate(&b->ev[i]));
+    for (int i = 0; i < 6; ++i) BK(cudaEventCreate(&b->ev[i]));
     BK(cudaMallocHost(&b->h_bytes, max_bytes + 64));
     BK(cudaMallocHost(&b->h_seq_off, max_reads * 8));
     BK(cudaMallocHost(&b->h_seq_len, max_reads * 4));
     BK(cudaMallocHost(&b->h_grp_off, (max_reads + 1) * 4));
     BK(cudaMallocHost(&b->h_results, max_reads * sizeof(utb_result)));
-    BK(cudaMallocHost(&b->h_counters, 3 * COUNTER_SLOTS * 8));
+    BK(cudaMallocHost(&b->h_counters, 4 * COUNTER_SLOTS * 8));
     BK(cudaMalloc(&b->d_raw, max_bytes + 128));
     BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
     BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
@@ -1118,7 +1128,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_results, max_reads * sizeof(utb_result)));
     BK(cudaMalloc(&b->d_gen_list, max_reads * 4));
     BK(cudaMalloc(&b->d_gen_count, 4));
-    BK(cudaMalloc(&b->d_counters, 3 * COUNTER_SLOTS * 8));
+    BK(cudaMalloc(&b->d_counters, 4 * COUNTER_SLOTS * 8));
     BK(cudaMalloc(&b->d_hist, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMalloc(&b->d_tlab, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMalloc(&b->d_tcnt, (size_t)VB_BLOCKS * nl * 4));
@@ -1152,7 +1162,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     const uint32_t n_pos = n_groups * 32u;
     const uint32_t nstr = b->do_rc ? 2u : 1u;
     CK(cudaMemsetAsync(b->d_gen_count, 0, 4, b->st));
-    CK(cudaMemsetAsync(b->d_counters, 0, 3 * COUNTER_SLOTS * 8, b->st));
+    CK(cudaMemsetAsync(b->d_counters, 0, 4 * COUNTER_SLOTS * 8, b->st));
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
         pack_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
@@ -1170,6 +1180,7 @@ static int launch_stages(utb_batch *b, bool timed) {
             const unsigned pb = nb < 148u * 6u ? nb : 148u * 6u;   // persistent: 6 CTAs per SM
             if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
             else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            if (timed) CK(cudaEventRecord(b->ev[5], b->st));
             queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_counters);
             b->launches++;
         } else if (b->db->use_interp) {
@@ -1221,7 +1232,7 @@ extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, in
     int rc = launch_stages(b, true);
     if (rc) return rc;
     if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
-    CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 3 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
     CK(cudaEventRecord(b->done, b->st));
     b->in_flight = 1;
     return UTB_OK;
@@ -1262,6 +1273,19 @@ extern "C" int utb_batch_last_ms(utb_batch *b, float ms[4]) {
     return UTB_OK;
 }
 extern "C" uint64_t utb_batch_launches(const utb_batch *b) { return b ? b->launches : 0; }
+// Two-phase detail of the LAST run (valid after wait): ms[0] filter kernel, ms[1] queue kernel (0/0 when the
+// single lookup kernel ran); sectors[0] = filter probes (one sector each), sectors[1] = sectors the exact
+// path touched for the survivors.
+extern "C" int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]) {
+    if (!b || !ms || !sectors) { utb_set_error("utb_batch_lookup_detail: null argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    ms[0] = ms[1] = 0; sectors[0] = sectors[1] = 0;
+    if (!b->used_bloom) return UTB_OK;
+    CK(cudaEventElapsedTime(&ms[0], b->ev[1], b->ev[5]));
+    CK(cudaEventElapsedTime(&ms[1], b->ev[5], b->ev[2]));
+    for (int i = 0; i < COUNTER_SLOTS; ++i) { sectors[0] += b->h_counters[i]; sectors[1] += b->h_counters[3 * COUNTER_SLOTS + i]; }
+    return UTB_OK;
+}
 
 extern "C" int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint64_t *launches) {
     if (!b || iters < 1) { utb_set_error("utb_batch_rerun_device: bad argument"); return UTB_ERR_ARG; }
@@ -1272,6 +1296,7 @@ extern "C" int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint
     for (int it = 0; it < iters; ++it) {
         int rc = launch_stages(b, true);
         if (rc) return rc;
+        CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
         CK(cudaStreamSynchronize(b->st));
         float t[4];
         rc = utb_batch_last_ms(b, t);
@@ -1338,9 +1363,9 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     uint32_t *d_hits, *d_gl, *d_gc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
     CK(cudaMalloc(&d_hits, (nh + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
-    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 3 * COUNTER_SLOTS * 8));
+    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
     CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 3 * COUNTER_SLOTS * 8));
+    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1;
