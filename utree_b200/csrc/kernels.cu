@@ -489,9 +489,17 @@ __device__ __noinline__ uint32_t fast_lookup_cold(const DevDB &db, uint64_t w) {
     return rr[0];
 }
 #define Q_CHUNK 128u              // queue slots a warp reserves per atomic
+#ifndef FILT_ILP
+#define FILT_ILP 2                // filter probes in flight per lane
+#endif
 #define Q_INVALID 0xFFFFFFFFu
-template <int NSTR>
-__global__ void __launch_bounds__(256, 6)
+#ifndef FILT_MINB
+#define FILT_MINB 5               // CTAs per SM the register budget is sized for
+#endif
+// DIAG (UTB_FILT_DIAG, measurements only): 1 = no survivor queue (count only), 2 = also no window extraction
+// (synthetic words), 0 = product
+template <int NSTR, int DIAG>
+__global__ void __launch_bounds__(256, FILT_MINB)
 filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
               uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
               uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
@@ -505,35 +513,51 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     uint32_t chunk_used = Q_CHUNK;                                 // "no chunk yet"
     bool have_chunk = false;
     uint32_t nv = 0, nh = 0;
-    for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n_slots; base += stride) {
-        const uint64_t slot = base + lane;
-        const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
-        uint64_t w = 0;
-        const bool valid = slot < n_slots && window_at(pk, bad, pos, w);
-        if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
-        const bool pass = valid && bloom_maybe(db, w);
-        uint32_t r = valid ? HIT_MISS : HIT_NOWIN;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-        const uint32_t c = __popc(m);
-        if (c) {
-            if (chunk_used + c > Q_CHUNK) {                        // retire the chunk (pad its tail) and take a new one
-                if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
-                unsigned long long nb = 0;
-                if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
-                chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
-                chunk_used = 0;
-                have_chunk = chunk_base + Q_CHUNK <= q_cap;        // beyond capacity: resolve inline from here on
-            }
-            if (pass) {
-                if (have_chunk) {
-                    const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
-                    q_words[idx] = w; q_slots[idx] = (uint32_t)slot;
-                } else r = fast_lookup_cold(db, w);
-            }
-            chunk_used += c;
+    // every warp takes FILT_ILP x 32 consecutive slots per round: the FILT_ILP filter loads of a lane are in flight together
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * FILT_ILP; base < n_slots; base += stride * FILT_ILP) {
+        uint64_t w[FILT_ILP], h[FILT_ILP];
+        uint4 v[FILT_ILP];
+        bool valid[FILT_ILP];
+#pragma unroll
+        for (int u = 0; u < FILT_ILP; ++u) {
+            const uint64_t slot = base + 32u * u + lane;
+            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+            w[u] = 0;
+            if (DIAG == 2) { valid[u] = slot < n_slots; w[u] = slot * 0x9E3779B97F4A7C15ull; }
+            else valid[u] = slot < n_slots && window_at(pk, bad, pos, w[u]);
+            if (NSTR == 2 && (slot & 1)) w[u] = revcomp_word(w[u]);
+            h[u] = mix64(w[u]);
+            v[u] = make_uint4(0, 0, 0, 0);
+            if (valid[u]) v[u] = __ldg(db.bloom + __umul64hi(h[u], db.bloom_blocks));
         }
-        if (slot < n_slots) hits[slot] = r;
-        nv += valid; nh += r < HIT_NOWIN;
+#pragma unroll
+        for (int u = 0; u < FILT_ILP; ++u) {
+            const uint64_t slot = base + 32u * u + lane;
+            const uint4 m4 = bloom_masks(h[u]);
+            const bool pass = valid[u] & ((v[u].x & m4.x) == m4.x) & ((v[u].y & m4.y) == m4.y) & ((v[u].z & m4.z) == m4.z) & ((v[u].w & m4.w) == m4.w);
+            uint32_t r = valid[u] ? HIT_MISS : HIT_NOWIN;
+            const uint32_t m = DIAG ? 0u : __ballot_sync(0xFFFFFFFFu, pass);
+            const uint32_t c = __popc(m);
+            if (DIAG) nh += pass;
+            if (c) {
+                if (chunk_used + c > Q_CHUNK) {                    // retire the chunk (pad its tail) and take a new one
+                    if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
+                    unsigned long long nb = 0;
+                    if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
+                    chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                    chunk_used = 0;
+                    have_chunk = chunk_base + Q_CHUNK <= q_cap;    // beyond capacity: resolve inline from here on
+                }
+                if (pass) {
+                    if (have_chunk) {
+                        const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
+                        q_words[idx] = w[u]; q_slots[idx] = (uint32_t)slot;
+                    } else { r = fast_lookup_cold(db, w[u]); if (r != HIT_MISS) hits[slot] = r; }   // queue full
+                }
+                chunk_used += c;
+            }
+            nv += valid[u]; nh += r < HIT_NOWIN;                   // hits[] was pre-set to MISS: nothing to store for the rest
+        }
     }
     if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
     for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xFFFFFFFFu, nv, o); nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); }
@@ -712,22 +736,46 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
     __syncwarp();
     uint32_t n = 0;
     bool overflow = false;
-    for (uint64_t base = 0; base < count; base += 32) {
-        uint64_t i = base + lane;
-        uint32_t h = i < count ? __ldg(in.hits + start + i) : HIT_NOWIN;
-        bool ok = h < db.max_ix;
-        n += __popc(__ballot_sync(0xFFFFFFFFu, ok));
-        uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-        if (ok && (uint32_t)(__ffs(peers) - 1) == lane) {          // one lane per distinct label
-            uint32_t c = __popc(peers), slot = (h * 2654435761u) >> 26;   // 6 bits
-            for (uint32_t tries = 0;; ++tries) {
-                if (tries == VW_SLOTS) { overflow = true; break; }
-                uint32_t old = atomicCAS(&key[slot], UTB_BAD32, h);
-                if (old == UTB_BAD32 || old == h) { atomicAdd(&cnt[slot], c); break; }
-                slot = (slot + 1) & (VW_SLOTS - 1);
+    // 128 slots per round (one uint4 per lane); most slots are empty, so a round without a label costs one ballot
+    const uint32_t mis = (uint32_t)((4u - (start & 3u)) & 3u);     // slots before the first 16-byte boundary
+    for (uint64_t base = 0; base < count + 128; base += 128) {
+        uint32_t hv[4];
+        if (base == 0) {                                           // unaligned head: up to 3 slots, scalar
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hv[c] = HIT_NOWIN;
+            if (lane < mis && lane < count) hv[0] = __ldg(in.hits + start + lane);
+        } else {
+            const uint64_t i0 = mis + (base - 128) + 4ull * lane;   // aligned body
+            if (i0 + 4 <= count) {
+                const uint4 q4 = __ldg(reinterpret_cast<const uint4 *>(in.hits + start + i0));
+                hv[0] = q4.x; hv[1] = q4.y; hv[2] = q4.z; hv[3] = q4.w;
+            } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) hv[c] = i0 + c < count ? __ldg(in.hits + start + i0 + c) : HIT_NOWIN;
             }
+            if (mis + (base - 128) >= count) break;
         }
-        __syncwarp();
+        const bool any4 = hv[0] < db.max_ix || hv[1] < db.max_ix || hv[2] < db.max_ix || hv[3] < db.max_ix;
+        if (!__any_sync(0xFFFFFFFFu, any4)) continue;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t h = hv[c];
+            const bool ok = h < db.max_ix;
+            const uint32_t okm = __ballot_sync(0xFFFFFFFFu, ok);
+            if (!okm) continue;
+            n += __popc(okm);
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+            if (ok && (uint32_t)(__ffs(peers) - 1) == lane) {      // one lane per distinct label
+                uint32_t cc = __popc(peers), slot = (h * 2654435761u) >> 26;   // 6 bits
+                for (uint32_t tries = 0;; ++tries) {
+                    if (tries == VW_SLOTS) { overflow = true; break; }
+                    uint32_t old = atomicCAS(&key[slot], UTB_BAD32, h);
+                    if (old == UTB_BAD32 || old == h) { atomicAdd(&cnt[slot], cc); break; }
+                    slot = (slot + 1) & (VW_SLOTS - 1);
+                }
+            }
+            __syncwarp();
+        }
     }
     if (__any_sync(0xFFFFFFFFu, overflow)) {
         if (lane == 0) gen_list[atomicAdd(gen_count, 1u)] = r;
@@ -1177,9 +1225,17 @@ static int launch_stages(utb_batch *b, bool timed) {
         b->used_bloom = bloom;
         if (b->db->use_interp && bloom) {
             CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
-            const unsigned pb = nb < 148u * 6u ? nb : 148u * 6u;   // persistent: 6 CTAs per SM
-            if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
-            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            // hits are sparse (only filter survivors that really match): one streaming fill instead of a dense
+            // store stream interleaved with the random filter reads
+            CK(cudaMemsetAsync(b->d_hits, 0xFF, (size_t)n_pos * nstr * 4, b->st));
+            if (timed) CK(cudaEventRecord(b->ev[4], b->st));
+            const unsigned pb = nb < 148u * FILT_MINB ? nb : 148u * FILT_MINB;   // persistent: FILT_MINB CTAs per SM
+            const char *dg = getenv("UTB_FILT_DIAG");
+            const int diag = dg ? atoi(dg) : 0;
+            if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            else if (diag == 2) filter_kernel<2, 2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            else if (nstr == 2) filter_kernel<2, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            else filter_kernel<1, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
             queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_counters);
             b->launches++;
@@ -1281,7 +1337,7 @@ extern "C" int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t secto
     CK(cudaSetDevice(b->db->device));
     ms[0] = ms[1] = 0; sectors[0] = sectors[1] = 0;
     if (!b->used_bloom) return UTB_OK;
-    CK(cudaEventElapsedTime(&ms[0], b->ev[1], b->ev[5]));
+    CK(cudaEventElapsedTime(&ms[0], b->ev[4], b->ev[5]));   // the kernel alone (the hits fill before it is part of the stage)
     CK(cudaEventElapsedTime(&ms[1], b->ev[5], b->ev[2]));
     for (int i = 0; i < COUNTER_SLOTS; ++i) { sectors[0] += b->h_counters[i]; sectors[1] += b->h_counters[3 * COUNTER_SLOTS + i]; }
     return UTB_OK;
