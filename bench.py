@@ -188,7 +188,24 @@ def oracle_sector_stats(ctr_path, reads_bytes, rec_bytes, n_sample, threads):
             "port_reads_per_s": n_sample / dt, "out_file": fa + ".out", "fasta": fa}
 
 
+_REAL_STDOUT = None
+
+
+def emit_json(line):
+    """The ONE JSON line goes to the process's original stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -401,7 +418,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line:
-        print(json.dumps(line), flush=True)
+        emit_json(line)
 
 
 def reference_arm(args, cfg, rank, world, local, ncpu, rec_bytes, workload):
@@ -414,7 +431,7 @@ def reference_arm(args, cfg, rank, world, local, ncpu, rec_bytes, workload):
     ctr_path = os.path.join(work_dir(), f"{args.config}_{cfg_key(args.config, cfg)}.ctr")
     if not os.path.exists(ctr_path):
         if not have_gpu:
-            print(json.dumps({"impl": "reference", "unavailable": "synthetic CTR needs the GPU synthesiser and no GPU is visible"}))
+            emit_json({"impl": "reference", "unavailable": "synthetic CTR needs the GPU synthesiser and no GPU is visible"})
             return
         ctr_path, _ = ensure_ctr(args.config, cfg, local)
     n_avail = min(cfg["reads"], 2_000_000)
@@ -452,7 +469,7 @@ def reference_arm(args, cfg, rank, world, local, ncpu, rec_bytes, workload):
                              "sample": f"{times[0][0]} reads per step of the same synthetic reads; search time = wall minus a 1-read run"},
             "e2e": {"value": round(value, 1), "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,117 @@
+"""Parity at the scales BASELINE.json names, against the UNMODIFIED reference
+binary (oracle/_ref, threads=1 = input order) on the GPU box: the L2-scale CTR,
+the L4 CTR, a uint32_t-label CTR with > 65,536 labels at complevel 0, and long /
+whole-genome queries up to the 16,777,214-base limit.  Inputs come from the GPU
+synthesiser (itself checked against the real builder in test_gpu_parity.py)."""
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(ROOT, "oracle", "_ref")
+need_ref = pytest.mark.skipif(not os.path.exists(os.path.join(REF, "utree-search_gg")), reason="oracle/_ref not built")
+
+
+def _ref_search(ctr, fasta, out, u32=False):
+    exe = os.path.join(REF, "utree-search_gg" + ("_u32" if u32 else ""))
+    p = subprocess.run([exe, ctr, fasta, out, "1", "RC"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-500:]
+    return open(out, "rb").read()
+
+
+def _ours(ctr_path, fasta_bytes):
+    from utree_b200 import capi
+    ctr = capi.Ctr(ctr_path)
+    s = capi.Searcher(ctr, devices=(0,), host_threads=8)
+    try:
+        rc, ex, text, st = s.search_mem(fasta_bytes, do_rc=True)
+        assert rc == 0 and ex == 0
+        return text, st
+    finally:
+        s.destroy(); ctr.close()
+
+
+@pytest.fixture(scope="module")
+def bench_mod(built):
+    sys.path.insert(0, ROOT)
+    import bench
+    from utree_b200 import build
+    build.build_synth()
+    return bench
+
+
+@need_ref
+@pytest.mark.parametrize("config,n_reads", [("l2s", 150_000), ("l4", 300_000)])
+def test_l2_scale_and_l4_match_reference(bench_mod, tmp_path, config, n_reads):
+    cfg = dict(bench_mod.CONFIGS[config])
+    ctr_path, meta = bench_mod.ensure_ctr(config, cfg, 0)
+    assert meta["records"] > (900_000_000 if config == "l2s" else 40_000_000)
+    reads = bench_mod.make_reads(cfg, 5_000_000, n_reads, 0)           # a window of the read stream the bench never uses
+    fa = str(tmp_path / "r.fa")
+    reads.tofile(fa)
+    want = _ref_search(ctr_path, fa, str(tmp_path / "ref.out"))
+    got, st = _ours(ctr_path, reads.tobytes())
+    assert got == want
+    assert want.count(b"\n") > 0.9 * n_reads * (0.5 if config == "l4" else 1) * 0.5
+    assert st["lookups"] > 200 * n_reads
+
+
+@need_ref
+def test_uint32_labels_over_64k_match_reference(bench_mod, tmp_path):
+    """IXTYPE=uint32_t (SZ=9), complevel 0, 73,260 labels, 250 bp reads."""
+    from utree_b200 import synthgpu
+    uni = synthgpu.Universe(77, 60, 11, 10, 10, 6000)                 # 66,000 genomes
+    ctr_path = os.path.join(bench_mod.work_dir(), "u32_test.ctr")
+    n, nl = uni.build_ctr(ctr_path, complevel=0, ix_bytes=4)
+    try:
+        assert nl > 65536 and n > 100_000_000
+        reads = uni.make_reads(100_000, read_len=250, read_seed=5)
+        fa = str(tmp_path / "r.fa")
+        reads.tofile(fa)
+        want = _ref_search(ctr_path, fa, str(tmp_path / "ref.out"), u32=True)
+        got, st = _ours(ctr_path, reads.tobytes())
+        assert got == want
+        assert st["hits"] > 10 * 100_000                              # dense tree: most k-mers of a read hit
+    finally:
+        os.remove(ctr_path)
+
+
+@need_ref
+def test_long_and_whole_genome_queries_match_reference(bench_mod, tmp_path):
+    """10 kb - 1 Mb reads, whole genomes, and one query at the 16,777,214-base limit vs the L2-scale CTR."""
+    from utree_b200 import synthgpu
+    cfg = dict(bench_mod.CONFIGS["l2s"])
+    ctr_path, _ = bench_mod.ensure_ctr("l2s", cfg, 0)
+    uni = synthgpu.Universe(bench_mod.SEED, *cfg["universe"])
+    rng = np.random.default_rng(4)
+    g = [uni.genome_ascii(i) for i in (0, 1, 2, 77, 4999)]            # 4 Mb each
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    recs = [(b"whole_genome_0", g[0]), (b"whole_genome_rc", g[3].translate(comp)[::-1]),
+            (b"max_length", (g[0] + g[1] + g[2] + g[4] + g[3])[:16_777_214])]
+    for i in range(40):
+        L = int(10 ** rng.uniform(4, 6))
+        src = g[int(rng.integers(len(g)))]
+        st = int(rng.integers(0, len(src) - L))
+        seq = bytearray(src[st:st + L])
+        for p in rng.integers(0, L, L // 100):                         # 1 % substitutions
+            seq[p] = b"ACGT"[(b"ACGT".index(seq[p]) + 1) % 4]
+        if i % 5 == 0:
+            seq[L // 2:L // 2 + 3] = b"NNN"
+        recs.append((b"long%d" % i, bytes(seq)))
+    recs.append((b"short_after_long", g[1][1000:1150]))
+    fasta = b"".join(b">" + n + b"\n" + s + b"\n" for n, s in recs)
+    fa = str(tmp_path / "long.fa")
+    open(fa, "wb").write(fasta)
+    t = time.time()
+    want = _ref_search(ctr_path, fa, str(tmp_path / "ref.out"))
+    t_ref = time.time() - t
+    got, st = _ours(ctr_path, fasta)
+    assert got == want
+    assert want.count(b"\n") == len(recs)
+    print(f"long queries: {sum(len(s) for _, s in recs) / 1e6:.1f} Mb, reference {t_ref:.1f} s (incl. load), ours {st['seconds_total']:.2f} s")
