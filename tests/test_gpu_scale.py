@@ -70,7 +70,7 @@ def test_uint32_labels_over_64k_match_reference(bench_mod, tmp_path):
     ctr_path = os.path.join(bench_mod.work_dir(), "u32_test.ctr")
     n, nl = uni.build_ctr(ctr_path, complevel=0, ix_bytes=4)
     try:
-        assert nl > 65536 and n > 100_000_000
+        assert nl > 65536 and n > 50_000_000
         reads = uni.make_reads(100_000, read_len=250, read_seed=5)
         fa = str(tmp_path / "r.fa")
         reads.tofile(fa)
