@@ -107,6 +107,15 @@ int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
 /* Blocks until the batch is done; *results points at n_reads records in
  * pinned memory, valid until the next submit on this batch. */
 int utb_batch_wait(utb_batch *b, const utb_result **results);
+/* Same pipeline, but the output LINES (itree.c:1032, 1040, 1096) are built on
+ * the device too.  The caller additionally fills, per read, where its name
+ * sits in the raw bytes (utb_batch_name_off/_len, pinned).  wait_text returns
+ * the finished text of the batch (pinned, valid until the next submit) and the
+ * number of reads with >= 1 hit. */
+uint32_t *utb_batch_name_off(utb_batch *b);
+uint32_t *utb_batch_name_len(utb_batch *b);
+int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
+int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len, uint64_t *good_finds);
 /* Re-runs only the device stages on the inputs already resident from the last
  * submit (no PCIe traffic) `iters` times and reports CUDA-event milliseconds
  * per stage, summed over iters: ms[0]=pack ms[1]=lookup ms[2]=vote ms[3]=total.

@@ -274,3 +274,46 @@ def test_irregular_ctr_takes_the_exact_probe_path(built, tmp_path):
         s.destroy()
     finally:
         db.free(); ctr.close(); orc.free()
+
+
+@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[7], CASES[8]])
+def test_host_formatter_path_matches_reference(gpu, tmp_path, db_name, reads, out, rc):
+    """UTB_HOST_FORMAT=1: result records come back and the host formatter team writes the lines
+    (default: the lines are built on the device)."""
+    from utree_b200 import capi
+    os.environ["UTB_HOST_FORMAT"] = "1"
+    try:
+        s = capi.Searcher(gpu[db_name][0], devices=(0,), host_threads=4)
+    finally:
+        del os.environ["UTB_HOST_FORMAT"]
+    try:
+        o = str(tmp_path / "out.txt")
+        code, ref_exit, st = s.search_file(gold(reads), o, do_rc=bool(rc))
+        assert code == 0 and open(o, "rb").read() == open(gold(out), "rb").read()
+    finally:
+        s.destroy()
+
+
+@pytest.mark.parametrize("host_format", [0, 1])
+def test_zero_copy_from_pinned_caller_buffer(gpu, host_format):
+    """utb_search_mem on a page-locked caller buffer: framed in place, copied to the device from where it lies."""
+    import torch
+    from utree_b200 import capi
+    data = open(gold("toyB_reads.fa"), "rb").read() + open(gold("edge_reads.fa"), "rb").read()
+    want_b = open(gold("toyB_u32_rc.out"), "rb").read()
+    pinned = torch.empty(len(data), dtype=torch.uint8, pin_memory=True)
+    pinned.numpy()[:] = np.frombuffer(data, dtype=np.uint8)
+    if host_format:
+        os.environ["UTB_HOST_FORMAT"] = "1"
+    os.environ["UTB_BATCH_MB"] = "33"
+    try:
+        s = capi.Searcher(gpu["toyB_u32"][0], devices=(0, 0), host_threads=6)
+    finally:
+        os.environ.pop("UTB_HOST_FORMAT", None); os.environ.pop("UTB_BATCH_MB", None)
+    try:
+        rc, ex, text, st = s.search_mem(None, do_rc=True, ptr=pinned.data_ptr(), n=len(data))
+        rc2, ex2, text2, st2 = s.search_mem(data, do_rc=True)            # pageable copy of the same bytes
+        assert rc == 0 and rc2 == 0 and text == text2
+        assert text.startswith(want_b) and st["reads"] == st2["reads"]
+    finally:
+        s.destroy()

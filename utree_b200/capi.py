@@ -49,7 +49,7 @@ EXPORTS = [
     "utb_device_count", "utb_db_upload", "utb_db_free", "utb_db_hbm_bytes", "utb_db_lookup_mode",
     "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
     "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
-    "utb_batch_submit", "utb_batch_wait", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail",
+    "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail",
     "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_frame_records", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
     "utb_main", "utb_measure_rand32",

@@ -76,6 +76,8 @@ struct utb_db {
     void *binix, *recs, *blob, *off, *rank, *by_rank, *keys, *aux, *bloom;
     int bloom_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
     double ema_hit_rate;       // of the batches seen so far
+    size_t max_label;          // longest label, bytes
+    double text_per_read;      // running estimate of output bytes per read (sizes the speculative text D2H)
     uint64_t hbm_bytes;
     int l2_window;             // persisting-L2 window over binix configured
     size_t l2_window_bytes;
@@ -884,6 +886,137 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
 }
 
 // ---------------------------------------------------------------------------
+// output text on the device (the fprintf lines of itree.c:1032, 1040, 1096)
+// ---------------------------------------------------------------------------
+// The host formatter competes with the framer for a handful of cores (16 for
+// 8 GPUs on the test box), so the lines are produced here: per-read length,
+// exclusive scan, then one warp per read copies name, label prefix and the
+// numeric tail.  The host only moves the finished text to the sink.
+__device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
+    return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u :
+           v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+__device__ __forceinline__ uint32_t tax_len_of(const DevDB &db, const utb_result &v) {
+    uint32_t ll = __ldg(db.off + v.label + 1) - __ldg(db.off + v.label) - 1u;
+    if (v.kind == UTB_WALK) {
+        if (v.cut == UTB_CUT_EMPTY) ll = 0;                        // dv == -1 (itree.c:1087)
+        else if (v.cut != UTB_CUT_FULL && v.cut < ll) ll = v.cut;  // first dv bytes (itree.c:1088)
+    }
+    return ll;
+}
+__global__ void __launch_bounds__(256)
+fmt_len_kernel(DevDB db, const utb_result *__restrict__ res, const uint32_t *__restrict__ name_len, uint32_t n_reads,
+               uint32_t *__restrict__ line_len) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const utb_result v = res[r];
+    uint32_t n = 0;
+    if (v.kind != UTB_NONE) {
+        n = __ldg(name_len + r) + 1u + tax_len_of(db, v) + 1u + dec_digits(v.found) + 1u + dec_digits(v.uix) + 1u;
+        n += v.kind == UTB_STAR ? 1u : dec_digits(v.sl) + 1u + dec_digits(v.ol);
+        n += 1u;
+    }
+    line_len[r] = n;
+}
+// exclusive scan of u32 (n up to 2^31): block sums, scan of the sums by one block, local scan + base
+#define SCAN_TILE 2048u
+__global__ void __launch_bounds__(256)
+scan_sums_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t sh[8];
+    const uint32_t base = blockIdx.x * SCAN_TILE;
+    uint32_t acc = 0;
+    for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) acc += in[base + i];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += sh[w]; sums[blockIdx.x] = t; }
+}
+__global__ void __launch_bounds__(1024)
+scan_top_kernel(uint32_t *__restrict__ sums, uint32_t nb, uint32_t *__restrict__ total) {
+    __shared__ uint32_t sh[1024];
+    uint32_t carry = 0;
+    for (uint32_t base = 0; base < nb; base += 1024) {
+        uint32_t i = base + threadIdx.x, v = i < nb ? sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t o = 1; o < 1024; o <<= 1) {
+            uint32_t t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) sums[i] = carry + sh[threadIdx.x] - v;           // exclusive
+        carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(256)
+scan_apply_kernel(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__restrict__ sums, uint32_t *__restrict__ out) {
+    __shared__ uint32_t sh[8];
+    __shared__ uint32_t run;
+    const uint32_t base = blockIdx.x * SCAN_TILE;
+    if (threadIdx.x == 0) run = sums[blockIdx.x];
+    __syncthreads();
+    for (uint32_t c = 0; c < SCAN_TILE; c += 256) {
+        const uint32_t i = base + c + threadIdx.x;
+        const uint32_t v = i < n ? in[i] : 0;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31) >= (uint32_t)o) x += t; }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        uint32_t wbase = run;
+        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += sh[w];
+        if (i < n) out[i] = wbase + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) run = wbase + x;
+        __syncthreads();
+    }
+}
+__device__ __forceinline__ uint32_t put_dec(char *p, uint32_t v) {
+    const uint32_t n = dec_digits(v);
+    for (uint32_t i = n; i; --i) { p[i - 1] = (char)('0' + v % 10u); v /= 10u; }
+    return n;
+}
+__global__ void __launch_bounds__(256)
+slots_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, uint32_t *__restrict__ slots) {
+    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) slots[r] = (seq_len[r] + 1u + 31u) / 32u;           // utb_read_slots
+}
+#define FW_WARPS 8
+__global__ void __launch_bounds__(FW_WARPS * 32)
+fmt_write_kernel(DevDB db, const utb_result *__restrict__ res, const uint8_t *__restrict__ raw,
+                 const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ name_len,
+                 const uint32_t *__restrict__ line_off, uint32_t n_reads, char *__restrict__ text) {
+    __shared__ char s_tail[FW_WARPS][48];
+    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    const uint32_t r = blockIdx.x * FW_WARPS + wib;
+    if (r >= n_reads) return;
+    const utb_result v = res[r];
+    if (v.kind == UTB_NONE) return;
+    char *out = text + line_off[r];
+    const uint32_t nl = __ldg(name_len + r), tl = tax_len_of(db, v);
+    const uint8_t *nm = raw + __ldg(name_off + r);
+    const char *lab = db.blob + __ldg(db.off + v.label);
+    uint32_t tn = 0;
+    if (lane == 0) {                                               // "\t<found>\t<uix>\t*\n" or "...\t<sl>;<ol>\n"
+        char *t = s_tail[wib];
+        t[tn++] = '\t'; tn += put_dec(t + tn, v.found);
+        t[tn++] = '\t'; tn += put_dec(t + tn, v.uix);
+        t[tn++] = '\t';
+        if (v.kind == UTB_STAR) t[tn++] = '*';
+        else { tn += put_dec(t + tn, v.sl); t[tn++] = ';'; tn += put_dec(t + tn, v.ol); }
+        t[tn++] = '\n';
+    }
+    tn = __shfl_sync(0xFFFFFFFFu, tn, 0);
+    __syncwarp();
+    for (uint32_t i = lane; i < nl; i += 32) out[i] = (char)nm[i];
+    if (lane == 0) out[nl] = '\t';
+    for (uint32_t i = lane; i < tl; i += 32) out[nl + 1 + i] = lab[i];
+    for (uint32_t i = lane; i < tn; i += 32) out[nl + 1 + tl + i] = s_tail[wib][i];
+}
+
+// ---------------------------------------------------------------------------
 // random-sector gather microbenchmark (roofline denominator)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -1000,6 +1133,7 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
     db->d.rank = (const uint32_t *)db->rank;
     db->d.by_rank = (const uint32_t *)db->by_rank;
     db->hbm_bytes = nb_binix + nb_recs + ctr->blob_len + 3 * (nl + 1) * 4;
+    for (size_t i = 0; i < nl; ++i) { size_t l = ctr->off[i + 1] - ctr->off[i]; if (l > db->max_label) db->max_label = l; }
     // Is the CTR regular (what utree-compress emits: every bucket strictly
     // sorted, at most the first-bin quirk)?  Then the interpolation search is
     // exact; otherwise keep the reference's probe sequence.
@@ -1105,10 +1239,13 @@ struct utb_batch {
     // pinned host
     char *h_bytes; uint64_t *h_seq_off; uint32_t *h_seq_len; uint32_t *h_grp_off;
     utb_result *h_results; unsigned long long *h_counters;
+    uint32_t *h_name_off, *h_name_len; char *h_text; uint32_t *h_text_len; size_t text_cap;   // device-side formatting
     // device
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
     uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
     utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count;
+    uint32_t *d_name_off, *d_name_len, *d_line_len, *d_line_off, *d_scan_sums, *d_text_len; char *d_text;
+    int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
@@ -1131,6 +1268,10 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     if (b->st) cudaStreamSynchronize(b->st);
     cudaFreeHost(b->h_bytes); cudaFreeHost(b->h_seq_off); cudaFreeHost(b->h_seq_len); cudaFreeHost(b->h_grp_off);
     cudaFreeHost(b->h_results); cudaFreeHost(b->h_counters);
+    cudaFreeHost(b->h_name_off); cudaFreeHost(b->h_name_len); cudaFreeHost(b->h_text); cudaFreeHost(b->h_text_len);
+    cudaFree(b->d_name_off); cudaFree(b->d_name_len); cudaFree(b->d_line_len); cudaFree(b->d_line_off); cudaFree(b->d_scan_sums);
+    cudaFree(b->d_text_len); cudaFree(b->d_text);
+    if (b->text_len_ready) cudaEventDestroy(b->text_len_ready);
     cudaFree(b->d_raw); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_grp_off);
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
@@ -1166,6 +1307,16 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMallocHost(&b->h_grp_off, (max_reads + 1) * 4));
     BK(cudaMallocHost(&b->h_results, max_reads * sizeof(utb_result)));
     BK(cudaMallocHost(&b->h_counters, 4 * COUNTER_SLOTS * 8));
+    BK(cudaMallocHost(&b->h_name_off, (max_reads + 1) * 4));
+    BK(cudaMallocHost(&b->h_name_len, (max_reads + 1) * 4));
+    BK(cudaMallocHost(&b->h_text_len, 4));
+    BK(cudaEventCreateWithFlags(&b->text_len_ready, cudaEventDisableTiming));
+    BK(cudaMalloc(&b->d_name_off, (max_reads + 1) * 4));
+    BK(cudaMalloc(&b->d_name_len, (max_reads + 1) * 4));
+    BK(cudaMalloc(&b->d_line_len, (max_reads + 1) * 4));
+    BK(cudaMalloc(&b->d_line_off, (max_reads + 1) * 4));
+    BK(cudaMalloc(&b->d_scan_sums, (max_reads / SCAN_TILE + 2) * 4));
+    BK(cudaMalloc(&b->d_text_len, 4));
     BK(cudaMalloc(&b->d_raw, max_bytes + 128));
     BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
     BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
@@ -1263,13 +1414,46 @@ static int launch_stages(utb_batch *b, bool timed) {
     return UTB_OK;
 }
 
+// text buffers are allocated on first use (the device-resident measurement batches never format)
+static int ensure_text_buffers(utb_batch *b) {
+    if (b->d_text) return UTB_OK;
+    size_t cap = b->max_bytes + b->max_reads * (b->db->max_label + 48) + 64;
+    if (cap >= ((size_t)1 << 32)) { utb_set_error("batch too large for device-side formatting"); return UTB_ERR_LIMIT; }
+    CK(cudaMalloc(&b->d_text, cap));
+    CK(cudaMallocHost(&b->h_text, cap));
+    b->text_cap = cap;
+    return UTB_OK;
+}
+
+static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
 extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
+    return submit_impl(b, nullptr, n_bytes, n_reads, do_rc, 0, 0);
+}
+extern "C" int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
+    return submit_impl(b, nullptr, n_bytes, n_reads, do_rc, 1, 0);
+}
+// Pipeline-internal variant: `src` (pinned host memory, or NULL for the batch's own staging) holds the raw
+// bytes; total_groups != 0 means the caller already summed utb_read_slots() over the reads, so the
+// per-read offsets are scanned on the device instead of in a serial host loop.
+extern "C" int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc,
+                                   int want_text, uint64_t total_groups) {
+    return submit_impl(b, src, n_bytes, n_reads, do_rc, want_text, total_groups);
+}
+extern "C" int utb_host_ptr_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return a.type == cudaMemoryTypeHost;
+}
+extern "C" uint32_t *utb_batch_name_off(utb_batch *b) { return b->h_name_off; }
+extern "C" uint32_t *utb_batch_name_len(utb_batch *b) { return b->h_name_len; }
+
+static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups) {
     if (!b) { utb_set_error("utb_batch_submit: null batch"); return UTB_ERR_ARG; }
     if (n_bytes > b->max_bytes || n_reads > b->max_reads) { utb_set_error("utb_batch_submit: batch over capacity"); return UTB_ERR_LIMIT; }
     CK(cudaSetDevice(b->db->device));
     // position space: read r owns groups [grp_off[r], grp_off[r+1])
-    uint64_t g = 0;
-    for (size_t r = 0; r < n_reads; ++r) {
+    uint64_t g = total_groups;
+    if (!total_groups) for (size_t r = 0; r < n_reads; ++r) {
         uint32_t len = b->h_seq_len[r];
         if (len > UTB_MAXSEQ) { utb_set_error("read %zu: %u bases exceeds the 16777214-base limit", r, len); return UTB_ERR_LIMIT; }
         if (b->h_seq_off[r] + len > n_bytes) { utb_set_error("read %zu: sequence outside the batch bytes", r); return UTB_ERR_ARG; }
@@ -1277,17 +1461,56 @@ extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, in
         g += utb_read_slots(len);
     }
     if (g > b->max_groups) { utb_set_error("utb_batch_submit: %llu position groups exceed capacity %llu", (unsigned long long)g, (unsigned long long)b->max_groups); return UTB_ERR_LIMIT; }
-    b->h_grp_off[n_reads] = (uint32_t)g;
+    if (!total_groups) b->h_grp_off[n_reads] = (uint32_t)g;
     b->n_reads = n_reads; b->n_groups = (uint32_t)g; b->do_rc = do_rc ? 1 : 0;
+    b->want_text = want_text;
+    if (want_text) {
+        int rt = ensure_text_buffers(b);
+        if (rt) return rt;
+        if (n_reads) {
+            CK(cudaMemcpyAsync(b->d_name_off, b->h_name_off, n_reads * 4, cudaMemcpyHostToDevice, b->st));
+            CK(cudaMemcpyAsync(b->d_name_len, b->h_name_len, n_reads * 4, cudaMemcpyHostToDevice, b->st));
+        }
+    }
     if (n_reads) {
-        CK(cudaMemcpyAsync(b->d_raw, b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
+        CK(cudaMemcpyAsync(b->d_raw, src ? src : b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
         CK(cudaMemcpyAsync(b->d_seq_off, b->h_seq_off, n_reads * 8, cudaMemcpyHostToDevice, b->st));
         CK(cudaMemcpyAsync(b->d_seq_len, b->h_seq_len, n_reads * 4, cudaMemcpyHostToDevice, b->st));
-        CK(cudaMemcpyAsync(b->d_grp_off, b->h_grp_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, b->st));
+        if (!total_groups) CK(cudaMemcpyAsync(b->d_grp_off, b->h_grp_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, b->st));
+        else {                                                     // grp_off = exclusive scan of the per-read slot counts
+            const uint32_t n = (uint32_t)n_reads, nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+            slots_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->d_seq_len, n, b->d_line_len);
+            scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
+            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_text_len);
+            scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_grp_off);
+            b->launches += 4;
+        }
     }
     int rc = launch_stages(b, true);
     if (rc) return rc;
-    if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
+    if (want_text) {
+        // lines built on the device: lengths -> exclusive scan -> one warp per read writes its line
+        const uint32_t n = (uint32_t)n_reads, nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+        CK(cudaMemsetAsync(b->d_text_len, 0, 4, b->st));
+        if (n) {
+            fmt_len_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->db->d, b->d_results, b->d_name_len, n, b->d_line_len);
+            scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
+            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_text_len);
+            scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_line_off);
+            fmt_write_kernel<<<(n + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, 0, b->st>>>(
+                b->db->d, b->d_results, b->d_raw, b->d_name_off, b->d_name_len, b->d_line_off, n, b->d_text);
+            b->launches += 5;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemcpyAsync(b->h_text_len, b->d_text_len, 4, cudaMemcpyDeviceToHost, b->st));
+        // the text length is only known on the device: copy an estimate now (no extra round trip in the
+        // common case), wait_text tops it up if it was short
+        size_t est = (size_t)(b->db->text_per_read * 1.15 * (double)n_reads) + 4096;
+        if (b->db->text_per_read <= 0) est = 0;
+        if (est > b->text_cap) est = b->text_cap;
+        b->text_prefetched = est;
+        if (est) CK(cudaMemcpyAsync(b->h_text, b->d_text, est, cudaMemcpyDeviceToHost, b->st));
+    } else if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
     CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
     CK(cudaEventRecord(b->done, b->st));
     b->in_flight = 1;
@@ -1308,6 +1531,28 @@ extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
     }
     b->in_flight = 0;
     if (results) *results = b->h_results;
+    return UTB_OK;
+}
+
+// After utb_batch_submit_text: blocks until the batch is done and its output text is in pinned host memory.
+extern "C" int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len, uint64_t *good_finds) {
+    if (!b || !text || !len) { utb_set_error("utb_batch_wait_text: null argument"); return UTB_ERR_ARG; }
+    if (!b->want_text) { utb_set_error("utb_batch_wait_text: batch was not submitted with utb_batch_submit_text"); return UTB_ERR_ARG; }
+    int rc = utb_batch_wait(b, nullptr);
+    if (rc) return rc;
+    const size_t n = *b->h_text_len;
+    if (n > b->text_cap) { utb_set_error("device text overflow"); return UTB_ERR_LIMIT; }
+    if (n > b->text_prefetched) {
+        CK(cudaMemcpyAsync(b->h_text + b->text_prefetched, b->d_text + b->text_prefetched, n - b->text_prefetched,
+                           cudaMemcpyDeviceToHost, b->st));
+        CK(cudaStreamSynchronize(b->st));
+    }
+    if (b->n_reads >= 64) {
+        double r = (double)n / (double)b->n_reads;
+        b->db->text_per_read = b->db->text_per_read <= 0 ? r : 0.5 * b->db->text_per_read + 0.5 * r;
+    }
+    *text = b->h_text; *len = n;
+    if (good_finds) { uint64_t g = 0; for (int i = 0; i < COUNTER_SLOTS; ++i) g += b->h_counters[2 * COUNTER_SLOTS + i]; *good_finds = g; }
     return UTB_OK;
 }
 

@@ -33,6 +33,9 @@
 #include <unistd.h>
 
 int utb_batch_last_ms(utb_batch *b, float ms[4]);
+int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
+int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
+int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
 
 #define SLOTS_PER_DEVICE 3
@@ -100,6 +103,7 @@ typedef struct {
     size_t n_bytes, n_reads;
     uint32_t *name_off, *name_len;
     uint64_t first_read;           /* global index of the slot's first read */
+    const char *host_bytes;        /* where this batch's raw bytes live on the host (staging, or the caller's pinned buffer) */
     int state;                     /* 0 free, 1 submitted */
 } slot_t;
 
@@ -114,6 +118,7 @@ struct utb_searcher {
     size_t batch_bytes, batch_reads;
     size_t max_label;              /* longest label incl. NUL */
     int verbose;                   /* CLI: progress lines on stdout */
+    int device_format;             /* output lines built on the GPU (default) or by the host formatter team */
 };
 
 static double now_s(void) {
@@ -133,6 +138,8 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->batch_bytes = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : DEFAULT_BATCH_BYTES;
     if (s->batch_bytes < 2 * (size_t)UTB_LINELEN + 4096) s->batch_bytes = 2 * (size_t)UTB_LINELEN + 4096; /* one max record must fit */
     s->batch_reads = s->batch_bytes / 64;
+    e = getenv("UTB_HOST_FORMAT");
+    s->device_format = !(e && atoi(e) != 0);
     for (uint32_t i = 0; i < ctr->max_ix; ++i) {
         size_t l = ctr->off[i + 1] - ctr->off[i];
         if (l > s->max_label) s->max_label = l;
@@ -152,9 +159,8 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
         sl->dev_index = i % n_devices;
         int rc = utb_batch_create(s->dbs[sl->dev_index], s->batch_bytes, s->batch_reads, &sl->b);
         if (rc) { utb_searcher_destroy(s); return rc; }
-        sl->name_off = (uint32_t *)malloc((s->batch_reads + 1) * 4);
-        sl->name_len = (uint32_t *)malloc((s->batch_reads + 1) * 4);
-        if (!sl->name_off || !sl->name_len) { utb_searcher_destroy(s); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+        sl->name_off = utb_batch_name_off(sl->b);                  /* pinned: the device formatter reads them too */
+        sl->name_len = utb_batch_name_len(sl->b);
     }
     *out = s;
     return UTB_OK;
@@ -162,10 +168,7 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
 
 void utb_searcher_destroy(utb_searcher *s) {
     if (!s) return;
-    if (s->slots) for (int i = 0; i < s->n_slots; ++i) {
-        utb_batch_destroy(s->slots[i].b);
-        free(s->slots[i].name_off); free(s->slots[i].name_len);
-    }
+    if (s->slots) for (int i = 0; i < s->n_slots; ++i) utb_batch_destroy(s->slots[i].b);
     if (s->dbs) for (int d = 0; d < s->n_devices; ++d) utb_db_free(s->dbs[d]);
     free(s->slots); free(s->dbs); free(s->devices); free(s);
 }
@@ -338,6 +341,20 @@ static void emit_part(void *c_, int part, int nparts) {
     }
 }
 
+typedef struct { sink_t *sink; const char *text; size_t len, off; } copy_ctx;
+static void copy_part(void *c_, int part, int nparts) {
+    copy_ctx *c = (copy_ctx *)c_;
+    size_t a = c->len * (size_t)part / (size_t)nparts, b = c->len * (size_t)(part + 1) / (size_t)nparts;
+    if (a == b) return;
+    if (c->sink->fd < 0) { memcpy(c->sink->map + 64 + c->off + a, c->text + a, b - a); return; }
+    const char *p = c->text + a; size_t n = b - a; off_t o = (off_t)(c->off + a);
+    while (n) {
+        ssize_t k = pwrite(c->sink->fd, p, n, o);
+        if (k < 0) { if (errno == EINTR) continue; c->sink->failed = 1; return; }
+        p += k; o += k; n -= (size_t)k;
+    }
+}
+
 static void *formatter_main(void *arg) {
     run_t *R = (run_t *)arg;
     utb_searcher *s = R->s;
@@ -352,12 +369,24 @@ static void *formatter_main(void *arg) {
         if (!have) break;
         slot_t *sl = &s->slots[seq % (uint64_t)s->n_slots];
         const utb_result *res = NULL;
+        const char *text = NULL; size_t text_len = 0; uint64_t good = 0;
         double tw = now_s();
-        int rc = utb_batch_wait(sl->b, &res);
+        int rc = s->device_format ? utb_batch_wait_text(sl->b, &text, &text_len, &good) : utb_batch_wait(sl->b, &res);
         R->st.fm_wait_gpu += now_s() - tw;
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
-        if (!rc) {
-            F.sl = sl; F.res = res; F.bytes = utb_batch_bytes(sl->b);
+        if (!rc && s->device_format) {
+            double tf = now_s();
+            if (text_len && !sink_reserve(R->sink, R->sink->off + text_len)) {
+                copy_ctx cc = {R->sink, text, text_len, R->sink->off};
+                team_run(&R->fmt_team, copy_part, &cc);
+                R->sink->off += text_len;
+                R->st.out_bytes += text_len;
+            }
+            R->st.good_finds += good;
+            R->st.fm_emit += now_s() - tf;
+            R->st.d2h_bytes += text_len + 4 * 1024 * 8 + 4;
+        } else if (!rc) {
+            F.sl = sl; F.res = res; F.bytes = sl->host_bytes;
             double tf = now_s();
             team_run(&R->fmt_team, fmt_part, &F);
             R->st.fm_format += now_s() - tf;
@@ -372,12 +401,14 @@ static void *formatter_main(void *arg) {
             }
             for (int p = 0; p < R->fmt_team.n; ++p) F.len[p] = 0;
             R->st.fm_emit += now_s() - tf;
+            R->st.d2h_bytes += sl->n_reads * sizeof(utb_result) + 32;
+        }
+        if (!rc) {
             uint64_t lk = 0, ht = 0; float ms[4] = {0, 0, 0, 0};
             utb_batch_counts(sl->b, &lk, &ht);
             utb_batch_last_ms(sl->b, ms);
             R->st.lookups += lk; R->st.hits += ht;
             R->st.seconds_device += 1e-3 * (double)ms[3];
-            R->st.d2h_bytes += sl->n_reads * sizeof(utb_result) + 32;
             if (s->verbose) {   /* itree.c:878 */
                 uint64_t a = sl->first_read, b = sl->first_read + sl->n_reads;
                 for (uint64_t m = (a >> 20) + 1; (m << 20) <= b; ++m)
@@ -409,6 +440,13 @@ typedef struct {
     size_t max_rec;                /* capacity of the per-read arrays */
     size_t err_rec[MAX_TEAM]; int err_code[MAX_TEAM];
     size_t end_of_records;         /* byte after the last complete record */
+    /* newline index (fast path): positions of every '\n', per segment, in one arena */
+    uint32_t *idx; size_t idx_cap;                 /* arena and its size in entries */
+    size_t idx_off[MAX_TEAM], idx_room[MAX_TEAM];  /* region of each segment */
+    int has_nul[MAX_TEAM], idx_overflow[MAX_TEAM];
+    size_t nl_total;
+    uint64_t groups[MAX_TEAM];                     /* 32-base position groups of the records each worker framed */
+    int groups_valid;
 } frame_ctx;
 
 static void count_part(void *c_, int part, int nparts) {
@@ -488,6 +526,109 @@ static void frame_part(void *c_, int part, int nparts) {
     }
 }
 
+
+/* Pass 1 (fast path): one sweep records the position of every newline of the
+ * segment and notes whether a NUL byte occurs (AVX2 when the CPU has it). */
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2")))
+static size_t index_avx2(const char *buf, size_t a, size_t b, uint32_t *out, size_t room, int *has_nul) {
+    const __m256i nl = _mm256_set1_epi8('\n'), zero = _mm256_setzero_si256();
+    __m256i accz = zero;
+    size_t n = 0, i = a;
+    for (; i + 32 <= b; i += 32) {
+        __m256i v = _mm256_loadu_si256((const __m256i *)(buf + i));
+        uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, nl));
+        accz = _mm256_or_si256(accz, _mm256_cmpeq_epi8(v, zero));
+        while (m) {
+            if (n < room) out[n] = (uint32_t)(i + (size_t)__builtin_ctz(m));
+            ++n; m &= m - 1;
+        }
+    }
+    int z = _mm256_movemask_epi8(accz) != 0;
+    for (; i < b; ++i) {
+        if (buf[i] == '\n') { if (n < room) out[n] = (uint32_t)i; ++n; }
+        else if (!buf[i]) z = 1;
+    }
+    *has_nul = z;
+    return n;
+}
+#endif
+static size_t index_scalar(const char *buf, size_t a, size_t b, uint32_t *out, size_t room, int *has_nul) {
+    size_t n = 0;
+    const char *p = buf + a, *e = buf + b;
+    while (p < e) {
+        const char *q = (const char *)memchr(p, '\n', (size_t)(e - p));
+        if (!q) break;
+        if (n < room) out[n] = (uint32_t)(q - buf);
+        ++n; p = q + 1;
+    }
+    *has_nul = memchr(buf + a, 0, b - a) != NULL;
+    return n;
+}
+static void index_part(void *c_, int part, int nparts) {
+    frame_ctx *c = (frame_ctx *)c_;
+    size_t a = c->fill * (size_t)part / (size_t)nparts, b = c->fill * (size_t)(part + 1) / (size_t)nparts;
+    /* arena share proportional to the segment: one newline per 8 bytes, plus slack */
+    c->idx_off[part] = a / 8 + 64 * (size_t)part;
+    c->idx_room[part] = (b - a) / 8 + 64;
+    if (c->idx_off[part] + c->idx_room[part] > c->idx_cap) c->idx_room[part] = c->idx_off[part] < c->idx_cap ? c->idx_cap - c->idx_off[part] : 0;
+    uint32_t *out = c->idx + c->idx_off[part];
+    size_t n;
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx2")) n = index_avx2(c->buf, a, b, out, c->idx_room[part], &c->has_nul[part]);
+    else
+#endif
+        n = index_scalar(c->buf, a, b, out, c->idx_room[part], &c->has_nul[part]);
+    c->cnt[part] = n;
+    c->idx_overflow[part] = n > c->idx_room[part];
+}
+
+/* Pass 2 (fast path): records are dealt to the workers by index; line 2r / 2r+1
+ * boundaries come from the newline index, no byte is scanned twice.  Only valid
+ * when the buffer holds no NUL byte (strlen() semantics are then the identity). */
+static void frame_indexed_part(void *c_, int part, int nparts) {
+    frame_ctx *c = (frame_ctx *)c_;
+    const size_t r0 = c->n_rec * (size_t)part / (size_t)nparts, r1 = c->n_rec * (size_t)(part + 1) / (size_t)nparts;
+    c->err_rec[part] = (size_t)-1; c->err_code[part] = FE_NONE; c->groups[part] = 0;
+    if (r0 >= r1) return;
+    const char *buf = c->buf;
+    /* cursor over the global newline sequence: segment sp, local index sk */
+    size_t i = r0 ? 2 * r0 - 1 : 0;                /* first newline needed: the one before header r0 (or newline 0) */
+    int sp = 0;
+    while (sp + 1 < nparts && c->base[sp + 1] <= i) ++sp;
+    size_t sk = i - c->base[sp];
+#define NEXT_NL(var) do { while (sk >= c->cnt[sp]) { ++sp; sk = 0; } (var) = c->idx[c->idx_off[sp] + sk]; ++sk; ++i; } while (0)
+    size_t hs = 0;
+    if (r0) { size_t prev; NEXT_NL(prev); hs = prev + 1; }
+    uint64_t groups = 0;
+    for (size_t r = r0; r < r1; ++r) {
+        size_t hn, send, line_end;
+        NEXT_NL(hn);
+        const size_t ss = hn + 1;
+        if (i < c->nl_total) { size_t sn; NEXT_NL(sn); line_end = sn; send = sn + 1; }
+        else { line_end = c->fill; send = c->fill; }           /* last line without '\n' (EOF) */
+        int err = FE_NONE;
+        if (ss - hs >= UTB_LINELEN || send - ss >= UTB_LINELEN) err = FE_TOOLONG;
+        else if (buf[hs] != '>') err = FE_NOHEADER;             /* itree.c:880 */
+        else if (buf[ss] == '>' && ss < c->fill) err = FE_SEQ_GT;   /* itree.c:886 */
+        if (err) { c->err_rec[part] = r; c->err_code[part] = err; break; }
+        size_t length = line_end - ss;
+        if (length && buf[ss + length - 1] == '\r') --length;   /* itree.c:890 */
+        size_t nl = hs + 1;                                     /* name: up to the first ' ' or the newline (itree.c:881) */
+        while (nl < hn && buf[nl] != ' ') ++nl;
+        c->name_off[r] = (uint32_t)(hs + 1);
+        c->name_len[r] = (uint32_t)(nl - hs - 1);
+        c->seq_off[r] = ss;
+        c->seq_len[r] = (uint32_t)length;
+        groups += utb_read_slots((uint32_t)length);
+        if (r == c->n_rec - 1) c->end_of_records = send;
+        hs = send;
+    }
+#undef NEXT_NL
+    c->groups[part] = groups;
+}
+
 static const char *fe_text(int code) {
     switch (code) {
     case FE_NOHEADER: return "ERROR: no header '>'";
@@ -503,18 +644,24 @@ static const char *fe_text(int code) {
  * *err is FE_* of the record at index *n_out (or FE_NONE), *dangling tells
  * that at EOF a header line is left without its sequence line. */
 static void frame_buffer(team_t *team, frame_ctx *F, size_t *n_out, size_t *n_complete, size_t *used, int *err, int *dangling) {
-    team_run(team, count_part, F);
+    int indexed = F->idx != NULL && F->fill < 0xFFFFFFFFull;
+    if (indexed) team_run(team, index_part, F); else team_run(team, count_part, F);
     size_t nl_total = 0;
-    for (int p = 0; p < team->n; ++p) { F->base[p] = nl_total; nl_total += F->cnt[p]; }
+    for (int p = 0; p < team->n; ++p) {
+        F->base[p] = nl_total; nl_total += F->cnt[p];
+        if (indexed && (F->idx_overflow[p] || F->has_nul[p])) indexed = 0;    /* dense newlines or a NUL: exact byte-wise path */
+    }
+    F->nl_total = nl_total;
     size_t n_lines = nl_total + ((F->eof && F->fill && F->buf[F->fill - 1] != '\n') ? 1 : 0);   /* a last line without '\n' counts at EOF */
     F->n_rec = n_lines / 2;
     *dangling = F->eof && (n_lines & 1);                       /* header whose sequence fgets fails (itree.c:871-872) */
     if (F->n_rec > F->max_rec) { F->n_rec = F->max_rec; *dangling = 0; }   /* the rest comes back with the carry */
     F->end_of_records = 0;
-    for (int p = 0; p < team->n; ++p) { F->err_rec[p] = (size_t)-1; F->err_code[p] = FE_NONE; }
-    if (F->n_rec) team_run(team, frame_part, F);
+    for (int p = 0; p < team->n; ++p) { F->err_rec[p] = (size_t)-1; F->err_code[p] = FE_NONE; F->groups[p] = 0; }
+    if (F->n_rec) team_run(team, indexed ? frame_indexed_part : frame_part, F);
     size_t n = F->n_rec; *err = FE_NONE;
     for (int p = 0; p < team->n; ++p) if (F->err_rec[p] < n) { n = F->err_rec[p]; *err = F->err_code[p]; }
+    F->groups_valid = indexed && n == F->n_rec;                /* per-worker sums cover exactly the framed records */
     *n_out = n; *n_complete = F->n_rec; *used = F->end_of_records;
 }
 
@@ -531,10 +678,13 @@ int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t ma
     frame_ctx F;
     memset(&F, 0, sizeof F);
     F.buf = buf; F.fill = n; F.eof = eof; F.max_rec = max_reads;
+    F.idx_cap = n / 8 + 64 * (size_t)MAX_TEAM + 64;
+    F.idx = (uint32_t *)malloc(F.idx_cap * sizeof(uint32_t));     /* NULL: the byte-wise path is used */
     F.seq_off = seq_off; F.seq_len = seq_len; F.name_off = name_off; F.name_len = name_len;
     size_t nr, nc, u; int err, dangling;
     frame_buffer(&team, &F, &nr, &nc, &u, &err, &dangling);
     team_destroy(&team);
+    free(F.idx);
     *n_reads = nr; *used = u;
     if (err) { utb_set_error("%s [L %zu]", fe_text(err), nr + 1); if (ref_exit) *ref_exit = 2; return UTB_ERR_FORMAT; }
     if (dangling) { utb_set_error("ERROR: can't read sequence L %zu", nr); if (ref_exit) *ref_exit = 2; return UTB_ERR_FORMAT; }
@@ -570,7 +720,8 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     uint64_t launches0 = 0;
     for (int i = 0; i < s->n_slots; ++i) { s->slots[i].state = 0; launches0 += utb_batch_launches(s->slots[i].b); }
     /* split the host threads between the two teams */
-    int T = s->host_threads, n_rd = T >= 4 ? T / 2 : 1, n_fm = T >= 4 ? T - n_rd : 1;
+    /* with the lines built on the device the formatter only moves finished text: most threads frame */
+    int T = s->host_threads, n_fm = T >= 4 ? (s->device_format ? (3 * T + 7) / 8 : T / 2) : 1, n_rd = T >= 4 ? T - n_fm : 1;
     team_t rd_team;
     if (team_init(&rd_team, n_rd) || team_init(&R.fmt_team, n_fm)) { utb_set_error("cannot start worker threads"); return UTB_ERR_NOMEM; }
     pthread_t fmt;
@@ -578,6 +729,13 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
 
     char *carry = (char *)malloc(s->batch_bytes);
     size_t carry_len = 0;
+    /* newline-index arena of the framer (one newline per 8 bytes; denser input takes the byte-wise path) */
+    size_t idx_cap = s->batch_bytes / 8 + 64 * (size_t)MAX_TEAM + 64;
+    uint32_t *idx = (uint32_t *)malloc(idx_cap * sizeof(uint32_t));
+    /* a caller buffer that is already page-locked is framed in place and copied to the device from where it
+     * lies: no staging memcpy, no carry (batches are just consecutive ranges of it) */
+    const int zero_copy = src->fd < 0 && src->mem_len && utb_host_ptr_is_pinned(src->mem) &&
+                          utb_host_ptr_is_pinned(src->mem + src->mem_len - 1);
     int rc = UTB_OK, fmt_err = 0;
     char fmt_msg[256] = "";
     uint64_t seq = 0, n_reads_total = 0;
@@ -592,19 +750,26 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         pthread_mutex_unlock(&R.mu);
         rd_t[0] += now_s() - tp; tp = now_s();
         if (dev_err) break;
-        char *buf = utb_batch_bytes(sl->b);
+        const char *buf = utb_batch_bytes(sl->b);
         size_t cap = utb_batch_max_bytes(sl->b), fill = carry_len;
-        if (carry_len) memcpy(buf, carry, carry_len);
-        carry_len = 0;
-        ssize_t k = src_fill(src, &rd_team, buf + fill, cap - fill);
-        if (k < 0) { rc = UTB_ERR_IO; utb_set_error("read error on input: %s", strerror(errno)); break; }
-        fill += (size_t)k;
+        if (zero_copy) {
+            buf = src->mem + src->mem_pos;
+            fill = src->mem_len - src->mem_pos < cap ? src->mem_len - src->mem_pos : cap;
+            if (src->mem_pos + fill == src->mem_len) src->eof = 1;
+        } else {
+            if (carry_len) memcpy(utb_batch_bytes(sl->b), carry, carry_len);
+            carry_len = 0;
+            ssize_t k = src_fill(src, &rd_team, utb_batch_bytes(sl->b) + fill, cap - fill);
+            if (k < 0) { rc = UTB_ERR_IO; utb_set_error("read error on input: %s", strerror(errno)); break; }
+            fill += (size_t)k;
+        }
         rd_t[1] += now_s() - tp; tp = now_s();
         if (!fill) break;                                          /* clean EOF */
 
         frame_ctx F;
         memset(&F, 0, sizeof F);
         F.buf = buf; F.fill = fill; F.eof = src->eof; F.max_rec = utb_batch_max_reads(sl->b);
+        F.idx = idx; F.idx_cap = idx ? idx_cap : 0;
         F.seq_off = utb_batch_seq_off(sl->b); F.seq_len = utb_batch_seq_len(sl->b);
         F.name_off = sl->name_off; F.name_len = sl->name_len;
         size_t n, n_complete, end_of_records; int err_code, dangling;
@@ -615,10 +780,18 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         uint64_t max_slots = utb_batch_max_slots(sl->b), groups = 0;
         int cut = 0;
         if (n > max_reads) { n = max_reads; cut = 1; }
-        for (size_t r = 0; r < n; ++r) {
-            uint64_t g = utb_read_slots(F.seq_len[r]);
-            if (groups + g > max_slots) { n = r; cut = 1; break; }
-            groups += g;
+        int groups_known = 0;
+        if (F.groups_valid && !cut) {                              /* the workers summed the groups while framing */
+            for (int p = 0; p < rd_team.n; ++p) groups += F.groups[p];
+            groups_known = groups <= max_slots;
+        }
+        if (!groups_known) {
+            groups = 0;
+            for (size_t r = 0; r < n; ++r) {
+                uint64_t g = utb_read_slots(F.seq_len[r]);
+                if (groups + g > max_slots) { n = r; cut = 1; break; }
+                groups += g;
+            }
         }
         if (cut) fmt_err = 0;                                      /* the bad record, if any, comes back with the carry */
         size_t used = (n == n_complete) ? end_of_records : (size_t)sl->name_off[n] - 1;
@@ -631,16 +804,19 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
             snprintf(fmt_msg, sizeof fmt_msg, "ERROR: record larger than the %zu-byte batch buffer", cap);
         }
         sl->n_reads = n;
+        sl->host_bytes = buf;
         sl->n_bytes = fmt_err ? fill : used;
         sl->first_read = n_reads_total;
         n_reads_total += n;
-        if (!fmt_err && used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
+        if (zero_copy) { src->mem_pos += fmt_err ? fill : used; if (src->mem_pos < src->mem_len) src->eof = 0; }
+        else if (!fmt_err && used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
         rd_t[2] += now_s() - tp; tp = now_s();
         if (n) {
             /* every sequence lies inside the first n_bytes of the buffer */
-            int r2 = utb_batch_submit(sl->b, fmt_err ? fill : used, n, do_rc);
+            int r2 = utb_batch_submit_ex(sl->b, zero_copy ? buf : NULL, fmt_err ? fill : used, n, do_rc, s->device_format,
+                                         groups_known && !cut ? groups : 0);
             if (r2) { rc = r2; break; }
-            R.st.h2d_bytes += (fmt_err ? fill : used) + n * 16 + 4;
+            R.st.h2d_bytes += (fmt_err ? fill : used) + n * (s->device_format ? 24 : 16) + 4;
             pthread_mutex_lock(&R.mu);
             sl->state = 1;
             R.submitted = ++seq;
@@ -651,6 +827,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         if (fmt_err) break;
         if (src->eof && !carry_len) break;
     }
+    free(idx);
     pthread_mutex_lock(&R.mu);
     R.done_reading = 1;
     pthread_cond_broadcast(&R.cv);
