@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256, FILT_MINB)
 filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
               uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
               uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
-              uint64_t q_cap) {
+              uint64_t q_cap, uint32_t *__restrict__ hitmap) {
     // persistent warps: each owns a private chunk of the queue, so the global
     // counter sees one atomic per Q_CHUNK survivors instead of one per warp-step
     const uint32_t lane = threadIdx.x & 31u;
@@ -554,7 +554,10 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
                     if (have_chunk) {
                         const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
                         q_words[idx] = w[u]; q_slots[idx] = (uint32_t)slot;
-                    } else { r = fast_lookup_cold(db, w[u]); if (r != HIT_MISS) hits[slot] = r; }   // queue full
+                    } else {                                       // queue full: resolve here
+                        r = fast_lookup_cold(db, w[u]);
+                        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); }
+                    }
                 }
                 chunk_used += c;
             }
@@ -573,7 +576,7 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
 __global__ void __launch_bounds__(256, 6)
 queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32_t *__restrict__ q_slots,
                     const unsigned long long *__restrict__ q_count, uint64_t q_cap,
-                    uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+                    uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
     const uint64_t n = *q_count < q_cap ? *q_count : q_cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t nh = 0, nsect = 0;
@@ -584,7 +587,7 @@ queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32
         uint32_t rr[1], sc;
         fast_lookup<1>(db, ww, rr, &sc);
         nsect += sc;
-        if (rr[0] != HIT_MISS) { hits[slot] = rr[0]; ++nh; }
+        if (rr[0] != HIT_MISS) { hits[slot] = rr[0]; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
     }
     for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); nsect += __shfl_xor_sync(0xFFFFFFFFu, nsect, o); }
     if ((threadIdx.x & 31u) == 0) {
@@ -699,6 +702,8 @@ struct VoteIn {            // where a read's hit slots live
     const uint32_t *seq_len;
     const uint64_t *off;       // stage-level mode: explicit ranges (overrides batch mode)
     uint32_t nstr;
+    // two-phase lookup: one bit per slot that holds a label; hits[] is then only valid where the bit is set
+    const uint32_t *hitmap;
 };
 __device__ __forceinline__ void vote_range(const VoteIn &in, uint32_t r, uint64_t &start, uint64_t &count) {
     if (in.off) { start = in.off[r]; count = in.off[r + 1] - start; return; }
@@ -738,7 +743,32 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
     __syncwarp();
     uint32_t n = 0;
     bool overflow = false;
-    // 128 slots per round (one uint4 per lane); most slots are empty, so a round without a label costs one ballot
+    if (in.hitmap) {
+        // sparse: scan the read's words of the hit map (1/32 of the slot bytes), gather only the flagged slots
+        const uint32_t *hm = in.hitmap + (start >> 5);             // start is a multiple of 32 in batch mode
+        const uint32_t nwords = (uint32_t)((count + 31) >> 5);
+        for (uint32_t wbase = 0; wbase < nwords; wbase += 32) {
+            uint32_t m = wbase + lane < nwords ? __ldg(hm + wbase + lane) : 0u;
+            while (__any_sync(0xFFFFFFFFu, m != 0)) {
+                uint32_t h = HIT_NOWIN;
+                if (m) { const uint32_t bit = __ffs(m) - 1; m &= m - 1; h = __ldg(in.hits + start + 32ull * (wbase + lane) + bit); }
+                const bool ok = h < db.max_ix;
+                n += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+                if (ok && (uint32_t)(__ffs(peers) - 1) == lane) {
+                    uint32_t cc = __popc(peers), slot = (h * 2654435761u) >> 26;
+                    for (uint32_t tries = 0;; ++tries) {
+                        if (tries == VW_SLOTS) { overflow = true; break; }
+                        uint32_t old = atomicCAS(&key[slot], UTB_BAD32, h);
+                        if (old == UTB_BAD32 || old == h) { atomicAdd(&cnt[slot], cc); break; }
+                        slot = (slot + 1) & (VW_SLOTS - 1);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+    // dense: 128 slots per round (one uint4 per lane); a round without a label costs one ballot
     const uint32_t mis = (uint32_t)((4u - (start & 3u)) & 3u);     // slots before the first 16-byte boundary
     for (uint64_t base = 0; base < count + 128; base += 128) {
         uint32_t hv[4];
@@ -778,6 +808,7 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
             }
             __syncwarp();
         }
+    }
     }
     if (__any_sync(0xFFFFFFFFu, overflow)) {
         if (lane == 0) gen_list[atomicAdd(gen_count, 1u)] = r;
@@ -833,6 +864,18 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
         vote_range(in, r, start, count);
         // 1. histogram (warp-aggregated global atomics) + foundUniq
         uint32_t n_local = 0;
+        if (in.hitmap) {
+            const uint32_t *hm = in.hitmap + (start >> 5);
+            const uint64_t nwords = (count + 31) >> 5;
+            for (uint64_t wi = tid; wi < nwords; wi += VB_THREADS) {
+                uint32_t m = __ldg(hm + wi);
+                while (m) {
+                    const uint32_t bit = __ffs(m) - 1; m &= m - 1;
+                    const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
+                    if (h < db.max_ix) { atomicAdd(&hist[h], 1u); ++n_local; }
+                }
+            }
+        } else
         for (uint64_t base = 0; base < count; base += VB_THREADS) {
             uint64_t i = base + tid;
             uint32_t h = i < count ? __ldg(in.hits + start + i) : HIT_NOWIN;
@@ -1249,6 +1292,7 @@ struct utb_batch {
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
+    uint32_t *d_hitmap;
     // last submit
     size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom;
     uint64_t launches;
@@ -1276,7 +1320,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
-    cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount);
+    cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -1338,6 +1382,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         BK(cudaMalloc(&b->d_qwords, b->q_cap * 8));
         BK(cudaMalloc(&b->d_qslots, b->q_cap * 4));
         BK(cudaMalloc(&b->d_qcount, 8));
+        BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
     }
     if (db->l2_window) {
         cudaStreamAttrValue a;
@@ -1376,19 +1421,19 @@ static int launch_stages(utb_batch *b, bool timed) {
         b->used_bloom = bloom;
         if (b->db->use_interp && bloom) {
             CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
-            // hits are sparse (only filter survivors that really match): one streaming fill instead of a dense
-            // store stream interleaved with the random filter reads
-            CK(cudaMemsetAsync(b->d_hits, 0xFF, (size_t)n_pos * nstr * 4, b->st));
+            // hits are sparse (only filter survivors that really match): the survivor kernel flags them in a
+            // 1-bit-per-slot map, the vote reads the map and gathers only flagged slots
+            CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st));
             if (timed) CK(cudaEventRecord(b->ev[4], b->st));
             const unsigned pb = nb < 148u * FILT_MINB ? nb : 148u * FILT_MINB;   // persistent: FILT_MINB CTAs per SM
             const char *dg = getenv("UTB_FILT_DIAG");
             const int diag = dg ? atoi(dg) : 0;
-            if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
-            else if (diag == 2) filter_kernel<2, 2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
-            else if (nstr == 2) filter_kernel<2, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
-            else filter_kernel<1, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap);
+            if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else if (diag == 2) filter_kernel<2, 2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else if (nstr == 2) filter_kernel<2, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else filter_kernel<1, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
-            queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_counters);
+            queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
             b->launches++;
         } else if (b->db->use_interp) {
             if (nstr == 2) lookup_kernel<2, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
@@ -1403,6 +1448,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     if (n_reads) {
         VoteIn in;
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
+        in.hitmap = b->used_bloom ? b->d_hitmap : nullptr;
         vote_warp_kernel<<<(n_reads + VW_WARPS - 1) / VW_WARPS, VW_WARPS * 32, 0, b->st>>>(
             d, in, n_reads, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
         vote_block_kernel<<<VB_BLOCKS, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
@@ -1669,7 +1715,7 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
-    VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1;
+    VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = nullptr;
     vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, d_res, d_gl, d_gc, d_cnt);
     vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
     CK(cudaGetLastError());
