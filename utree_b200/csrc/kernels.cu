@@ -827,14 +827,18 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
         if (lane == 0) { out->kind = UTB_STAR; out->label = lab; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
         return;
     }
-    // sort the <= 64 entries by label rank (strcmp order, itree.c:1041)
+    // sort the entries by label rank (strcmp order, itree.c:1041): compact the occupied slots first -- a read
+    // typically holds 2-3 labels, so ranking costs uix compares per entry instead of a sweep over all 64 slots
     uint32_t *rk = s_rk[wib], *T_lab = s_lab[wib], *T_cnt = s_tc[wib];
-    uint32_t r0 = k0 != UTB_BAD32 ? __ldg(db.rank + k0) : UTB_BAD32;
-    uint32_t r1 = k1 != UTB_BAD32 ? __ldg(db.rank + k1) : UTB_BAD32;
-    rk[lane] = r0; rk[lane + 32] = r1;
+    const uint32_t r0 = k0 != UTB_BAD32 ? __ldg(db.rank + k0) : UTB_BAD32;
+    const uint32_t r1 = k1 != UTB_BAD32 ? __ldg(db.rank + k1) : UTB_BAD32;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t i0 = __popc(m0 & lt), i1 = __popc(m0) + __popc(m1 & lt);
+    if (k0 != UTB_BAD32) rk[i0] = r0;
+    if (k1 != UTB_BAD32) rk[i1] = r1;
     __syncwarp();
     uint32_t p0 = 0, p1 = 0;
-    for (uint32_t j = 0; j < VW_SLOTS; ++j) { uint32_t x = rk[j]; p0 += x < r0; p1 += x < r1; }
+    for (uint32_t j = 0; j < uix; ++j) { const uint32_t x = rk[j]; p0 += x < r0; p1 += x < r1; }
     if (k0 != UTB_BAD32) { T_lab[p0] = k0; T_cnt[p0] = cnt[lane]; }
     if (k1 != UTB_BAD32) { T_lab[p1] = k1; T_cnt[p1] = cnt[lane + 32]; }
     __syncwarp();
