@@ -317,3 +317,41 @@ def test_zero_copy_from_pinned_caller_buffer(gpu, host_format):
         assert text.startswith(want_b) and st["reads"] == st2["reads"]
     finally:
         s.destroy()
+
+
+@pytest.mark.parametrize("env", [{"UTB_BLOOM": "0"}, {"UTB_BLOOM": "1"}, {"UTB_LOOKUP": "exact"}])
+@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[5], CASES[7]])
+def test_every_lookup_variant_gives_the_reference_output(ctrs, tmp_path, env, db_name, reads, out, rc):
+    """Whole search with the pre-filter forced off (fused key-window kernel), forced on (two-phase),
+    and with the reference probe sequence: identical bytes."""
+    from utree_b200 import capi
+    os.environ.update(env)
+    try:
+        ctr = capi.Ctr(ctrs[db_name])
+        s = capi.Searcher(ctr, devices=(0,), host_threads=3)
+    finally:
+        for k in env:
+            del os.environ[k]
+    try:
+        code, ref_exit, text, st = s.search_mem(open(gold(reads), "rb").read(), do_rc=bool(rc))
+        assert code == 0 and text == open(gold(out), "rb").read()
+    finally:
+        s.destroy(); ctr.close()
+
+
+@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[5], CASES[7]])
+def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, reads, out, rc):
+    """UTB_PARTITION=1 forces the large-batch path (shared-memory counting sort into 64 filter-slice
+    partitions + cooperative probe sweep) on small inputs: identical bytes."""
+    from utree_b200 import capi
+    os.environ["UTB_PARTITION"] = "1"
+    try:
+        ctr = capi.Ctr(ctrs[db_name])
+        s = capi.Searcher(ctr, devices=(0,), host_threads=3)
+    finally:
+        del os.environ["UTB_PARTITION"]
+    try:
+        code, ref_exit, text, st = s.search_mem(open(gold(reads), "rb").read(), do_rc=bool(rc))
+        assert code == 0 and text == open(gold(out), "rb").read()
+    finally:
+        s.destroy(); ctr.close()

@@ -23,12 +23,14 @@
 // sequence, itree.c:699-730), vote_warp_kernel / vote_block_kernel (full
 // aufbau vote, itree.c:1028-1098).
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "utb_internal.h"
 
+namespace cg = cooperative_groups;
 #define SUFMASK 0xFFFFFFFFFFull
 #define HIT_MISS 0xFFFFFFFFu   // looked up, not found (BAD_IX widened)
 #define HIT_NOWIN 0xFFFFFFFEu  // no valid 32-mer window here: no lookup made
@@ -75,9 +77,9 @@ struct utb_db {
     int use_interp;            // lookup kernel variant in use
     void *binix, *recs, *blob, *off, *rank, *by_rank, *keys, *aux, *bloom;
     int bloom_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
-    double ema_hit_rate;       // of the batches seen so far
+    volatile double ema_hit_rate;   // of the batches seen so far (written by the formatter thread, read at submit)
     size_t max_label;          // longest label, bytes
-    double text_per_read;      // running estimate of output bytes per read (sizes the speculative text D2H)
+    volatile double text_per_read;  // running estimate of output bytes per read (sizes the speculative text D2H)
     uint64_t hbm_bytes;
     int l2_window;             // persisting-L2 window over binix configured
     size_t l2_window_bytes;
@@ -571,6 +573,163 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
         if (nv) atomicAdd(counters + cs, (unsigned long long)nv);
         if (nh) atomicAdd(counters + COUNTER_SLOTS + cs, (unsigned long long)nh);
     }
+}
+
+// ---- partitioned filter pass (UTB_PARTITION=1) -------------------------------------
+// One random 128-byte DRAM line per probe is what bounds filter_kernel.  Here the
+// lookups of a batch are first bucketed by the top 6 bits of the filter hash
+// (64 partitions = 64 contiguous ~34 MB slices of the filter): partition_kernel
+// streams (word, slot) records into per-partition arrays (12 B per lookup,
+// sequential), then probe_kernel sweeps the partitions in order with the whole
+// grid, so the slice being probed stays resident in the 126 MB L2 and each of its
+// lines is fetched from HBM once per batch instead of once per probe.
+#define NPART 64u
+#define PART_MIN_SLOTS (400ull << 20)   // lookup slots in a batch from which the partitioned pass is used (~1.3 M reads of 150 bp)
+#define P_CTAS (148u * 4u)      // partitioner CTAs; each owns one output region per partition
+#define P_TILE 4096u            // slots a CTA sorts in shared memory at a time
+#define P_SMEM (P_TILE * 8u + P_TILE * 4u + P_TILE)   // words + slots + partition ids
+// Partitioner: every CTA counting-sorts one 4096-slot tile at a time in shared memory and appends each
+// partition's run to its own region [(c*NPART+p)*cap_cp, +cap_cp), so the global stores are contiguous
+// runs (~47 records) instead of one transaction per record (scattered 8-byte stores cost as much as
+// scattered sector reads, profiles/).  No global atomics; the fill of every region is stored at the end.
+// Hash partitions are uniform and every CTA sees the same share of the batch, so regions fill evenly
+// (cap_cp carries 25 % head-room; an overflowing record is resolved inline).
+template <int NSTR>
+__global__ void __launch_bounds__(256, 4)
+partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
+                 unsigned long long *__restrict__ counters,
+                 uint64_t *__restrict__ p_words, uint32_t *__restrict__ p_slots, uint32_t *__restrict__ p_fill,
+                 uint32_t cap_cp, uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
+    extern __shared__ __align__(16) unsigned char p_smem[];
+    uint64_t *s_words = reinterpret_cast<uint64_t *>(p_smem);
+    uint32_t *s_slots = reinterpret_cast<uint32_t *>(p_smem + P_TILE * 8u);
+    uint8_t *s_part = p_smem + P_TILE * 12u;
+    __shared__ uint32_t s_hist[NPART], s_start[NPART], s_cur[NPART];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint64_t n_slots = (uint64_t)n_pos * NSTR;
+    if (tid < NPART) s_cur[tid] = 0;
+    uint32_t nv = 0, nh = 0;
+    const uint64_t region0 = (uint64_t)blockIdx.x * NPART * cap_cp;
+    for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_slots; tile += (uint64_t)gridDim.x * P_TILE) {
+        if (tid < NPART) s_hist[tid] = 0;
+        __syncthreads();
+        // pass A: partition id and rank inside the tile (the word is recomputed in pass B: cheaper than 16 live u64)
+        uint32_t meta[P_TILE / 256];                               // rank << 8 | part, or 0xFFFFFFFF
+#pragma unroll
+        for (uint32_t k = 0; k < P_TILE / 256; ++k) {
+            const uint64_t slot = tile + k * 256u + tid;
+            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+            uint64_t w;
+            meta[k] = 0xFFFFFFFFu;
+            if (slot < n_slots && window_at(pk, bad, pos, w)) {
+                if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
+                const uint32_t part = (uint32_t)(mix64(w) >> 58);
+                meta[k] = (atomicAdd(&s_hist[part], 1u) << 8) | part;
+                ++nv;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {                                            // exclusive scan of the 64 bins by one warp
+            const uint32_t h0 = s_hist[2 * tid], h1 = s_hist[2 * tid + 1];
+            uint32_t x = h0 + h1;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((int)tid >= o) x += t; }
+            s_start[2 * tid] = x - h0 - h1; s_start[2 * tid + 1] = x - h1;
+        }
+        __syncthreads();
+        // pass B: scatter into shared memory in partition order
+#pragma unroll
+        for (uint32_t k = 0; k < P_TILE / 256; ++k) {
+            if (meta[k] == 0xFFFFFFFFu) continue;
+            const uint64_t slot = tile + k * 256u + tid;
+            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+            uint64_t w;
+            window_at(pk, bad, pos, w);
+            if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
+            const uint32_t part = meta[k] & 0xFFu, dst = s_start[part] + (meta[k] >> 8);
+            s_words[dst] = w; s_slots[dst] = (uint32_t)slot; s_part[dst] = (uint8_t)part;
+        }
+        __syncthreads();
+        // pass C: contiguous runs out to the regions
+        const uint32_t total = s_start[NPART - 1] + s_hist[NPART - 1];
+        for (uint32_t e = tid; e < total; e += 256) {
+            const uint32_t part = s_part[e], at = s_cur[part] + (e - s_start[part]);
+            if (at < cap_cp) {
+                const uint64_t idx = region0 + (uint64_t)part * cap_cp + at;
+                p_words[idx] = s_words[e]; p_slots[idx] = s_slots[e];
+            } else if (bloom_maybe(db, s_words[e])) {              // region full: resolve here
+                const uint32_t r = fast_lookup_cold(db, s_words[e]);
+                if (r != HIT_MISS) { hits[s_slots[e]] = r; atomicOr(hitmap + (s_slots[e] >> 5), 1u << (s_slots[e] & 31u)); ++nh; }
+            }
+        }
+        __syncthreads();
+        if (tid < NPART) s_cur[tid] += s_hist[tid];
+    }
+    __syncthreads();
+    if (tid < NPART) p_fill[blockIdx.x * NPART + tid] = s_cur[tid] < cap_cp ? s_cur[tid] : cap_cp;
+    for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xFFFFFFFFu, nv, o); nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); }
+    if (lane == 0) {
+        const uint32_t cs = (blockIdx.x * 8 + (tid >> 5)) & (COUNTER_SLOTS - 1);
+        if (nv) atomicAdd(counters + cs, (unsigned long long)nv);
+        if (nh) atomicAdd(counters + COUNTER_SLOTS + cs, (unsigned long long)nh);
+    }
+}
+
+// Probe pass (cooperative launch): the whole grid sweeps partition 0, then 1, ... with a grid barrier in
+// between, so exactly one ~34 MB slice of the filter is live in L2 at a time; the records are read with
+// streaming loads (evict-first) so that they do not push that slice out.
+#define P_SUB 1024u             // records of a region one warp takes at a time
+__global__ void __launch_bounds__(256, 6)
+probe_kernel(DevDB db, const uint64_t *__restrict__ p_words, const uint32_t *__restrict__ p_slots,
+             const uint32_t *__restrict__ p_fill, uint32_t cap_cp, uint32_t n_ctas,
+             uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count, uint64_t q_cap,
+             uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
+    cg::grid_group grid = cg::this_grid();
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t subs = (cap_cp + P_SUB - 1) / P_SUB;            // work items per region
+    uint64_t chunk_base = 0;
+    uint32_t chunk_used = Q_CHUNK, nh = 0;
+    bool have_chunk = false;
+    for (uint32_t part = 0; part < NPART; ++part) {
+        for (uint32_t item = gwarp; item < n_ctas * subs; item += n_warps) {
+            const uint32_t c = item / subs, sub = item % subs;
+            const uint32_t fill = __ldg(p_fill + c * NPART + part);
+            const uint64_t base = ((uint64_t)c * NPART + part) * cap_cp;
+            const uint32_t j1 = min(fill, (sub + 1) * P_SUB);
+            for (uint32_t j0 = sub * P_SUB; j0 < j1; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const bool live = j < j1;
+                const uint64_t w = live ? __ldcs(p_words + base + j) : 0;
+                const bool pass = live && bloom_maybe(db, w);
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
+                const uint32_t cnt = __popc(m);
+                if (!cnt) continue;
+                if (chunk_used + cnt > Q_CHUNK) {
+                    if (have_chunk) for (uint32_t k = chunk_used + lane; k < Q_CHUNK; k += 32) q_slots[chunk_base + k] = Q_INVALID;
+                    unsigned long long nb = 0;
+                    if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
+                    chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
+                    chunk_used = 0;
+                    have_chunk = chunk_base + Q_CHUNK <= q_cap;
+                }
+                if (pass) {
+                    const uint32_t slot = __ldcs(p_slots + base + j);
+                    if (have_chunk) {
+                        const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
+                        q_words[idx] = w; q_slots[idx] = slot;
+                    } else {
+                        const uint32_t r = fast_lookup_cold(db, w);
+                        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
+                    }
+                }
+                chunk_used += cnt;
+            }
+        }
+        grid.sync();
+    }
+    if (have_chunk) for (uint32_t k = chunk_used + lane; k < Q_CHUNK; k += 32) q_slots[chunk_base + k] = Q_INVALID;
+    for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
+    if (lane == 0 && nh) atomicAdd(counters + COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)nh);
 }
 
 __global__ void __launch_bounds__(256, 6)
@@ -1139,6 +1298,7 @@ static int upload_streamed(void *dst, const void *src, size_t n, cudaStream_t st
     return UTB_OK;
 }
 
+static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db);
 extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
     if (!ctr || !out) { utb_set_error("utb_db_upload: null argument"); return UTB_ERR_ARG; }
     *out = nullptr;
@@ -1148,6 +1308,13 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
     utb_db *db = (utb_db *)calloc(1, sizeof(utb_db));
     if (!db) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     db->device = device;
+    rc = db_upload_impl(ctr, device, db);
+    if (rc) { utb_db_free(db); return rc; }                        // device buffers allocated so far are released
+    *out = db;
+    return UTB_OK;
+}
+static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db) {
+    int rc;
     cudaStream_t st;
     CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
     size_t nb_binix = (size_t)UTB_NUMBINS * ctr->binix_bytes;
@@ -1258,7 +1425,6 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
                 p.persistingL2CacheMaxSize >> 20, pl >> 20, p.accessPolicyMaxWindowSize >> 20, fgv,
                 db->l2_window_bytes >> 20, db->l2_hit_ratio);
     }
-    *out = db;
     return UTB_OK;
 }
 
@@ -1297,6 +1463,7 @@ struct utb_batch {
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
+    uint64_t *d_pwords; uint32_t *d_pslots; uint32_t *d_pfill; uint64_t p_total, part_min_slots;   // partitioned filter pass
     // last submit
     size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom;
     uint64_t launches;
@@ -1325,6 +1492,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
+    cudaFree(b->d_pwords); cudaFree(b->d_pslots); cudaFree(b->d_pfill);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -1387,6 +1555,16 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         BK(cudaMalloc(&b->d_qslots, b->q_cap * 4));
         BK(cudaMalloc(&b->d_qcount, 8));
         BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
+        // Partitioned filter pass: pays once a batch holds enough lookups for the probes of a partition to
+        // reuse its filter lines (and to amortise 64 grid barriers); UTB_PARTITION=1 forces it, =0 disables it.
+        const char *pe = getenv("UTB_PARTITION");
+        b->part_min_slots = pe ? (atoi(pe) ? 0 : ~0ull) : PART_MIN_SLOTS;
+        if (npos * 2 >= b->part_min_slots) {                        // one region per (CTA, partition), 25 % head-room
+            b->p_total = (uint64_t)((double)(npos * 2) * 1.25) + (uint64_t)P_CTAS * NPART * 64;
+            BK(cudaMalloc(&b->d_pwords, b->p_total * 8));
+            BK(cudaMalloc(&b->d_pslots, b->p_total * 4));
+            BK(cudaMalloc(&b->d_pfill, (size_t)P_CTAS * NPART * 4));
+        }
     }
     if (db->l2_window) {
         cudaStreamAttrValue a;
@@ -1432,7 +1610,29 @@ static int launch_stages(utb_batch *b, bool timed) {
             const unsigned pb = nb < 148u * FILT_MINB ? nb : 148u * FILT_MINB;   // persistent: FILT_MINB CTAs per SM
             const char *dg = getenv("UTB_FILT_DIAG");
             const int diag = dg ? atoi(dg) : 0;
-            if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            if (b->d_pwords && !diag && (uint64_t)n_pos * nstr >= b->part_min_slots) {
+                const uint64_t n_slots = (uint64_t)n_pos * nstr;
+                const unsigned tiles = (unsigned)((n_slots + P_TILE - 1) / P_TILE);
+                const unsigned gb = tiles < P_CTAS ? tiles : P_CTAS;
+                uint32_t cap_cp = (uint32_t)((double)n_slots / ((double)gb * NPART) * 1.25) + 64;   // <= p_total / (gb * NPART)
+                if (nstr == 2) {
+                    CK(cudaFuncSetAttribute(partition_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+                    partition_kernel<2><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_pslots, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
+                } else {
+                    CK(cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+                    partition_kernel<1><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_pslots, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
+                }
+                // cooperative launch: the grid barrier between partitions needs every CTA resident
+                int per_sm = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel, 256, 0));
+                if (per_sm > 6) per_sm = 6;
+                unsigned pgrid = 148u * (unsigned)(per_sm > 0 ? per_sm : 1), n_ctas = gb;
+                DevDB dd = d;
+                void *args[] = {&dd, &b->d_pwords, &b->d_pslots, &b->d_pfill, &cap_cp, &n_ctas, &b->d_qwords, &b->d_qslots,
+                                &b->d_qcount, &b->q_cap, &b->d_hits, &b->d_hitmap, &b->d_counters};
+                CK(cudaLaunchCooperativeKernel((void *)probe_kernel, dim3(pgrid), dim3(256), args, 0, b->st));
+                b->launches++;
+            } else if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             else if (diag == 2) filter_kernel<2, 2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             else if (nstr == 2) filter_kernel<2, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             else filter_kernel<1, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
