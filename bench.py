@@ -260,12 +260,11 @@ def main():
     # ---- database resident in HBM ---------------------------------------------
     t = time.time()
     ctr = capi.Ctr(ctr_path)
-    searcher = capi.Searcher(ctr, devices=(local,), host_threads=max(2, ncpu // max(world, 1)))
+    db = capi.Db(ctr, local)
     db_load_s = time.time() - t
     log(f"rank {rank}: CTR resident in HBM in {db_load_s:.1f} s ({ctr.num_nodes} records, {ctr.max_ix} labels)")
 
     # ---- value: device-resident pass ---------------------------------------------
-    db = capi.Db(ctr, local)      # second handle for the resident batch (the searcher owns its own)
     batch = capi.Batch(db, reads_np.size, n_reads)
     batch.bytes[:reads_np.size] = reads_np
     r = np.arange(n_reads, dtype=np.uint64)
@@ -280,7 +279,7 @@ def main():
         batch.rerun_device(1)
     barrier()
     ms_sum = np.zeros(4)
-    det_ms, det_sect = np.zeros(2), [0, 0]
+    det_ms, det_sect, part_ms = np.zeros(2), [0, 0], np.zeros(2)
     launches = 0
     for _ in range(args.steps):
         ms, l = batch.rerun_device(1)
@@ -288,8 +287,12 @@ def main():
         launches += l
         dm, det_sect = batch.lookup_detail()
         det_ms += np.array(dm)
+        part_ms += np.array(batch.partition_detail())
     barrier()
     dev_s = ms_sum[3] / 1e3
+    lookup_mode, hbm_bytes = db.lookup_mode(), int(db.hbm_bytes())
+    batch.destroy(); db.free()          # the e2e searcher below uploads its own copy: never both resident at once
+    searcher = capi.Searcher(ctr, devices=(local,), host_threads=max(2, ncpu // max(world, 1)))
 
     # ---- e2e: host buffers through the C ABI --------------------------------------
     import ctypes
@@ -342,12 +345,25 @@ def main():
         # Reference-layout figure of SURVEY 8d: bytes the reference's own probe sequence would touch.
         ref_bytes = sect["bytes_per_lookup"] * lookups
         ref_equiv = ref_bytes / (lookup_ms * 1e-3) / 1e9
-        if two_phase:
+        partitioned = part_ms[1] > 0
+        filter_bytes = 16.0 * (ctr.num_nodes // 8 + 1024)          # the Bloom filter, read once per partition sweep
+        if two_phase and partitioned:
+            # phase A = partition_kernel (stream: 12 B per lookup out) + probe_kernel (12 B per lookup in, the filter
+            # once, every probe an L2 hit on the partition's resident slice); the longer of the two is the dominant kernel
+            pm, qm = part_ms[0] / args.steps, part_ms[1] / args.steps
+            if qm >= pm:
+                k_name, k_ms = "probe_kernel (partitioned Bloom probes, cooperative sweep of 64 L2-resident filter slices)", qm
+                k_bytes = 12.0 * det_sect[0] + filter_bytes
+            else:
+                k_name, k_ms = "partition_kernel<2> (shared-memory counting sort of lookups into 64 filter-slice partitions)", pm
+                k_bytes = 12.0 * det_sect[0] + 0.375 * 160 * n_reads
+            stage_bytes = 24.0 * det_sect[0] + filter_bytes + 32.0 * det_sect[1]
+        elif two_phase:
             # dominant kernel = filter_kernel: one 32-byte sector per lookup, nothing else to read
             k_name, k_ms = "filter_kernel<2> (Bloom pre-filter, phase A of the two-phase lookup)", det_ms[0] / args.steps
             k_bytes = 32.0 * det_sect[0]
             stage_bytes = 32.0 * (det_sect[0] + det_sect[1])
-        elif db.lookup_mode():
+        elif lookup_mode:
             k_name, k_ms = "lookup_kernel<2,true,false> (key-window search)", lookup_ms
             k_bytes = stage_bytes = None          # not instrumented in the fused kernel
         else:
@@ -356,26 +372,37 @@ def main():
         if k_bytes is None:
             k_bytes = stage_bytes = ref_bytes
         achieved = k_bytes / (k_ms * 1e-3) / 1e9
+        stream_bound = two_phase and partitioned                     # streaming kernels are held against the copy peak
         # ncu dram__bytes_read+write per launch of the same kernel/workload shape, when a capture is committed
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            per_lookup = tr.get(args.config, {}).get("filter_kernel_dram_bytes_per_lookup" if two_phase else "lookup_kernel_dram_bytes_per_lookup")
+            key = ("probe_kernel_dram_bytes_per_lookup" if "probe_kernel" in k_name else "partition_kernel_dram_bytes_per_lookup") if stream_bound \
+                else ("filter_kernel_dram_bytes_per_lookup" if two_phase else "lookup_kernel_dram_bytes_per_lookup")
+            per_lookup = tr.get(args.config, {}).get(key)
             traffic = round(per_lookup * lookups) if per_lookup else None
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": k_name, "achieved": round(achieved, 1), "peak": round(rand32, 1),
-                    "unit": "GB/s", "frac": round(achieved / rand32, 4), "traffic": traffic,
-                    "algorithmic_bytes": "32 B x the sectors the kernel must touch (one per filter probe), counted on the device",
-                    "peak_kind": "measured random 32B-sector gather, 8 GiB working set (utb_measure_rand32); the L2 fills whole "
-                                 "128 B lines, so this equals ~6 TB/s of DRAM reads (profiles/r01_membench_ncu.txt)",
+        peak = stream_peak if stream_bound else rand32
+        roofline = {"bound": "hbm", "kernel": k_name, "achieved": round(achieved, 1), "peak": round(peak, 1),
+                    "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                    "algorithmic_bytes": ("12 B per lookup record + the 2.2 GB filter once (streamed); the probes themselves are L2 hits"
+                                          if stream_bound else
+                                          "32 B x the sectors the kernel must touch (one per filter probe), counted on the device"),
+                    "peak_kind": ("MEASURED_PEAKS.json hbm_gbs (streaming copy)" if stream_bound else
+                                  "measured random 32B-sector gather, 8 GiB working set (utb_measure_rand32); the L2 fills whole "
+                                  "128 B lines, so this equals ~6 TB/s of DRAM reads (profiles/r01_membench_ncu.txt)"),
+                    "rand32_peak": round(rand32, 1),
+                    "l2_probes_per_s": round(det_sect[0] / (part_ms[1] / args.steps * 1e-3), 1) if stream_bound else None,
+                    "phase_a_ms": {"partition_kernel": round(float(part_ms[0] / args.steps), 3), "probe_kernel": round(float(part_ms[1] / args.steps), 3)}
+                                  if stream_bound else {"filter_kernel": round(float(det_ms[0] / args.steps), 3)},
                     "stream_peak": stream_peak, "stream_peak_kind": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                     "dram_line_fill_frac_of_stream": round(achieved * 4 / stream_peak, 4),
                     "kernel_ms": round(float(k_ms), 3), "kernel_share_of_step": round(float(k_ms * args.steps / ms_sum[3]), 4),
                     "lookups_per_launch": lookups,
                     "lookup_stage": {"ms": round(float(lookup_ms), 3), "bytes": stage_bytes,
                                      "gbs": round(stage_bytes / (lookup_ms * 1e-3) / 1e9, 1),
-                                     "frac": round(stage_bytes / (lookup_ms * 1e-3) / 1e9 / rand32, 4),
+                                     "frac": round(stage_bytes / (lookup_ms * 1e-3) / 1e9 / peak, 4),
                                      "survivor_kernel_ms": round(float(det_ms[1] / args.steps), 3),
                                      "sectors_per_lookup": round((det_sect[0] + det_sect[1]) / max(lookups, 1), 3) if two_phase else None},
                     "reference_layout_equiv": {"bytes_per_lookup": round(sect["bytes_per_lookup"], 2), "gbs": round(ref_equiv, 1),
@@ -410,10 +437,10 @@ def main():
                                                                  "fm_wait_gpu", "fm_format", "fm_emit", "seconds_device")}},
             "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "db": {"records": int(ctr.num_nodes), "labels": int(ctr.max_ix), "file_bytes": ctr_meta["bytes"],
-                   "hbm_bytes": int(db.hbm_bytes()), "load_s": round(db_load_s, 1)},
+                   "hbm_bytes": hbm_bytes, "load_s": round(db_load_s, 1)},
             "hit_rate": round(hits / max(lookups, 1), 4), "lookups_per_read": round(lookups / n_reads, 2),
         }
-    batch.destroy(); db.free(); searcher.destroy(); ctr.close()
+    searcher.destroy(); ctr.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

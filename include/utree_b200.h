@@ -128,6 +128,9 @@ int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits);
  * the exact search touched for the survivors.  All zero when the single lookup
  * kernel ran (pre-filter off). */
 int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]);
+/* Large batches split phase A into partition_kernel + probe_kernel (ms[0], ms[1]);
+ * both 0 when the direct filter kernel ran. */
+int utb_batch_partition_detail(utb_batch *b, float ms[2]);
 
 /* ---- stage-level entry points (parity tests call the kernels 1:1) --------- */
 /* words[n] (host) -> ix[n] (host): label id or 0xFFFFFFFF, exactly

@@ -257,7 +257,8 @@ enum { FW_MISS = 0, FW_FOUND = 1, FW_LEFT = 2, FW_RIGHT = 3, FW_SLOW = 4 };
 struct FastProbe {
     uint64_t a, b;      // bucket [a,b), quirk-adjusted
     uint64_t ws;        // first key of the current window (multiple of KW)
-    uint64_t pos;       // FW_FOUND: index of the only key equal to t in the window
+    uint64_t pos;       // FW_FOUND: index of the first key equal to t in the window
+    uint32_t cnt;       // FW_FOUND: length of the run of equal keys (records that differ only in the suffix's low byte)
     uint32_t t, lo8;    // target key and the suffix's low byte
     int st;
 };
@@ -270,7 +271,7 @@ __device__ __forceinline__ void fast_begin(const DevDB &db, uint64_t word, FastP
     q.t = (uint32_t)(suf >> 8); q.lo8 = (uint32_t)(suf & 0xFFu);
     bool live = a < b && b <= db.num_nodes;                        // itree.c:726 (+ bounds guard)
     if (live && (uint32_t)p == db.quirk_bin) { a += 1; live = a < b; }   // record 0 is unreachable for xtSuffixBS
-    q.a = a; q.b = b; q.pos = 0;
+    q.a = a; q.b = b; q.pos = 0; q.cnt = 0;
     q.st = live ? FW_LEFT : FW_MISS;                               // any non-final state: "window pending"
     q.ws = live ? ((a + __umul64hi(suf << 24, b - a)) & ~(uint64_t)(KW - 1)) : 0;   // a + floor(n*s/2^40) < b
 }
@@ -278,9 +279,11 @@ __device__ __forceinline__ void fast_begin(const DevDB &db, uint64_t word, FastP
 // line in L2, so the neighbouring sectors a later step may need are L2 hits;
 // asking for them up front would cost as much as further misses
 // (profiles/r01_membench_ncu.txt).
-__device__ __forceinline__ void window_step(const DevDB &db, FastProbe &q) {
+__device__ __forceinline__ void window_fetch(const DevDB &db, const FastProbe &q, uint4 &k0, uint4 &k1) {
     const uint4 *p = reinterpret_cast<const uint4 *>(db.keys + q.ws);
-    const uint4 k0 = __ldg(p), k1 = __ldg(p + 1);
+    k0 = __ldg(p); k1 = __ldg(p + 1);
+}
+__device__ __forceinline__ void window_rank(FastProbe &q, const uint4 &k0, const uint4 &k1) {
     const uint32_t kk[KW] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
     const uint64_t wa = q.ws > q.a ? q.ws : q.a, wb = q.ws + KW < q.b ? q.ws + KW : q.b;
     const uint32_t j0 = (uint32_t)(wa - q.ws), j1 = (uint32_t)(wb - q.ws);   // in-bucket slots [j0, j1)
@@ -296,8 +299,7 @@ __device__ __forceinline__ void window_step(const DevDB &db, FastProbe &q) {
         if (lt == 0 && left_open) { q.st = FW_LEFT; q.ws -= KW; }             // every key here is larger
         else if (lt == j1 - j0 && right_open) { q.st = FW_RIGHT; q.ws += KW; } // every key here is smaller
         else q.st = FW_MISS;
-    } else if (eq == 1) { q.st = FW_FOUND; q.pos = wa + lt; }
-    else q.st = FW_SLOW;                                           // equal 32-bit keys: needs the low byte to order
+    } else { q.st = FW_FOUND; q.pos = wa + lt; q.cnt = eq; }       // eq > 1: k-mers of related genomes that differ in the last 4 bases
 }
 __device__ __forceinline__ uint64_t load_aux(const DevDB &db, uint64_t i) {
     return db.aux32 ? (uint64_t)__ldg(db.aux32 + i) : __ldg(db.aux64 + i);
@@ -325,33 +327,53 @@ __device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)
     uint32_t ns = 0;
 #pragma unroll
     for (int i = 0; i < N; ++i) fast_begin(db, w[i], q[i]);
+    int dir[N];
+    bool act[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         ns += ((w[i] >> 40) & 7u) == 7u ? 2u : 1u;                 // BinIx[p], BinIx[p+1]: 4-byte entries, 8 per sector
-        if (q[i].st == FW_MISS) continue;                          // empty bucket
-        int dir = 0;                                               // direction of the last move
-        for (int step = 0; step < FW_MAX_STEPS; ++step) {
-            ++ns;
-            window_step(db, q[i]);
-            if (q[i].st != FW_LEFT && q[i].st != FW_RIGHT) break;
-            if (dir && q[i].st != dir) { q[i].st = FW_MISS; break; }   // turned around: the target falls between two adjacent windows
-            dir = q[i].st;
-        }
-        if (q[i].st == FW_LEFT || q[i].st == FW_RIGHT) q[i].st = FW_SLOW;   // estimate off by several sectors
+        dir[i] = 0; act[i] = q[i].st != FW_MISS;                   // empty bucket: nothing to search
     }
-    // hits fetch low byte + id; a neighbour key is checked when the match sits on a window edge
+    // the N searches advance in lock-step: all key sectors of a step are requested before any is ranked
+    for (int step = 0; step < FW_MAX_STEPS; ++step) {
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) any |= act[i];
+        if (!any) break;
+        uint4 k0[N], k1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) if (act[i]) { ++ns; window_fetch(db, q[i], k0[i], k1[i]); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (!act[i]) continue;
+            window_rank(q[i], k0[i], k1[i]);
+            if (q[i].st != FW_LEFT && q[i].st != FW_RIGHT) act[i] = false;
+            else if (dir[i] && q[i].st != dir[i]) { q[i].st = FW_MISS; act[i] = false; }   // turned around: between two adjacent windows
+            else dir[i] = q[i].st;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) if (q[i].st == FW_LEFT || q[i].st == FW_RIGHT) q[i].st = FW_SLOW;   // estimate off by several sectors
+    // matches fetch low byte + id of every record in the run of equal keys (one sector of aux); a neighbour key is
+    // checked when the run touches an open window edge, because it could continue outside
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         r[i] = HIT_MISS;
         if (q[i].st == FW_FOUND) {
             ++ns;
-            const uint64_t ax = load_aux(db, q[i].pos);
-            uint32_t nb = ~q[i].t;
             const uint64_t wa = q[i].ws > q[i].a ? q[i].ws : q[i].a, wb = q[i].ws + KW < q[i].b ? q[i].ws + KW : q[i].b;
-            if (q[i].pos == wa && wa > q[i].a) nb = __ldg(db.keys + q[i].pos - 1);
-            else if (q[i].pos == wb - 1 && wb < q[i].b) nb = __ldg(db.keys + q[i].pos + 1);
-            if (nb == q[i].t) q[i].st = FW_SLOW;                   // the run of equal keys crosses the window
-            else if ((uint32_t)(ax & 0xFFu) == q[i].lo8) { uint32_t ix = (uint32_t)(ax >> 8); r[i] = ix < db.max_ix ? ix : HIT_MISS; }
+            uint32_t nbl = ~q[i].t, nbr = ~q[i].t;
+            if (q[i].pos == wa && wa > q[i].a) nbl = __ldg(db.keys + q[i].pos - 1);
+            if (q[i].pos + q[i].cnt == wb && wb < q[i].b) nbr = __ldg(db.keys + q[i].pos + q[i].cnt);
+            uint64_t ax[KW];
+#pragma unroll
+            for (uint32_t j = 0; j < KW; ++j) ax[j] = j < q[i].cnt ? load_aux(db, q[i].pos + j) : 0;
+            if (nbl == q[i].t || nbr == q[i].t) q[i].st = FW_SLOW; // the run of equal keys crosses the window
+            else {
+#pragma unroll
+                for (uint32_t j = 0; j < KW; ++j)
+                    if (j < q[i].cnt && (uint32_t)(ax[j] & 0xFFu) == q[i].lo8) { const uint32_t ix = (uint32_t)(ax[j] >> 8); r[i] = ix < db.max_ix ? ix : HIT_MISS; }
+            }
         }
         if (q[i].st == FW_SLOW) { r[i] = fast_slow(db, q[i].a, q[i].b, q[i].t, q[i].lo8); ns += 8; }
     }
@@ -613,19 +635,26 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
     for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_slots; tile += (uint64_t)gridDim.x * P_TILE) {
         if (tid < NPART) s_hist[tid] = 0;
         __syncthreads();
-        // pass A: partition id and rank inside the tile (the word is recomputed in pass B: cheaper than 16 live u64)
-        uint32_t meta[P_TILE / 256];                               // rank << 8 | part, or 0xFFFFFFFF
+        // pass A: partition id and rank inside the tile.  One thread per POSITION: a single window extraction
+        // feeds both strands (slots 2*pos and 2*pos+1).  The words are recomputed in pass B, which is cheaper
+        // than keeping 16 u64 live across the barrier.
+        constexpr uint32_t PPT = P_TILE / NSTR / 256;               // positions per thread
+        uint32_t meta[PPT * NSTR];                                  // rank << 8 | part, or 0xFFFFFFFF
+        const uint32_t tile_pos = (uint32_t)(tile / NSTR);
 #pragma unroll
-        for (uint32_t k = 0; k < P_TILE / 256; ++k) {
-            const uint64_t slot = tile + k * 256u + tid;
-            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+        for (uint32_t k = 0; k < PPT; ++k) {
+            const uint32_t pos = tile_pos + k * 256u + tid;
             uint64_t w;
-            meta[k] = 0xFFFFFFFFu;
-            if (slot < n_slots && window_at(pk, bad, pos, w)) {
-                if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
-                const uint32_t part = (uint32_t)(mix64(w) >> 58);
-                meta[k] = (atomicAdd(&s_hist[part], 1u) << 8) | part;
-                ++nv;
+#pragma unroll
+            for (int st = 0; st < NSTR; ++st) meta[k * NSTR + st] = 0xFFFFFFFFu;
+            if (pos < n_pos && window_at(pk, bad, pos, w)) {
+#pragma unroll
+                for (int st = 0; st < NSTR; ++st) {
+                    const uint64_t ws = st ? revcomp_word(w) : w;
+                    const uint32_t part = (uint32_t)(mix64(ws) >> 58);
+                    meta[k * NSTR + st] = (atomicAdd(&s_hist[part], 1u) << 8) | part;
+                }
+                nv += NSTR;
             }
         }
         __syncthreads();
@@ -638,15 +667,19 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
         __syncthreads();
         // pass B: scatter into shared memory in partition order
 #pragma unroll
-        for (uint32_t k = 0; k < P_TILE / 256; ++k) {
-            if (meta[k] == 0xFFFFFFFFu) continue;
-            const uint64_t slot = tile + k * 256u + tid;
-            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+        for (uint32_t k = 0; k < PPT; ++k) {
+            if (meta[k * NSTR] == 0xFFFFFFFFu) continue;           // both strands share validity
+            const uint32_t pos = tile_pos + k * 256u + tid;
             uint64_t w;
             window_at(pk, bad, pos, w);
-            if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
-            const uint32_t part = meta[k] & 0xFFu, dst = s_start[part] + (meta[k] >> 8);
-            s_words[dst] = w; s_slots[dst] = (uint32_t)slot; s_part[dst] = (uint8_t)part;
+#pragma unroll
+            for (int st = 0; st < NSTR; ++st) {
+                const uint32_t m = meta[k * NSTR + st];
+                const uint32_t part = m & 0xFFu, dst = s_start[part] + (m >> 8);
+                s_words[dst] = st ? revcomp_word(w) : w;
+                s_slots[dst] = pos * NSTR + st;
+                s_part[dst] = (uint8_t)part;
+            }
         }
         __syncthreads();
         // pass C: contiguous runs out to the regions
@@ -739,6 +772,7 @@ queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32
     const uint64_t n = *q_count < q_cap ? *q_count : q_cap;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t nh = 0, nsect = 0;
+    // one survivor per thread (two per thread in lock-step measured slower: the pair waits for its longer chain)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t slot = q_slots[i];
         if (slot == Q_INVALID) continue;                           // padding of a retired chunk
@@ -1446,7 +1480,7 @@ extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_interp
 struct utb_batch {
     utb_db *db;
     cudaStream_t st;
-    cudaEvent_t done, ev[6];
+    cudaEvent_t done, ev[7];
     size_t max_bytes, max_reads;
     uint64_t max_groups;
     // pinned host
@@ -1465,7 +1499,7 @@ struct utb_batch {
     uint32_t *d_hitmap;
     uint64_t *d_pwords; uint32_t *d_pslots; uint32_t *d_pfill; uint64_t p_total, part_min_slots;   // partitioned filter pass
     // last submit
-    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom;
+    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom; int used_partition;
     uint64_t launches;
 };
 
@@ -1494,7 +1528,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_pwords); cudaFree(b->d_pslots); cudaFree(b->d_pfill);
     if (b->done) cudaEventDestroy(b->done);
-    for (int i = 0; i < 6; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
+    for (int i = 0; i < 7; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
     free(b);
 }
@@ -1516,7 +1550,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
 #define BK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { utb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); utb_batch_destroy(b); return UTB_ERR_CUDA; } } while (0)
     BK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
     BK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
-    for (int i = 0; i < 6; ++i) BK(cudaEventCreate(&b->ev[i]));
+    for (int i = 0; i < 7; ++i) BK(cudaEventCreate(&b->ev[i]));
     BK(cudaMallocHost(&b->h_bytes, max_bytes + 64));
     BK(cudaMallocHost(&b->h_seq_off, max_reads * 8));
     BK(cudaMallocHost(&b->h_seq_len, max_reads * 4));
@@ -1601,6 +1635,7 @@ static int launch_stages(utb_batch *b, bool timed) {
         // pre-filter on while misses dominate (it only adds a fetch to lookups that hit)
         const bool bloom = b->db->bloom && (b->db->bloom_mode == 1 || (b->db->bloom_mode == 2 && b->db->ema_hit_rate < 0.40));
         b->used_bloom = bloom;
+        b->used_partition = 0;
         if (b->db->use_interp && bloom) {
             CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
             // hits are sparse (only filter survivors that really match): the survivor kernel flags them in a
@@ -1622,6 +1657,8 @@ static int launch_stages(utb_batch *b, bool timed) {
                     CK(cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
                     partition_kernel<1><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_pslots, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
                 }
+                if (timed) CK(cudaEventRecord(b->ev[6], b->st));
+                b->used_partition = 1;
                 // cooperative launch: the grid barrier between partitions needs every CTA resident
                 int per_sm = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel, 256, 0));
@@ -1827,6 +1864,16 @@ extern "C" uint64_t utb_batch_launches(const utb_batch *b) { return b ? b->launc
 // Two-phase detail of the LAST run (valid after wait): ms[0] filter kernel, ms[1] queue kernel (0/0 when the
 // single lookup kernel ran); sectors[0] = filter probes (one sector each), sectors[1] = sectors the exact
 // path touched for the survivors.
+// ms[0] partition_kernel, ms[1] probe_kernel of the LAST run; both 0 when the direct filter kernel ran.
+extern "C" int utb_batch_partition_detail(utb_batch *b, float ms[2]) {
+    if (!b || !ms) { utb_set_error("utb_batch_partition_detail: null argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    ms[0] = ms[1] = 0;
+    if (!b->used_bloom || !b->used_partition) return UTB_OK;
+    CK(cudaEventElapsedTime(&ms[0], b->ev[4], b->ev[6]));
+    CK(cudaEventElapsedTime(&ms[1], b->ev[6], b->ev[5]));
+    return UTB_OK;
+}
 extern "C" int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]) {
     if (!b || !ms || !sectors) { utb_set_error("utb_batch_lookup_detail: null argument"); return UTB_ERR_ARG; }
     CK(cudaSetDevice(b->db->device));

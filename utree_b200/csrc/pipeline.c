@@ -39,7 +39,8 @@ int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
 
 #define SLOTS_PER_DEVICE 3
-#define DEFAULT_BATCH_BYTES ((size_t)64 << 20)
+#define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* large enough for the device's partitioned lookup pass on the full-size batches */
+#define RAMP_BYTES ((size_t)64 << 20)              /* first / last batches: small, so the pipeline fills and drains fast */
 #define MAX_TEAM 64
 
 /* ---- thread team: leader + helpers, fork/join with barriers ----------------- */
@@ -752,6 +753,16 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         if (dev_err) break;
         const char *buf = utb_batch_bytes(sl->b);
         size_t cap = utb_batch_max_bytes(sl->b), fill = carry_len;
+        /* batch-size schedule: ramp up (64, 64, 128 MiB, then full) and, when the input size is known, down again */
+        if (cap > 2 * RAMP_BYTES) {
+            size_t want = seq < 2 ? RAMP_BYTES : seq == 2 ? 2 * RAMP_BYTES : cap;
+            size_t left = src->fd < 0 ? src->mem_len - src->mem_pos : src->seekable ? (size_t)(src->file_size - src->file_off) : (size_t)-1;
+            if (left != (size_t)-1 && left + carry_len <= 3 * RAMP_BYTES) want = RAMP_BYTES;
+            else if (left != (size_t)-1 && left + carry_len < want + 2 * RAMP_BYTES && want > 2 * RAMP_BYTES) want = left + carry_len - 2 * RAMP_BYTES;
+            if (want < carry_len + 4096) want = carry_len + 4096;  /* a carried partial record must be able to complete */
+            if (want < 2 * (size_t)UTB_LINELEN + 4096) want = 2 * (size_t)UTB_LINELEN + 4096;
+            if (want < cap) cap = want;
+        }
         if (zero_copy) {
             buf = src->mem + src->mem_pos;
             fill = src->mem_len - src->mem_pos < cap ? src->mem_len - src->mem_pos : cap;
