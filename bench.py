@@ -35,6 +35,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+from oracle import oracle_api  # noqa: E402  (CPU checker: used only by the cpu_baseline / reference legs)
 
 CONFIGS = {
     # name: universe (phyla, genera, species, strains, genome_len), complevel, ix_bytes, reads/GPU, read_len
@@ -68,7 +69,8 @@ def cfg_key(name, cfg):
 
 def ensure_ctr(name, cfg, device):
     """Synthesises the CTR once per box (cached so both arms see the same file)."""
-    from utree_b200 import build, synthgpu
+    from utree_b200 import build
+    from tools import synthgpu
     build.build_synth()
     path = os.path.join(work_dir(), f"{name}_{cfg_key(name, cfg)}.ctr")
     meta = path + ".json"
@@ -86,7 +88,7 @@ def ensure_ctr(name, cfg, device):
 
 
 def make_reads(cfg, first, n_reads, device, out=None):
-    from utree_b200 import synthgpu
+    from tools import synthgpu
     uni = synthgpu.Universe(SEED, *cfg["universe"])
     return uni.make_reads(n_reads, read_len=cfg["read_len"], read_seed=SEED + 1, first=first, device=device, out=out)
 
@@ -176,7 +178,7 @@ def oracle_sector_stats(ctr_path, reads_bytes, rec_bytes, n_sample, threads):
     from utree_b200 import capi
     fa = os.path.join(work_dir(), f"sect_{os.getpid()}.fa")
     reads_bytes[:n_sample * rec_bytes].tofile(fa)
-    orc = capi.OracleDb(ctr_path)
+    orc = oracle_api.OracleDb(ctr_path)
     t = time.time()
     rc, st, err = orc.search_file(fa, fa + ".out", do_rc=True, threads=threads)
     dt = time.time() - t
@@ -475,7 +477,7 @@ def reference_arm(args, cfg, rank, world, local, ncpu, rec_bytes, workload):
                 times.append((n_s, secs))
     else:
         from utree_b200 import capi
-        orc = capi.OracleDb(ctr_path)
+        orc = oracle_api.OracleDb(ctr_path)
         fa = os.path.join(work_dir(), f"refport_{os.getpid()}.fa")
         n_s = min(n_avail, 200_000)
         reads_np[:n_s * rec_bytes].tofile(fa)

@@ -10,7 +10,7 @@ sha256 of the reference-made .ctr so that synth.compress can be checked.
 import hashlib, json, os, subprocess, sys, tempfile
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from utree_b200 import synth
+from tools import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")

@@ -9,6 +9,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import conftest  # noqa: F401  (puts the repo root on sys.path)
+from oracle import oracle_api
 from conftest import GOLD, REFDIR, ROOT, gold
 
 
@@ -40,9 +42,9 @@ def test_library_exports_every_declared_symbol(built):
 
 def test_product_does_not_reference_oracle():
     """The oracle is test infrastructure: nothing under utree_b200/csrc or include/ may name it."""
-    for d in ("utree_b200/csrc", "include"):
+    for d in ("utree_b200/csrc", "include", "utree_b200"):
         for f in os.listdir(os.path.join(ROOT, d)):
-            if f.endswith((".c", ".cu", ".h")):
+            if f.endswith((".c", ".cu", ".h", ".py")):
                 txt = open(os.path.join(ROOT, d, f)).read()
                 assert "oracle" not in txt.lower(), f
     so = open(os.path.join(ROOT, "utree_b200", "csrc", "libutree_b200.so"), "rb").read()
@@ -52,8 +54,8 @@ def test_product_does_not_reference_oracle():
 @pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
 def test_ctr_loader_matches_oracle_loader(built, ctrs, name):
     from utree_b200 import capi
-    ctr, orc = capi.Ctr(ctrs[name]), capi.OracleDb(ctrs[name])
-    O = capi.oracle()
+    ctr, orc = capi.Ctr(ctrs[name]), oracle_api.OracleDb(ctrs[name])
+    O = oracle_api.oracle()
     try:
         assert ctr.num_nodes == O.orc_db_num_nodes(orc.h)
         assert ctr.ix_bytes == O.orc_db_ix_bytes(orc.h) and ctr.binix_bytes == O.orc_db_binix_bytes(orc.h)
@@ -68,12 +70,13 @@ def test_ctr_loader_matches_oracle_loader(built, ctrs, name):
 
 def test_ctr_loader_dedups_repeated_labels(built, tmp_path):
     """A label string seen twice keeps its first id (addSampleUdX, itree.c:219-220)."""
-    from utree_b200 import capi, synth
+    from utree_b200 import capi
+    from tools import synth
     words = np.array([5 << 40 | 7, 5 << 40 | 9, 6 << 40 | 1], dtype=np.uint64)
     tail = b"k__A;p__B\t1\nk__A;p__C\t1\nk__A;p__B\t1\nk__A;p__D\t0\n"
     p = str(tmp_path / "d.ctr")
     synth.ctr_write(p, words, np.array([0, 1, 2]), tail, 2)
-    ctr, orc = capi.Ctr(p), capi.OracleDb(p)
+    ctr, orc = capi.Ctr(p), oracle_api.OracleDb(p)
     try:
         assert ctr.max_ix == orc.max_ix == 3
         assert [ctr.label(i) for i in range(3)] == [b"k__A;p__B", b"k__A;p__C", b"k__A;p__D"]
@@ -198,7 +201,7 @@ def test_framer_partial_buffer_carries_the_tail(built):
 def test_formatter_matches_oracle_lines(built, ctrs):
     """utb_format_results on oracle votes == the golden output of the reference."""
     from utree_b200 import capi
-    ctr, orc = capi.Ctr(ctrs["toyA"]), capi.OracleDb(ctrs["toyA"])
+    ctr, orc = capi.Ctr(ctrs["toyA"]), oracle_api.OracleDb(ctrs["toyA"])
     try:
         data = open(gold("toyA_reads.fa"), "rb").read()
         rc, ex, used, recs, (name_off, name_len) = capi.frame_records(data, threads=3)

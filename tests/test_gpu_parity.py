@@ -6,6 +6,8 @@ import subprocess
 import numpy as np
 import pytest
 
+import conftest  # noqa: F401  (puts the repo root on sys.path)
+from oracle import oracle_api
 from conftest import BAD_CASES, CASES, ROOT, gold, read_fasta
 
 pytestmark = pytest.mark.gpu
@@ -18,7 +20,7 @@ def gpu(built, ctrs):
     state = {}
     for name, path in ctrs.items():
         ctr = capi.Ctr(path)
-        state[name] = (ctr, capi.Db(ctr, 0), capi.OracleDb(path))
+        state[name] = (ctr, capi.Db(ctr, 0), oracle_api.OracleDb(path))
     yield state
     for ctr, db, orc in state.values():
         db.free(); ctr.close(); orc.free()
@@ -31,7 +33,7 @@ def _rand_words_for(orc_path_words, rng, n_extra):
 @pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
 def test_lookup_words_match_oracle(gpu, name):
     """XT_getIX32 on members, near-members, same-prefix strangers and random words."""
-    from utree_b200 import synth
+    from tools import synth
     ctr, db, orc = gpu[name]
     words, ixs, _, _ = synth.ubt_read(gold(name + ".ubt"))
     rng = np.random.default_rng(5)
@@ -182,7 +184,8 @@ def test_synthetic_ctr_equals_reference_built_tree(built, tmp_path, complevel):
     same universe through utree-build_gg + utree-compress and through
     uts_build_ctr must classify identically (reference search on both trees),
     and the product must match the reference on the synthesised tree."""
-    from utree_b200 import build, capi, synthgpu
+    from utree_b200 import build, capi
+    from tools import synthgpu
     build.build_synth()
     ref = os.path.join(ROOT, "oracle", "_ref")
     uni = synthgpu.Universe(seed=99, n_phyla=2, n_genera=2, n_species=2, n_strains=3, genome_len=30000)
@@ -224,10 +227,11 @@ def _lookup_probe_words(words, rng):
 @pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
 def test_both_lookup_variants_match_oracle(built, ctrs, name):
     """Interpolation-start search (regular CTRs) and the exact-probe kernel give XT_getIX32's answer."""
-    from utree_b200 import capi, synth
+    from utree_b200 import capi
+    from tools import synth
     words, _, _, _ = synth.ubt_read(gold(name + ".ubt"))
     w = _lookup_probe_words(words, np.random.default_rng(17))
-    orc = capi.OracleDb(ctrs[name])
+    orc = oracle_api.OracleDb(ctrs[name])
     want = orc.lookup_many(w)
     orc.free()
     ctr = capi.Ctr(ctrs[name])
@@ -249,7 +253,8 @@ def test_both_lookup_variants_match_oracle(built, ctrs, name):
 def test_irregular_ctr_takes_the_exact_probe_path(built, tmp_path):
     """A CTR with an unsorted bucket (never produced by utree-compress): the loader detects it
     and the device emulates xtSuffixBS's probe sequence, matching the oracle hit for hit."""
-    from utree_b200 import capi, synth
+    from utree_b200 import capi
+    from tools import synth
     rng = np.random.default_rng(23)
     words, ixs, tail, _ = synth.ubt_read(gold("dense.ubt"))
     binix = synth.binix_like_reference(words)
@@ -260,7 +265,7 @@ def test_irregular_ctr_takes_the_exact_probe_path(built, tmp_path):
         shuffled[idx] = shuffled[rng.permutation(idx)]
     path = str(tmp_path / "irregular.ctr")
     synth.ctr_write(path, shuffled, ixs, tail, 2, binix=binix)
-    ctr, orc = capi.Ctr(path), capi.OracleDb(path)
+    ctr, orc = capi.Ctr(path), oracle_api.OracleDb(path)
     db = capi.Db(ctr, 0)
     try:
         assert db.lookup_mode() == 0

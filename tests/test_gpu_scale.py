@@ -65,7 +65,7 @@ def test_l2_scale_and_l4_match_reference(bench_mod, tmp_path, config, n_reads):
 @need_ref
 def test_uint32_labels_over_64k_match_reference(bench_mod, tmp_path):
     """IXTYPE=uint32_t (SZ=9), complevel 0, 73,260 labels, 250 bp reads."""
-    from utree_b200 import synthgpu
+    from tools import synthgpu
     uni = synthgpu.Universe(77, 60, 11, 10, 10, 6000)                 # 66,000 genomes
     ctr_path = os.path.join(bench_mod.work_dir(), "u32_test.ctr")
     n, nl = uni.build_ctr(ctr_path, complevel=0, ix_bytes=4)
@@ -85,7 +85,7 @@ def test_uint32_labels_over_64k_match_reference(bench_mod, tmp_path):
 @need_ref
 def test_long_and_whole_genome_queries_match_reference(bench_mod, tmp_path):
     """10 kb - 1 Mb reads, whole genomes, and one query at the 16,777,214-base limit vs the L2-scale CTR."""
-    from utree_b200 import synthgpu
+    from tools import synthgpu
     cfg = dict(bench_mod.CONFIGS["l2s"])
     ctr_path, _ = bench_mod.ensure_ctr("l2s", cfg, 0)
     uni = synthgpu.Universe(bench_mod.SEED, *cfg["universe"])

@@ -28,12 +28,13 @@ WORKER = textwrap.dedent("""
     import numpy as np
     import torch.distributed as dist
     from utree_b200 import capi, shard
+    from oracle import oracle_api
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
     rank, world = dist.get_rank(), dist.get_world_size()
     data = open({fasta!r}, "rb").read()
     lo, hi = shard.split_fasta(data, rank, world)
     mine = data[lo:hi]
-    ctr, orc = capi.Ctr({ctr!r}), capi.OracleDb({ctr!r})
+    ctr, orc = capi.Ctr({ctr!r}), oracle_api.OracleDb({ctr!r})
     rc, ex, used, recs, (name_off, name_len) = capi.frame_records(mine, threads=2)
     assert rc == 0 and used == len(mine)
     res = np.zeros(len(recs), dtype=capi.RESULT_DTYPE)

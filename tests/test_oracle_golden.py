@@ -5,13 +5,15 @@ import os
 import numpy as np
 import pytest
 
+import conftest  # noqa: F401  (puts the repo root on sys.path)
+from oracle import oracle_api
 from conftest import BAD_CASES, CASES, gold, read_fasta
 
 
 @pytest.fixture(scope="module")
 def orcs(built, ctrs):
     from utree_b200 import capi
-    d = {k: capi.OracleDb(v) for k, v in ctrs.items()}
+    d = {k: oracle_api.OracleDb(v) for k, v in ctrs.items()}
     yield d
     for o in d.values():
         o.free()
@@ -43,20 +45,21 @@ def test_good_finds_match_reference_stdout(orcs, tmp_path, meta):
 
 def test_revcomp_word_is_rc_of_text(built):
     """rc(kmer) equals the k-mer of the reverse-complemented text."""
-    from utree_b200 import capi, synth
+    from utree_b200 import capi
+    from tools import synth
     rng = np.random.default_rng(3)
     codes = rng.integers(0, 4, 200, dtype=np.uint8)
     w = synth.kmer_words(codes)
     rc_text = (3 - codes)[::-1]
     w_rc = synth.kmer_words(rc_text)[::-1]
-    O = capi.oracle()
+    O = oracle_api.oracle()
     assert [O.orc_revcomp_word(int(x)) for x in w] == [int(x) for x in w_rc]
     assert np.array_equal(synth.revcomp_words(w), w_rc)
 
 
 def test_slide_skips_ambiguous_windows(orcs):
     """Every all-ACGT window exactly once, none containing another byte (App. B.2)."""
-    from utree_b200 import synth
+    from tools import synth
     orc = orcs["toyA"]
     seq = read_fasta(gold("edge_reads.fa"))[7][1]          # manyN
     assert b"N" in seq and b"n" in seq
@@ -71,7 +74,7 @@ def test_slide_skips_ambiguous_windows(orcs):
 
 def test_lookup_on_dense_buckets(orcs):
     """xtSuffixBS on buckets of size 1..513: members hit with their id, neighbours miss."""
-    from utree_b200 import synth
+    from tools import synth
     words, ixs, _, _ = synth.ubt_read(gold("dense.ubt"))
     orc = orcs["dense"]
     got = orc.lookup_many(words)
@@ -86,7 +89,7 @@ def test_lookup_on_dense_buckets(orcs):
 def test_quirk_bucket_semantics(orcs):
     """the lone record of the first bin is lost; the folded bucket
     is searched with the reference's probe sequence."""
-    from utree_b200 import synth
+    from tools import synth
     words, ixs, _, _ = synth.ubt_read(gold("quirk.ubt"))
     orc = orcs["quirk"]
     got = orc.lookup_many(words)

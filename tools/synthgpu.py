@@ -1,4 +1,4 @@
-"""ctypes wrapper of libutb_synth.so (utree_b200/csrc/synth.cu): GPU-side
+"""ctypes wrapper of libutb_synth.so (tools/synth.cu): GPU-side
 generator of bench / large-test INPUTS (a CTR file and FASTA reads of a seeded
 synthetic universe).  Not on the search path."""
 from __future__ import annotations
@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libutb_synth.so")
+LIB_PATH = os.path.join(HERE, "libutb_synth.so")
 _lib = None
 
 

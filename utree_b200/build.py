@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libutree_b200.so")
-SYNTH_LIB = os.path.join(CSRC, "libutb_synth.so")   # bench/test input generator, not the product
+SYNTH_LIB = os.path.join(ROOT, "tools", "libutb_synth.so")   # bench/test input generator, not the product
 BIN = os.path.join(ROOT, "bin")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 GCC = "gcc"   # PATH gcc: $CC in this image points at a gcc without libgomp specs
@@ -71,7 +71,7 @@ def build(force=False, verbose=False):
 
 def build_synth(force=False):
     """libutb_synth.so: synthetic CTR / reads generator (CUB sort).  Inputs only."""
-    src = os.path.join(CSRC, "synth.cu")
+    src = os.path.join(ROOT, "tools", "synth.cu")
     if not force and _newer(SYNTH_LIB, [src]):
         return SYNTH_LIB
     _run([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -79,12 +79,6 @@ def build_synth(force=False):
     return SYNTH_LIB
 
 
-def build_oracle():
-    """Builds the CPU checker (and oracle/_ref when /root/reference exists)."""
-    _run(["make", "-C", os.path.join(ROOT, "oracle"), "all"])
-
-
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose=True)
     build_synth(force="--force" in sys.argv)
-    build_oracle()
