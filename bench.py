@@ -421,6 +421,13 @@ def main():
                 cpu = {"value": round(rate, 1), "unit": "reads/s", "cores": ncpu, "kind": "reference",
                        "sample": f"first {n_s} of the same reads, reference binary threads={ncpu}, wall minus 1-read run, {secs:.1f} s",
                        "lookups_per_s": round(rate * sect["lookups_per_read"], 1)}
+                try:                                                  # and single-threaded (the parity configuration)
+                    r1, n1, s1, _ = cpu_reference_rate(cfg, ctr_path, reads_np, rec_bytes, min(n_reads, 400_000), 4.0, 1)
+                    cpu["value_1thread"] = round(r1, 1)
+                    cpu["sample_1thread"] = f"first {n1} reads, threads=1, {s1:.1f} s"
+                except Exception as e:                                # never fail the bench line over the extra figure
+                    cpu["value_1thread"] = None
+                    log(f"1-thread reference run failed: {e}")
             else:
                 cpu = {"value": round(sect["port_reads_per_s"], 1), "unit": "reads/s", "cores": ncpu, "kind": "port",
                        "sample": f"first {n_sect} of the same reads, oracle port with {ncpu} OpenMP threads (with sector accounting)",
