@@ -201,6 +201,13 @@ void utb_free(void *p);
  * stdout banner, exit codes.  Returns the process exit code. */
 int utb_main(int argc, char **argv);
 
+/* ---- utree-compress equivalent (XT_cmp32, itree.c:1234-1315) -- */
+/* .ubt -> .ctr, byte-identical to the reference compressor (first-bin quirk
+ * included).  Host only. */
+int utb_compress_ubt(const char *ubt_path, const char *ctr_path, uint64_t *n_records, uint32_t *n_labels);
+/* The COMPRESS binary's CLI contract (itree.c:1352-1355). */
+int utb_compress_main(int argc, char **argv);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Random 32-byte-sector gather bandwidth over a working set of ws_bytes on
  * `device` (the roofline denominator of SURVEY 8d).  loads: sectors read. */

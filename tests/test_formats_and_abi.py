@@ -214,3 +214,38 @@ def test_formatter_matches_oracle_lines(built, ctrs):
         assert text == open(gold("toyA_rc.out"), "rb").read()
     finally:
         ctr.close(); orc.free()
+
+
+# ---- utree-compress equivalent ----------------------------------------
+@pytest.mark.parametrize("name", ["toyA", "toyB_u32", "quirk", "dense"])
+def test_compress_equals_reference_compressor(built, tmp_path, meta, name):
+    """utb_compress_ubt == utree-compress, byte for byte (sha256 recorded from the reference binary),
+    including the first-bin quirk (`quirk`, `dense`)."""
+    from utree_b200 import capi
+    out = str(tmp_path / "c.ctr")
+    n, nl = capi.compress_ubt(gold(name + ".ubt"), out)
+    assert _sha(out) == meta[name]["ctr_sha256"]
+    ctr = capi.Ctr(out)
+    try:
+        assert (ctr.num_nodes, ctr.max_ix) == (n, nl)
+    finally:
+        ctr.close()
+
+
+def test_compress_cli_contract(built, tmp_path, meta):
+    exe = os.path.join(ROOT, "bin", "utree-compress")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 1 and "usage: xtree-compress" in p.stdout                      # itree.c:1353
+    out = str(tmp_path / "q.ctr")
+    p = subprocess.run([exe, gold("quirk.ubt"), out], capture_output=True, text=True)
+    assert p.returncode == 0 and _sha(out) == meta["quirk"]["ctr_sha256"]
+    lines = p.stdout.splitlines()
+    assert lines[0].startswith("Nodes in input tree: 50 (PACKSIZE=32, CNTTYPE=NA, IXTYPE=uint16_t, el=10)")
+    assert lines[1] == "Using 32-bit counters" and lines[-1].startswith("Total nodes in tree: 50 [")
+    ref = os.path.join(REFDIR, "utree-compress")
+    if os.path.exists(ref):                                                                # live: same stdout, same bytes
+        out2 = str(tmp_path / "r.ctr")
+        q = subprocess.run([ref, gold("quirk.ubt"), out2], capture_output=True, text=True)
+        assert q.stdout == p.stdout and _sha(out2) == _sha(out)
+    p = subprocess.run([exe, str(tmp_path / "missing.ubt"), out], capture_output=True, text=True)
+    assert p.returncode == 0 and "Invalid input filename" in p.stdout                      # itree.c:1236: exit(0)

@@ -20,7 +20,7 @@ GCC = "gcc"   # PATH gcc: $CC in this image points at a gcc without libgomp spec
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 C_FLAGS = ["-std=gnu11", "-O2", "-g", "-Wall", "-Wextra", "-Wno-unused-parameter", "-fPIC", "-pthread"]
-C_SOURCES = ["ctr_loader.c", "pipeline.c"]
+C_SOURCES = ["ctr_loader.c", "pipeline.c", "compress.c"]
 
 
 def _run(cmd, log=None):
@@ -41,7 +41,7 @@ def _newer(target, sources):
 
 
 def build(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in C_SOURCES + ["kernels.cu", "utb_internal.h", "main.c"]]
+    srcs = [os.path.join(CSRC, f) for f in C_SOURCES + ["kernels.cu", "utb_internal.h", "main.c", "compress_main.c"]]
     srcs.append(os.path.join(ROOT, "include", "utree_b200.h"))
     exe = os.path.join(BIN, "utree-search_gg")
     if not force and _newer(LIB, srcs) and _newer(exe, srcs):
@@ -62,6 +62,8 @@ def build(force=False, verbose=False):
                             "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
     shutil.copyfile(exe, os.path.join(BIN, "utree-searchGG"))
     os.chmod(os.path.join(BIN, "utree-searchGG"), 0o755)
+    _run([GCC] + C_FLAGS + [os.path.join(CSRC, "compress_main.c"), "-o", os.path.join(BIN, "utree-compress"), "-L" + CSRC,
+                            "-lutree_b200", "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
     with open(os.path.join(CSRC, "build.log"), "w") as f:
         f.write("".join(log))
     if verbose:

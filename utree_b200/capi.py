@@ -50,7 +50,7 @@ EXPORTS = [
     "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail", "utb_batch_partition_detail",
     "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_frame_records", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
-    "utb_main", "utb_measure_rand32",
+    "utb_main", "utb_measure_rand32", "utb_compress_ubt", "utb_compress_main",
 ]
 
 _lib = None
@@ -164,6 +164,14 @@ def format_results(ctr, buf: bytes, name_off, name_len, results):
     _ck(lib().utb_format_results(ctr.h, buf, name_off.ctypes.data, name_len.ctypes.data, results.ctypes.data,
                                  results.size, out, cap, C.byref(n)))
     return out.raw[:n.value]
+
+
+def compress_ubt(ubt_path, ctr_path):
+    """utree-compress equivalent (utb_compress_ubt).  Returns (n_records, n_labels)."""
+    n, nl = C.c_uint64(), C.c_uint32()
+    lib().utb_compress_ubt.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
+    _ck(lib().utb_compress_ubt(os.fsencode(ubt_path), os.fsencode(ctr_path), C.byref(n), C.byref(nl)))
+    return n.value, nl.value
 
 
 def device_count():
