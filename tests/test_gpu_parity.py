@@ -360,3 +360,36 @@ def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, read
         assert code == 0 and text == open(gold(out), "rb").read()
     finally:
         s.destroy(); ctr.close()
+
+
+def test_empty_and_hitless_inputs(gpu, tmp_path):
+    """Empty FASTA, reads shorter than k, reads of only N: no output line, exit 0 (itree.c:1028)."""
+    from utree_b200 import capi
+    s = capi.Searcher(gpu["toyA"][0], devices=(0,), host_threads=2)
+    try:
+        for name, data, n_reads in (("empty", b"", 0), ("short", b">a\nACGT\n>b\n" + b"A" * 31 + b"\n", 2),
+                                    ("allN", b">n1\n" + b"N" * 200 + b"\n>n2\n\n", 2)):
+            p = str(tmp_path / (name + ".fa"))
+            open(p, "wb").write(data)
+            o = str(tmp_path / (name + ".out"))
+            rc, ex, st = s.search_file(p, o, do_rc=True)
+            assert (rc, ex) == (0, 0) and open(o, "rb").read() == b"" and st["reads"] == n_reads and st["good_finds"] == 0
+            rc, ex, text, st = s.search_mem(data, do_rc=True)
+            assert (rc, ex, text) == (0, 0, b"")
+    finally:
+        s.destroy()
+
+
+def test_cli_reads_fasta_from_a_pipe(ctrs, tmp_path):
+    """Non-seekable input (serial read path) gives the same bytes."""
+    exe = os.path.join(ROOT, "bin", "utree-search_gg")
+    o = str(tmp_path / "pipe.out")
+    with open(gold("toyA_reads.fa"), "rb") as f:
+        p = subprocess.run([exe, ctrs["toyA"], "/dev/stdin", o, "4", "RC"], stdin=f, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stderr
+    assert open(o, "rb").read() == open(gold("toyA_rc.out"), "rb").read()
+    # through a real pipe as well
+    q = subprocess.run(f"cat {gold('toyB_reads.fa')} | {exe} {ctrs['toyB_u32']} /dev/stdin {o} 3 RC", shell=True,
+                       capture_output=True, text=True, timeout=600)
+    assert q.returncode == 0, q.stderr
+    assert open(o, "rb").read() == open(gold("toyB_u32_rc.out"), "rb").read()
