@@ -45,6 +45,9 @@ CONFIGS = {
                 desc="L2-scale synthetic CTR (5000 genomes x 4 Mb, complevel 2) vs 10M x 150bp reads, RC"),
     "l4": dict(universe=(50, 20, 5, 1, 4_000_000), complevel=4, ix_bytes=2, reads=10_000_000, read_len=150,
                desc="L4 synthetic CTR (5000 genomes x 4 Mb, complevel 4) vs 10M x 150bp reads, RC"),
+    # IXTYPE=uint32_t (SZ=9), > 65,536 labels, complevel 0 (dense sampling), 250 bp reads (BASELINE.json configs[4])
+    "u32": dict(universe=(60, 11, 10, 10, 6000), complevel=0, ix_bytes=4, reads=10_000_000, read_len=250,
+                desc="uint32-label synthetic CTR (66000 genomes x 6 kb, 73500 labels, complevel 0) vs 10M x 250bp reads, RC"),
     "small": dict(universe=(4, 3, 3, 3, 400_000), complevel=2, ix_bytes=2, reads=400_000, read_len=150,
                   desc="small synthetic CTR (108 genomes x 0.4 Mb, complevel 2) vs 400k x 150bp reads, RC"),
 }

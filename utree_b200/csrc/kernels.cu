@@ -1593,6 +1593,8 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         // reuse its filter lines (and to amortise 64 grid barriers); UTB_PARTITION=1 forces it, =0 disables it.
         const char *pe = getenv("UTB_PARTITION");
         b->part_min_slots = pe ? (atoi(pe) ? 0 : ~0ull) : PART_MIN_SLOTS;
+        const char *pm = getenv("UTB_PARTITION_MIN_MSLOTS");      // threshold in Mi lookup slots (tuning)
+        if (pm && atoi(pm) > 0) b->part_min_slots = (uint64_t)atoi(pm) << 20;
         if (npos * 2 >= b->part_min_slots) {                        // one region per (CTA, partition), 25 % head-room
             b->p_total = (uint64_t)((double)(npos * 2) * 1.25) + (uint64_t)P_CTAS * NPART * 64;
             BK(cudaMalloc(&b->d_pwords, b->p_total * 8));

@@ -267,6 +267,8 @@ typedef struct {
     int error;              /* sticky UTB_ERR_* from the device side */
     char errmsg[512];
     utb_stats st;
+    /* UTB_TIMELINE=1: per-batch host timestamps (s since start) for the first 64 batches */
+    double t0, tl_submit[64], tl_framed[64], tl_gpu_done[64], tl_emitted[64]; size_t tl_reads[64];
 } run_t;
 
 /* ---- formatter ----------------------------------------------------------------------------- */
@@ -374,6 +376,7 @@ static void *formatter_main(void *arg) {
         double tw = now_s();
         int rc = s->device_format ? utb_batch_wait_text(sl->b, &text, &text_len, &good) : utb_batch_wait(sl->b, &res);
         R->st.fm_wait_gpu += now_s() - tw;
+        if (seq < 64) R->tl_gpu_done[seq] = now_s() - R->t0;
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
         if (!rc && s->device_format) {
             double tf = now_s();
@@ -416,6 +419,7 @@ static void *formatter_main(void *arg) {
                     printf("Searched %llu queries...\n", (unsigned long long)(m << 20));
             }
         }
+        if (seq < 64) R->tl_emitted[seq] = now_s() - R->t0;
         pthread_mutex_lock(&R->mu);
         sl->state = 0;
         pthread_cond_broadcast(&R->cv);
@@ -718,6 +722,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     pthread_cond_init(&R.cv, NULL);
     if (ref_exit) *ref_exit = 0;
     double t0 = now_s();
+    R.t0 = t0;
     uint64_t launches0 = 0;
     for (int i = 0; i < s->n_slots; ++i) { s->slots[i].state = 0; launches0 += utb_batch_launches(s->slots[i].b); }
     /* split the host threads between the two teams */
@@ -822,12 +827,14 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         if (zero_copy) { src->mem_pos += fmt_err ? fill : used; if (src->mem_pos < src->mem_len) src->eof = 0; }
         else if (!fmt_err && used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
         rd_t[2] += now_s() - tp; tp = now_s();
+        if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = n; }
         if (n) {
             /* every sequence lies inside the first n_bytes of the buffer */
             int r2 = utb_batch_submit_ex(sl->b, zero_copy ? buf : NULL, fmt_err ? fill : used, n, do_rc, s->device_format,
                                          groups_known && !cut ? groups : 0);
             if (r2) { rc = r2; break; }
             R.st.h2d_bytes += (fmt_err ? fill : used) + n * (s->device_format ? 24 : 16) + 4;
+            if (seq < 64) R.tl_submit[seq] = now_s() - t0;
             pthread_mutex_lock(&R.mu);
             sl->state = 1;
             R.submitted = ++seq;
@@ -856,6 +863,13 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     for (int i = 0; i < s->n_slots; ++i) R.st.kernel_launches += utb_batch_launches(s->slots[i].b);
     R.st.kernel_launches -= launches0;
     R.st.seconds_total = now_s() - t0;
+    if (getenv("UTB_TIMELINE")) {
+        fprintf(stderr, "utree-b200 timeline (ms): batch reads framed submitted gpu_done emitted\n");
+        for (uint64_t i = 0; i < seq && i < 64; ++i)
+            fprintf(stderr, "  %2llu %8zu %8.2f %8.2f %8.2f %8.2f\n", (unsigned long long)i, R.tl_reads[i], 1e3 * R.tl_framed[i],
+                    1e3 * R.tl_submit[i], 1e3 * R.tl_gpu_done[i], 1e3 * R.tl_emitted[i]);
+        fprintf(stderr, "  total %.2f ms\n", 1e3 * R.st.seconds_total);
+    }
     R.st.rd_wait_slot = rd_t[0]; R.st.rd_fill = rd_t[1]; R.st.rd_frame = rd_t[2]; R.st.rd_submit = rd_t[3];
     if (stats) *stats = R.st;
     if (!rc && fmt_err) {
