@@ -352,70 +352,77 @@ def main():
         ref_equiv = ref_bytes / (lookup_ms * 1e-3) / 1e9
         partitioned = part_ms[1] > 0
         filter_bytes = 16.0 * (ctr.num_nodes // 8 + 1024)          # the Bloom filter, read once per partition sweep
+        n_pos = 32.0 * ((cfg["read_len"] + 1 + 31) // 32) * n_reads  # positions of the packed stream (padded reads)
+        probes = det_sect[0] / 2.0                                  # ONE filter fetch per position serves both strands
+        surv_ms = det_ms[1] / args.steps
+        vote_ms = ms_sum[2] / args.steps
+        # candidates: (kernel, ms per launch, algorithmic bytes per launch, peak it is held against)
+        cand = []
         if two_phase and partitioned:
-            # phase A = partition_kernel (stream: 12 B per lookup out) + probe_kernel (12 B per lookup in, the filter
-            # once, every probe an L2 hit on the partition's resident slice); the longer of the two is the dominant kernel
             pm, qm = part_ms[0] / args.steps, part_ms[1] / args.steps
-            if qm >= pm:
-                k_name, k_ms = "probe_kernel (partitioned Bloom probes, cooperative sweep of 64 L2-resident filter slices)", qm
-                k_bytes = 12.0 * det_sect[0] + filter_bytes
-            else:
-                k_name, k_ms = "partition_kernel<2> (shared-memory counting sort of lookups into 64 filter-slice partitions)", pm
-                k_bytes = 12.0 * det_sect[0] + 0.375 * 160 * n_reads
-            stage_bytes = 24.0 * det_sect[0] + filter_bytes + 32.0 * det_sect[1]
+            cand.append(("partition_kernel<2> (shared-memory counting sort of positions into 64 filter-slice partitions)", pm,
+                         12.0 * probes + 0.375 * n_pos, "stream",
+                         "packed bases in (0.375 B/position) + one 12 B (word, position) record per valid position out"))
+            cand.append(("probe_kernel<2> (Bloom probes, cooperative sweep of 64 L2-resident filter slices)", qm,
+                         8.0 * probes + filter_bytes + 16.0 * hits, "stream",
+                         "8 B word per valid position + the 2.2 GB filter once + survivors (4 B position in, 12 B queue entry out); "
+                         "the probes themselves are L2 hits"))
+            stage_bytes = 20.0 * probes + 0.375 * n_pos + filter_bytes + 32.0 * det_sect[1]
         elif two_phase:
-            # dominant kernel = filter_kernel: one 32-byte sector per lookup, nothing else to read
-            k_name, k_ms = "filter_kernel<2> (Bloom pre-filter, phase A of the two-phase lookup)", det_ms[0] / args.steps
-            k_bytes = 32.0 * det_sect[0]
-            stage_bytes = 32.0 * (det_sect[0] + det_sect[1])
+            cand.append(("filter_kernel<2> (Bloom pre-filter, one fetch per position for both strands)", det_ms[0] / args.steps,
+                         32.0 * probes, "rand32", "32 B x one filter sector per valid position"))
+            stage_bytes = 32.0 * (probes + det_sect[1])
         elif lookup_mode:
-            k_name, k_ms = "lookup_kernel<2,true,false> (key-window search)", lookup_ms
-            k_bytes = stage_bytes = None          # not instrumented in the fused kernel
+            cand.append(("lookup_kernel<2,true,false> (key-window search)", lookup_ms, ref_bytes, "rand32", "SURVEY 8d reference-layout bytes"))
+            stage_bytes = ref_bytes
         else:
-            k_name, k_ms = "lookup_kernel<2,false,false> (reference probe sequence)", lookup_ms
-            k_bytes = stage_bytes = ref_bytes
-        if k_bytes is None:
-            k_bytes = stage_bytes = ref_bytes
+            cand.append(("lookup_kernel<2,false,false> (reference probe sequence)", lookup_ms, ref_bytes, "rand32", "SURVEY 8d reference-layout bytes"))
+            stage_bytes = ref_bytes
+        if two_phase:
+            cand.append(("queue_lookup_kernel (exact key-window search of the filter survivors)", surv_ms, 32.0 * det_sect[1], "rand32",
+                         "32 B x the sectors the exact path touches (index pair, key windows, aux), counted on the device"))
+        cand.append(("vote_warp_kernel (+ vote_block_kernel; per-read label multiset and aufbau walk)", vote_ms,
+                     det_sect[0] / 8.0 + 4.0 * hits + 32.0 * n_reads, "stream",
+                     "1 bit per lookup slot of the hit map + 4 B per hit + one 32 B result per read"))
+        k_name, k_ms, k_bytes, k_peak, k_alg = max(cand, key=lambda c: c[1])
         achieved = k_bytes / (k_ms * 1e-3) / 1e9
-        stream_bound = two_phase and partitioned                     # streaming kernels are held against the copy peak
+        stream_bound = k_peak == "stream"
         # ncu dram__bytes_read+write per launch of the same kernel/workload shape, when a capture is committed
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            key = ("probe_kernel_dram_bytes_per_lookup" if "probe_kernel" in k_name else "partition_kernel_dram_bytes_per_lookup") if stream_bound \
-                else ("filter_kernel_dram_bytes_per_lookup" if two_phase else "lookup_kernel_dram_bytes_per_lookup")
-            per_lookup = tr.get(args.config, {}).get(key)
+            per_lookup = tr.get(args.config, {}).get(k_name.split("<")[0].split(" ")[0] + "_dram_bytes_per_lookup")
             traffic = round(per_lookup * lookups) if per_lookup else None
         except Exception:
             pass
         peak = stream_peak if stream_bound else rand32
         roofline = {"bound": "hbm", "kernel": k_name, "achieved": round(achieved, 1), "peak": round(peak, 1),
                     "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                    "algorithmic_bytes": ("12 B per lookup record + the 2.2 GB filter once (streamed); the probes themselves are L2 hits"
-                                          if stream_bound else
-                                          "32 B x the sectors the kernel must touch (one per filter probe), counted on the device"),
+                    "algorithmic_bytes": k_alg,
                     "peak_kind": ("MEASURED_PEAKS.json hbm_gbs (streaming copy)" if stream_bound else
                                   "measured random 32B-sector gather, 8 GiB working set (utb_measure_rand32); the L2 fills whole "
                                   "128 B lines, so this equals ~6 TB/s of DRAM reads (profiles/r01_membench_ncu.txt)"),
                     "rand32_peak": round(rand32, 1),
-                    "l2_probes_per_s": round(det_sect[0] / (part_ms[1] / args.steps * 1e-3), 1) if stream_bound else None,
+                    "kernels": [{"kernel": c[0].split(" ")[0], "ms": round(float(c[1]), 3), "alg_gbs": round(c[2] / (c[1] * 1e-3) / 1e9, 1) if c[1] > 0 else None,
+                                 "frac": round(c[2] / (c[1] * 1e-3) / 1e9 / (stream_peak if c[3] == "stream" else rand32), 4) if c[1] > 0 else None,
+                                 "peak": c[3]} for c in cand],
+                    "filter_probes_per_s": round(probes / (part_ms[1] / args.steps * 1e-3), 1) if partitioned else
+                                           (round(probes / (det_ms[0] / args.steps * 1e-3), 1) if two_phase else None),
                     "phase_a_ms": {"partition_kernel": round(float(part_ms[0] / args.steps), 3), "probe_kernel": round(float(part_ms[1] / args.steps), 3)}
-                                  if stream_bound else {"filter_kernel": round(float(det_ms[0] / args.steps), 3)},
+                                  if partitioned else {"filter_kernel": round(float(det_ms[0] / args.steps), 3)},
                     "stream_peak": stream_peak, "stream_peak_kind": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
-                    "dram_line_fill_frac_of_stream": round(achieved * 4 / stream_peak, 4),
                     "kernel_ms": round(float(k_ms), 3), "kernel_share_of_step": round(float(k_ms * args.steps / ms_sum[3]), 4),
                     "lookups_per_launch": lookups,
                     "lookup_stage": {"ms": round(float(lookup_ms), 3), "bytes": stage_bytes,
                                      "gbs": round(stage_bytes / (lookup_ms * 1e-3) / 1e9, 1),
-                                     "frac": round(stage_bytes / (lookup_ms * 1e-3) / 1e9 / peak, 4),
-                                     "survivor_kernel_ms": round(float(det_ms[1] / args.steps), 3),
-                                     "sectors_per_lookup": round((det_sect[0] + det_sect[1]) / max(lookups, 1), 3) if two_phase else None},
+                                     "survivor_kernel_ms": round(float(surv_ms), 3),
+                                     "sectors_per_lookup": round((probes + det_sect[1]) / max(lookups, 1), 3) if two_phase else None},
                     "reference_layout_equiv": {"bytes_per_lookup": round(sect["bytes_per_lookup"], 2), "gbs": round(ref_equiv, 1),
                                                "ratio_to_peak": round(ref_equiv / rand32, 3),
                                                "note": "SURVEY 8d figure: what the reference's bisection would touch per lookup; "
                                                        "above 1 because the path no longer performs those probes"},
                     "stage_ms": {"pack": round(float(ms_sum[0] / args.steps), 3), "lookup": round(float(lookup_ms), 3),
-                                 "vote": round(float(ms_sum[2] / args.steps), 3)}}
+                                 "vote": round(float(vote_ms), 3)}}
         cpu = None
         if world == 1 and not args.no_cpu:
             exe = ref_binary(cfg)

@@ -124,8 +124,9 @@ int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint64_t *launc
 /* Counters of the last submit: valid 32-mer windows x strands (= lookups). */
 int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits);
 /* Two-phase lookup detail of the last run: ms[0] filter kernel, ms[1] survivor
- * kernel; sectors[0] filter probes (one 32-byte sector each), sectors[1] sectors
- * the exact search touched for the survivors.  All zero when the single lookup
+ * kernel; sectors[0] lookups the filter answered (one 32-byte filter sector is
+ * fetched per POSITION and serves both strands), sectors[1] sectors the exact
+ * search touched for the survivors.  All zero when the single lookup
  * kernel ran (pre-filter off). */
 int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]);
 /* Large batches split phase A into partition_kernel + probe_kernel (ms[0], ms[1]);

@@ -424,21 +424,33 @@ verify_kernel(DevDB db, unsigned long long *__restrict__ out) {
 // at upload, answers "certainly absent" with ONE 16-byte load: block =
 // 4 x u32, two bits per word, all eight tests on registers.  No false negatives,
 // so a filtered miss is a miss of XT_getIX32 too; positives take the exact path.
+//
+// The BLOCK of a word x is chosen by its strand-neutral form c = min(x, revcomp(x)),
+// the eight BITS by x itself.  A read position looks up x and revcomp(x)
+// (itree.c:887-898 appends the reverse complement, so both strands of every
+// window are searched): both share c, hence both tests are served by the same
+// 16-byte load -- one scattered fetch per POSITION instead of one per lookup.
+// Each record still sets eight bits of one block, so the false-positive rate is
+// that of the plain blocked filter (~0.1 % at 16 bits per record).
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
     x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
     return x ^ (x >> 33);
 }
-__device__ __forceinline__ uint4 bloom_masks(uint64_t h) {
-    const uint64_t g = h * 0x9E3779B97F4A7C15ull;                  // 8 x 5 bits: two bits in each of the 4 words
+// hc = mix64(min(x, revcomp(x))); the mask hash folds the word back in, so x and revcomp(x) get unrelated bits
+__device__ __forceinline__ uint4 bloom_masks(uint64_t hc, uint64_t x) {
+    const uint64_t g = ((hc ^ x) * 0x9E3779B97F4A7C15ull) >> 24;   // 8 x 5 bits: two bits in each of the 4 words
     return make_uint4((1u << (g & 31)) | (1u << ((g >> 5) & 31)), (1u << ((g >> 10) & 31)) | (1u << ((g >> 15) & 31)),
                       (1u << ((g >> 20) & 31)) | (1u << ((g >> 25) & 31)), (1u << ((g >> 30) & 31)) | (1u << ((g >> 35) & 31)));
 }
-__device__ __forceinline__ bool bloom_maybe(const DevDB &db, uint64_t word) {
-    const uint64_t h = mix64(word);
-    const uint4 v = __ldg(db.bloom + __umul64hi(h, db.bloom_blocks));   // ONE request for ONE line (profiles/r01_membench*)
-    const uint4 m = bloom_masks(h);
+__device__ __forceinline__ bool bloom_test(const uint4 &v, const uint4 &m) {
     return ((v.x & m.x) == m.x) & ((v.y & m.y) == m.y) & ((v.z & m.z) == m.z) & ((v.w & m.w) == m.w);
+}
+__device__ __forceinline__ uint64_t bloom_block_hash(uint64_t x, uint64_t rc) { return mix64(x < rc ? x : rc); }
+__device__ __forceinline__ bool bloom_maybe(const DevDB &db, uint64_t word) {
+    const uint64_t hc = bloom_block_hash(word, revcomp_word(word));
+    const uint4 v = __ldg(db.bloom + __umul64hi(hc, db.bloom_blocks));   // ONE request for ONE line (profiles/r01_membench*)
+    return bloom_test(v, bloom_masks(hc, word));
 }
 // one thread per prefix bin: inserts the words of the bin's records
 __global__ void __launch_bounds__(256)
@@ -452,9 +464,9 @@ bloom_build_kernel(DevDB db, uint32_t *__restrict__ bloom) {
     if (p == db.quirk_bin) ++a;                                    // the folded record is unreachable anyway
     for (uint64_t i = a; i < b; ++i) {
         const uint64_t word = ((uint64_t)p << 40) | ((uint64_t)db.keys[i] << 8) | (load_aux(db, i) & 0xFFu);
-        const uint64_t h = mix64(word);
-        uint32_t *blk = bloom + 4 * __umul64hi(h, db.bloom_blocks);
-        const uint4 m = bloom_masks(h);
+        const uint64_t hc = bloom_block_hash(word, revcomp_word(word));
+        uint32_t *blk = bloom + 4 * __umul64hi(hc, db.bloom_blocks);
+        const uint4 m = bloom_masks(hc, word);
         atomicOr(blk + 0, m.x); atomicOr(blk + 1, m.y); atomicOr(blk + 2, m.z); atomicOr(blk + 3, m.w);
     }
 }
@@ -505,90 +517,119 @@ lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
 // or two lanes per warp whose word passes the filter and walks the whole
 // index -> key line -> aux chain, while the other ~30 lanes idle: the kernel
 // is bound by warp latency, not by DRAM.  So the work is split into two dense
-// passes: phase A tests every window against the filter (one fetch, no chain)
-// and appends the survivors to a queue with a warp-aggregated atomic; phase B
-// runs the exact search over the queue with every lane busy.
+// passes: phase A tests every window against the filter (one fetch per POSITION
+// serves both strands, no chain) and appends the survivors to a queue with a
+// warp-aggregated atomic; phase B runs the exact search over the queue with
+// every lane busy.
 __device__ __noinline__ uint32_t fast_lookup_cold(const DevDB &db, uint64_t w) {
     uint64_t ww[1] = {w};
     uint32_t rr[1];
     fast_lookup<1>(db, ww, rr);
     return rr[0];
 }
-#define Q_CHUNK 128u              // queue slots a warp reserves per atomic
+#define Q_CHUNK 128u              // queue slots a warp reserves per atomic (>= 64: two ballots per step)
 #ifndef FILT_ILP
 #define FILT_ILP 2                // filter probes in flight per lane
 #endif
 #define Q_INVALID 0xFFFFFFFFu
 #ifndef FILT_MINB
-#define FILT_MINB 5               // CTAs per SM the register budget is sized for
+#define FILT_MINB 4               // CTAs per SM the register budget is sized for
 #endif
-// DIAG (UTB_FILT_DIAG, measurements only): 1 = no survivor queue (count only), 2 = also no window extraction
-// (synthetic words), 0 = product
-template <int NSTR, int DIAG>
+// A warp's private window into the survivor queue: the global counter sees one
+// atomic per Q_CHUNK survivors instead of one per warp-step.
+struct WarpQueue {
+    uint64_t base;
+    uint32_t used;
+    bool have;
+};
+__device__ __forceinline__ void wq_init(WarpQueue &q) { q.base = 0; q.used = Q_CHUNK; q.have = false; }
+__device__ __forceinline__ void wq_retire(const WarpQueue &q, uint32_t lane, uint32_t *__restrict__ q_slots) {
+    if (q.have) for (uint32_t j = q.used + lane; j < Q_CHUNK; j += 32) q_slots[q.base + j] = Q_INVALID;   // pad the tail
+}
+// make room for c more entries (warp-uniform call)
+__device__ __forceinline__ void wq_reserve(WarpQueue &q, uint32_t c, uint32_t lane, uint32_t *__restrict__ q_slots,
+                                           unsigned long long *__restrict__ q_count, uint64_t q_cap) {
+    if (q.used + c <= Q_CHUNK) return;
+    wq_retire(q, lane, q_slots);
+    unsigned long long nb = 0;
+    if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
+    q.base = __shfl_sync(0xFFFFFFFFu, nb, 0);
+    q.used = 0;
+    q.have = q.base + Q_CHUNK <= q_cap;                            // beyond capacity: the caller resolves inline
+}
+// queue overflow / region overflow: the exact search right here (rare)
+__device__ __noinline__ uint32_t resolve_inline(const DevDB &db, uint64_t w, uint32_t slot, uint32_t *__restrict__ hits,
+                                                uint32_t *__restrict__ hitmap) {
+    const uint32_t r = fast_lookup_cold(db, w);
+    if (r == HIT_MISS) return 0;
+    hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u));
+    return 1;
+}
+// Tests one position (both strands when NSTR == 2) against its filter block v and appends the survivors.
+// Warp-uniform call; `valid` lanes hold a window w with reverse complement rc and block hash hc.
+template <int NSTR>
+__device__ __forceinline__ uint32_t filter_emit(const DevDB &db, WarpQueue &wq, uint32_t lane, bool valid, uint64_t w, uint64_t rc,
+                                                uint64_t hc, const uint4 &v, uint32_t pos,
+                                                uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots,
+                                                unsigned long long *__restrict__ q_count, uint64_t q_cap,
+                                                uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
+    const bool passF = valid && bloom_test(v, bloom_masks(hc, w));
+    const bool passR = NSTR == 2 && valid && bloom_test(v, bloom_masks(hc, rc));
+    const uint32_t bF = __ballot_sync(0xFFFFFFFFu, passF);
+    const uint32_t bR = NSTR == 2 ? __ballot_sync(0xFFFFFFFFu, passR) : 0u;
+    const uint32_t cF = __popc(bF), c = cF + __popc(bR);
+    uint32_t nh = 0;
+    if (!c) return 0;
+    wq_reserve(wq, c, lane, q_slots, q_count, q_cap);
+    const uint32_t lt = (1u << lane) - 1u;
+    if (wq.have) {
+        const uint64_t at = wq.base + wq.used;
+        if (passF) { const uint64_t i = at + __popc(bF & lt); q_words[i] = w; q_slots[i] = pos * NSTR; }
+        if (passR) { const uint64_t i = at + cF + __popc(bR & lt); q_words[i] = rc; q_slots[i] = pos * NSTR + 1u; }
+    } else {
+        if (passF) nh += resolve_inline(db, w, pos * NSTR, hits, hitmap);
+        if (passR) nh += resolve_inline(db, rc, pos * NSTR + 1u, hits, hitmap);
+    }
+    wq.used += c;
+    return nh;
+}
+
+// Direct filter pass (batches too small for the partitioned pass): persistent warps, one lane per
+// position, FILT_ILP positions of a lane in flight together.
+template <int NSTR>
 __global__ void __launch_bounds__(256, FILT_MINB)
 filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
               uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
               uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
               uint64_t q_cap, uint32_t *__restrict__ hitmap) {
-    // persistent warps: each owns a private chunk of the queue, so the global
-    // counter sees one atomic per Q_CHUNK survivors instead of one per warp-step
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t n_slots = (uint64_t)n_pos * NSTR;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t chunk_base = 0;
-    uint32_t chunk_used = Q_CHUNK;                                 // "no chunk yet"
-    bool have_chunk = false;
+    WarpQueue wq;
+    wq_init(wq);
     uint32_t nv = 0, nh = 0;
-    // every warp takes FILT_ILP x 32 consecutive slots per round: the FILT_ILP filter loads of a lane are in flight together
-    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * FILT_ILP; base < n_slots; base += stride * FILT_ILP) {
-        uint64_t w[FILT_ILP], h[FILT_ILP];
+    // every warp takes FILT_ILP x 32 consecutive positions per round (n_pos is a multiple of 32)
+    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * FILT_ILP; base < n_pos; base += stride * FILT_ILP) {
+        uint64_t w[FILT_ILP], rc[FILT_ILP], hc[FILT_ILP];
         uint4 v[FILT_ILP];
         bool valid[FILT_ILP];
 #pragma unroll
         for (int u = 0; u < FILT_ILP; ++u) {
-            const uint64_t slot = base + 32u * u + lane;
-            const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
+            const uint64_t pos = base + 32u * u + lane;
             w[u] = 0;
-            if (DIAG == 2) { valid[u] = slot < n_slots; w[u] = slot * 0x9E3779B97F4A7C15ull; }
-            else valid[u] = slot < n_slots && window_at(pk, bad, pos, w[u]);
-            if (NSTR == 2 && (slot & 1)) w[u] = revcomp_word(w[u]);
-            h[u] = mix64(w[u]);
+            valid[u] = pos < n_pos && window_at(pk, bad, (uint32_t)pos, w[u]);
+            rc[u] = revcomp_word(w[u]);
+            hc[u] = bloom_block_hash(w[u], rc[u]);
             v[u] = make_uint4(0, 0, 0, 0);
-            if (valid[u]) v[u] = __ldg(db.bloom + __umul64hi(h[u], db.bloom_blocks));
+            if (valid[u]) v[u] = __ldg(db.bloom + __umul64hi(hc[u], db.bloom_blocks));
         }
 #pragma unroll
         for (int u = 0; u < FILT_ILP; ++u) {
-            const uint64_t slot = base + 32u * u + lane;
-            const uint4 m4 = bloom_masks(h[u]);
-            const bool pass = valid[u] & ((v[u].x & m4.x) == m4.x) & ((v[u].y & m4.y) == m4.y) & ((v[u].z & m4.z) == m4.z) & ((v[u].w & m4.w) == m4.w);
-            uint32_t r = valid[u] ? HIT_MISS : HIT_NOWIN;
-            const uint32_t m = DIAG ? 0u : __ballot_sync(0xFFFFFFFFu, pass);
-            const uint32_t c = __popc(m);
-            if (DIAG) nh += pass;
-            if (c) {
-                if (chunk_used + c > Q_CHUNK) {                    // retire the chunk (pad its tail) and take a new one
-                    if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
-                    unsigned long long nb = 0;
-                    if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
-                    chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
-                    chunk_used = 0;
-                    have_chunk = chunk_base + Q_CHUNK <= q_cap;    // beyond capacity: resolve inline from here on
-                }
-                if (pass) {
-                    if (have_chunk) {
-                        const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
-                        q_words[idx] = w[u]; q_slots[idx] = (uint32_t)slot;
-                    } else {                                       // queue full: resolve here
-                        r = fast_lookup_cold(db, w[u]);
-                        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); }
-                    }
-                }
-                chunk_used += c;
-            }
-            nv += valid[u]; nh += r < HIT_NOWIN;                   // hits[] was pre-set to MISS: nothing to store for the rest
+            const uint32_t pos = (uint32_t)(base + 32u * u + lane);
+            nh += filter_emit<NSTR>(db, wq, lane, valid[u], w[u], rc[u], hc[u], v[u], pos, q_words, q_slots, q_count, q_cap, hits, hitmap);
+            nv += valid[u] ? NSTR : 0;                             // hits[] is only valid where hitmap is set: nothing to store for misses
         }
     }
-    if (have_chunk) for (uint32_t j = chunk_used + lane; j < Q_CHUNK; j += 32) q_slots[chunk_base + j] = Q_INVALID;
+    wq_retire(wq, lane, q_slots);
     for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xFFFFFFFFu, nv, o); nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); }
     if (lane == 0) {
         const uint32_t cs = (blockIdx.x * 8 + (threadIdx.x >> 5)) & (COUNTER_SLOTS - 1);
@@ -597,101 +638,107 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     }
 }
 
-// ---- partitioned filter pass (UTB_PARTITION=1) -------------------------------------
+// ---- partitioned filter pass ----------------------------------------------------------
 // One random 128-byte DRAM line per probe is what bounds filter_kernel.  Here the
-// lookups of a batch are first bucketed by the top 6 bits of the filter hash
-// (64 partitions = 64 contiguous ~34 MB slices of the filter): partition_kernel
-// streams (word, slot) records into per-partition arrays (12 B per lookup,
-// sequential), then probe_kernel sweeps the partitions in order with the whole
-// grid, so the slice being probed stays resident in the 126 MB L2 and each of its
-// lines is fetched from HBM once per batch instead of once per probe.
+// positions of a batch are first bucketed by the top 6 bits of the filter's block
+// hash (64 partitions = 64 contiguous ~34 MB slices of the filter): partition_kernel
+// streams (forward word, position) records into per-partition arrays (12 B per
+// position = 6 B per lookup with both strands, sequential), then probe_kernel sweeps
+// the partitions in order with the whole grid, so the slice being probed stays
+// resident in the 126 MB L2 and each of its lines is fetched from HBM once per batch
+// instead of once per probe.
 #define NPART 64u
-#define PART_MIN_SLOTS (400ull << 20)   // lookup slots in a batch from which the partitioned pass is used (~1.3 M reads of 150 bp)
+#define PART_MIN_POS (256ull << 20)  // positions in a batch from which the partitioned pass is used (~1.6 M reads of 150 bp); below it the
+                                     // direct filter wins: 64 grid barriers per batch and a cooperative launch that cannot overlap other slots
 #define P_CTAS (148u * 4u)      // partitioner CTAs; each owns one output region per partition
-#define P_TILE 4096u            // slots a CTA sorts in shared memory at a time
-#define P_SMEM (P_TILE * 8u + P_TILE * 4u + P_TILE)   // words + slots + partition ids
-// Partitioner: every CTA counting-sorts one 4096-slot tile at a time in shared memory and appends each
-// partition's run to its own region [(c*NPART+p)*cap_cp, +cap_cp), so the global stores are contiguous
-// runs (~47 records) instead of one transaction per record (scattered 8-byte stores cost as much as
-// scattered sector reads, profiles/).  No global atomics; the fill of every region is stored at the end.
-// Hash partitions are uniform and every CTA sees the same share of the batch, so regions fill evenly
-// (cap_cp carries 25 % head-room; an overflowing record is resolved inline).
+#define P_TILE 4096u            // positions a CTA sorts in shared memory at a time
+#define P_PPT (P_TILE / 256u)   // positions per thread and tile
+#define P_SMEM (P_TILE * 8u + P_TILE * 4u)   // words in tile order + sorted order (local index | partition << 16)
+// Partitioner: every CTA counting-sorts one 4096-position tile at a time and appends each partition's
+// run to its own region [(c*NPART+p)*cap_cp, +cap_cp), so the global stores are contiguous runs (~47
+// records) instead of one transaction per record (scattered 8-byte stores cost as much as scattered
+// sector reads, profiles/).  The words stay in tile order in shared memory; only a 4-byte index is
+// scattered, and the output pass gathers through it.  No global atomics; the fill of every region is
+// stored at the end.  Hash partitions are uniform and every CTA sees the same share of the batch, so
+// regions fill evenly (cap_cp carries 25 % head-room; records of an overflowing tile are resolved inline).
 template <int NSTR>
 __global__ void __launch_bounds__(256, 4)
 partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
                  unsigned long long *__restrict__ counters,
-                 uint64_t *__restrict__ p_words, uint32_t *__restrict__ p_slots, uint32_t *__restrict__ p_fill,
+                 uint64_t *__restrict__ p_words, uint32_t *__restrict__ p_pos, uint32_t *__restrict__ p_fill,
                  uint32_t cap_cp, uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
     extern __shared__ __align__(16) unsigned char p_smem[];
-    uint64_t *s_words = reinterpret_cast<uint64_t *>(p_smem);
-    uint32_t *s_slots = reinterpret_cast<uint32_t *>(p_smem + P_TILE * 8u);
-    uint8_t *s_part = p_smem + P_TILE * 12u;
+    uint64_t *s_w = reinterpret_cast<uint64_t *>(p_smem);
+    uint32_t *s_ord = reinterpret_cast<uint32_t *>(p_smem + P_TILE * 8u);
     __shared__ uint32_t s_hist[NPART], s_start[NPART], s_cur[NPART];
+    __shared__ uint64_t s_gbase[NPART];                            // region base + fill - start: global index = s_gbase[part] + sorted rank
+    __shared__ uint32_t s_ovf;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint64_t n_slots = (uint64_t)n_pos * NSTR;
     if (tid < NPART) s_cur[tid] = 0;
     uint32_t nv = 0, nh = 0;
     const uint64_t region0 = (uint64_t)blockIdx.x * NPART * cap_cp;
-    for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_slots; tile += (uint64_t)gridDim.x * P_TILE) {
+    for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_pos; tile += (uint64_t)gridDim.x * P_TILE) {
         if (tid < NPART) s_hist[tid] = 0;
+        if (tid == 0) s_ovf = 0;
         __syncthreads();
-        // pass A: partition id and rank inside the tile.  One thread per POSITION: a single window extraction
-        // feeds both strands (slots 2*pos and 2*pos+1).  The words are recomputed in pass B, which is cheaper
-        // than keeping 16 u64 live across the barrier.
-        constexpr uint32_t PPT = P_TILE / NSTR / 256;               // positions per thread
-        uint32_t meta[PPT * NSTR];                                  // rank << 8 | part, or 0xFFFFFFFF
-        const uint32_t tile_pos = (uint32_t)(tile / NSTR);
+        // pass A: window, partition id and rank inside the tile.  A warp covers 32 consecutive positions = one
+        // group of the packed stream, so its pk/bad loads are warp-uniform.
+        uint32_t meta[P_PPT];                                      // rank << 6 | part, or 0xFFFFFFFF
+        const uint32_t tile_pos = (uint32_t)tile;
 #pragma unroll
-        for (uint32_t k = 0; k < PPT; ++k) {
-            const uint32_t pos = tile_pos + k * 256u + tid;
-            uint64_t w;
-#pragma unroll
-            for (int st = 0; st < NSTR; ++st) meta[k * NSTR + st] = 0xFFFFFFFFu;
-            if (pos < n_pos && window_at(pk, bad, pos, w)) {
-#pragma unroll
-                for (int st = 0; st < NSTR; ++st) {
-                    const uint64_t ws = st ? revcomp_word(w) : w;
-                    const uint32_t part = (uint32_t)(mix64(ws) >> 58);
-                    meta[k * NSTR + st] = (atomicAdd(&s_hist[part], 1u) << 8) | part;
-                }
+        for (uint32_t k = 0; k < P_PPT; ++k) {
+            const uint32_t local = k * 256u + tid;
+            const uint64_t pos = tile + local;
+            uint64_t w = 0;
+            meta[k] = 0xFFFFFFFFu;
+            if (pos < n_pos && window_at(pk, bad, (uint32_t)pos, w)) {
+                const uint32_t part = (uint32_t)(bloom_block_hash(w, revcomp_word(w)) >> 58);
+                meta[k] = (atomicAdd(&s_hist[part], 1u) << 6) | part;
                 nv += NSTR;
             }
+            s_w[local] = w;
         }
         __syncthreads();
         if (tid < 32) {                                            // exclusive scan of the 64 bins by one warp
             const uint32_t h0 = s_hist[2 * tid], h1 = s_hist[2 * tid + 1];
             uint32_t x = h0 + h1;
             for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((int)tid >= o) x += t; }
-            s_start[2 * tid] = x - h0 - h1; s_start[2 * tid + 1] = x - h1;
+            const uint32_t st0 = x - h0 - h1, st1 = x - h1, c0 = s_cur[2 * tid], c1 = s_cur[2 * tid + 1];
+            s_start[2 * tid] = st0; s_start[2 * tid + 1] = st1;
+            s_gbase[2 * tid] = region0 + (uint64_t)(2 * tid) * cap_cp + c0 - st0;
+            s_gbase[2 * tid + 1] = region0 + (uint64_t)(2 * tid + 1) * cap_cp + c1 - st1;
+            if (c0 + h0 > cap_cp || c1 + h1 > cap_cp) s_ovf = 1;
         }
         __syncthreads();
-        // pass B: scatter into shared memory in partition order
+        // pass B: the sorted order (4 bytes per record scattered; the words stay where they are)
 #pragma unroll
-        for (uint32_t k = 0; k < PPT; ++k) {
-            if (meta[k * NSTR] == 0xFFFFFFFFu) continue;           // both strands share validity
-            const uint32_t pos = tile_pos + k * 256u + tid;
-            uint64_t w;
-            window_at(pk, bad, pos, w);
-#pragma unroll
-            for (int st = 0; st < NSTR; ++st) {
-                const uint32_t m = meta[k * NSTR + st];
-                const uint32_t part = m & 0xFFu, dst = s_start[part] + (m >> 8);
-                s_words[dst] = st ? revcomp_word(w) : w;
-                s_slots[dst] = pos * NSTR + st;
-                s_part[dst] = (uint8_t)part;
-            }
+        for (uint32_t k = 0; k < P_PPT; ++k) {
+            const uint32_t m = meta[k];
+            if (m == 0xFFFFFFFFu) continue;
+            const uint32_t part = m & 63u;
+            s_ord[s_start[part] + (m >> 6)] = (k * 256u + tid) | (part << 16);
         }
         __syncthreads();
         // pass C: contiguous runs out to the regions
         const uint32_t total = s_start[NPART - 1] + s_hist[NPART - 1];
-        for (uint32_t e = tid; e < total; e += 256) {
-            const uint32_t part = s_part[e], at = s_cur[part] + (e - s_start[part]);
-            if (at < cap_cp) {
-                const uint64_t idx = region0 + (uint64_t)part * cap_cp + at;
-                p_words[idx] = s_words[e]; p_slots[idx] = s_slots[e];
-            } else if (bloom_maybe(db, s_words[e])) {              // region full: resolve here
-                const uint32_t r = fast_lookup_cold(db, s_words[e]);
-                if (r != HIT_MISS) { hits[s_slots[e]] = r; atomicOr(hitmap + (s_slots[e] >> 5), 1u << (s_slots[e] & 31u)); ++nh; }
+        if (!s_ovf) {
+            for (uint32_t e = tid; e < total; e += 256) {
+                const uint32_t o = s_ord[e], local = o & 0xFFFFu;
+                const uint64_t idx = s_gbase[o >> 16] + e;
+                p_words[idx] = s_w[local]; p_pos[idx] = tile_pos + local;
+            }
+        } else {                                                   // some region is full: per-record bound check
+            for (uint32_t e = tid; e < total; e += 256) {
+                const uint32_t o = s_ord[e], local = o & 0xFFFFu, part = o >> 16;
+                const uint32_t at = s_cur[part] + (e - s_start[part]);
+                const uint64_t w = s_w[local];
+                const uint32_t pos = tile_pos + local;
+                if (at < cap_cp) { const uint64_t idx = s_gbase[part] + e; p_words[idx] = w; p_pos[idx] = pos; }
+                else {
+                    const uint64_t rc = revcomp_word(w);
+                    if (bloom_maybe(db, w)) nh += resolve_inline(db, w, pos * NSTR, hits, hitmap);
+                    if (NSTR == 2 && bloom_maybe(db, rc)) nh += resolve_inline(db, rc, pos * NSTR + 1u, hits, hitmap);
+                }
             }
         }
         __syncthreads();
@@ -709,58 +756,78 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
 
 // Probe pass (cooperative launch): the whole grid sweeps partition 0, then 1, ... with a grid barrier in
 // between, so exactly one ~34 MB slice of the filter is live in L2 at a time; the records are read with
-// streaming loads (evict-first) so that they do not push that slice out.
-#define P_SUB 1024u             // records of a region one warp takes at a time
-__global__ void __launch_bounds__(256, 6)
-probe_kernel(DevDB db, const uint64_t *__restrict__ p_words, const uint32_t *__restrict__ p_slots,
-             const uint32_t *__restrict__ p_fill, uint32_t cap_cp, uint32_t n_ctas,
+// streaming loads (evict-first) so that they do not push that slice out.  Inside a partition the warps
+// draw work items (1024 records of one region) from a counter, so nobody waits at the barrier for a
+// warp that happened to own fuller regions.  Every lane carries two records per step: one 16-byte
+// record load, two filter loads in flight.
+#define P_SUB 1024u             // records of a region one work item covers
+template <int NSTR>
+__global__ void __launch_bounds__(256, 4)
+probe_kernel(DevDB db, const uint64_t *__restrict__ p_words, const uint32_t *__restrict__ p_pos,
+             const uint32_t *__restrict__ p_fill, uint32_t cap_cp, uint32_t n_ctas, uint32_t *__restrict__ p_ctr,
              uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count, uint64_t q_cap,
              uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
     cg::grid_group grid = cg::this_grid();
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t subs = (cap_cp + P_SUB - 1) / P_SUB;            // work items per region
-    uint64_t chunk_base = 0;
-    uint32_t chunk_used = Q_CHUNK, nh = 0;
-    bool have_chunk = false;
+    const uint32_t n_items = n_ctas * subs;
+    WarpQueue wq;
+    wq_init(wq);
+    uint32_t nh = 0;
     for (uint32_t part = 0; part < NPART; ++part) {
-        for (uint32_t item = gwarp; item < n_ctas * subs; item += n_warps) {
-            const uint32_t c = item / subs, sub = item % subs;
+        for (;;) {
+            uint32_t item = 0;
+            if (lane == 0) item = atomicAdd(p_ctr + part, 1u);
+            item = __shfl_sync(0xFFFFFFFFu, item, 0);
+            if (item >= n_items) break;
+            const uint32_t c = item / subs, sub = item - c * subs;
             const uint32_t fill = __ldg(p_fill + c * NPART + part);
-            const uint64_t base = ((uint64_t)c * NPART + part) * cap_cp;
+            const uint64_t base = ((uint64_t)c * NPART + part) * cap_cp;   // even: cap_cp is even
             const uint32_t j1 = min(fill, (sub + 1) * P_SUB);
-            for (uint32_t j0 = sub * P_SUB; j0 < j1; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                const bool live = j < j1;
-                const uint64_t w = live ? __ldcs(p_words + base + j) : 0;
-                const bool pass = live && bloom_maybe(db, w);
-                const uint32_t m = __ballot_sync(0xFFFFFFFFu, pass);
-                const uint32_t cnt = __popc(m);
-                if (!cnt) continue;
-                if (chunk_used + cnt > Q_CHUNK) {
-                    if (have_chunk) for (uint32_t k = chunk_used + lane; k < Q_CHUNK; k += 32) q_slots[chunk_base + k] = Q_INVALID;
-                    unsigned long long nb = 0;
-                    if (lane == 0) nb = atomicAdd(q_count, (unsigned long long)Q_CHUNK);
-                    chunk_base = __shfl_sync(0xFFFFFFFFu, nb, 0);
-                    chunk_used = 0;
-                    have_chunk = chunk_base + Q_CHUNK <= q_cap;
+            for (uint32_t j0 = sub * P_SUB; j0 < j1; j0 += 64) {
+                const uint32_t j = j0 + 2u * lane;
+                uint64_t w[2] = {0, 0}, rc[2], hc[2];
+                uint4 v[2];
+                bool live[2] = {j < j1, j + 1u < j1};
+                if (live[0]) {                                     // j + 1 < cap_cp always: one aligned 16-byte load
+                    const ulonglong2 t = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + j));
+                    w[0] = t.x; w[1] = t.y;
                 }
-                if (pass) {
-                    const uint32_t slot = __ldcs(p_slots + base + j);
-                    if (have_chunk) {
-                        const uint64_t idx = chunk_base + chunk_used + __popc(m & ((1u << lane) - 1u));
-                        q_words[idx] = w; q_slots[idx] = slot;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    rc[u] = revcomp_word(w[u]);
+                    hc[u] = bloom_block_hash(w[u], rc[u]);
+                    v[u] = make_uint4(0, 0, 0, 0);
+                    if (live[u]) v[u] = __ldg(db.bloom + __umul64hi(hc[u], db.bloom_blocks));
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    // the position is only needed by survivors (~2.5 %)
+                    const bool passF = live[u] && bloom_test(v[u], bloom_masks(hc[u], w[u]));
+                    const bool passR = NSTR == 2 && live[u] && bloom_test(v[u], bloom_masks(hc[u], rc[u]));
+                    const uint32_t bF = __ballot_sync(0xFFFFFFFFu, passF);
+                    const uint32_t bR = NSTR == 2 ? __ballot_sync(0xFFFFFFFFu, passR) : 0u;
+                    const uint32_t cF = __popc(bF), cnt = cF + __popc(bR);
+                    if (!cnt) continue;
+                    wq_reserve(wq, cnt, lane, q_slots, q_count, q_cap);
+                    const uint32_t lt = (1u << lane) - 1u;
+                    uint32_t pos = 0;
+                    if (passF || passR) pos = __ldcs(p_pos + base + j + u);
+                    if (wq.have) {
+                        const uint64_t at = wq.base + wq.used;
+                        if (passF) { const uint64_t i = at + __popc(bF & lt); q_words[i] = w[u]; q_slots[i] = pos * NSTR; }
+                        if (passR) { const uint64_t i = at + cF + __popc(bR & lt); q_words[i] = rc[u]; q_slots[i] = pos * NSTR + 1u; }
                     } else {
-                        const uint32_t r = fast_lookup_cold(db, w);
-                        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
+                        if (passF) nh += resolve_inline(db, w[u], pos * NSTR, hits, hitmap);
+                        if (passR) nh += resolve_inline(db, rc[u], pos * NSTR + 1u, hits, hitmap);
                     }
+                    wq.used += cnt;
                 }
-                chunk_used += cnt;
             }
         }
         grid.sync();
     }
-    if (have_chunk) for (uint32_t k = chunk_used + lane; k < Q_CHUNK; k += 32) q_slots[chunk_base + k] = Q_INVALID;
+    wq_retire(wq, lane, q_slots);
     for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
     if (lane == 0 && nh) atomicAdd(counters + COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)nh);
 }
@@ -1497,7 +1564,7 @@ struct utb_batch {
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
-    uint64_t *d_pwords; uint32_t *d_pslots; uint32_t *d_pfill; uint64_t p_total, part_min_slots;   // partitioned filter pass
+    uint64_t *d_pwords; uint32_t *d_ppos; uint32_t *d_pfill; uint32_t *d_pctr; uint64_t p_total, part_min_pos;   // partitioned filter pass
     // last submit
     size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom; int used_partition;
     uint64_t launches;
@@ -1526,7 +1593,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
-    cudaFree(b->d_pwords); cudaFree(b->d_pslots); cudaFree(b->d_pfill);
+    cudaFree(b->d_pwords); cudaFree(b->d_ppos); cudaFree(b->d_pfill); cudaFree(b->d_pctr);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 7; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -1589,17 +1656,18 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         BK(cudaMalloc(&b->d_qslots, b->q_cap * 4));
         BK(cudaMalloc(&b->d_qcount, 8));
         BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
-        // Partitioned filter pass: pays once a batch holds enough lookups for the probes of a partition to
+        // Partitioned filter pass: pays once a batch holds enough positions for the probes of a partition to
         // reuse its filter lines (and to amortise 64 grid barriers); UTB_PARTITION=1 forces it, =0 disables it.
         const char *pe = getenv("UTB_PARTITION");
-        b->part_min_slots = pe ? (atoi(pe) ? 0 : ~0ull) : PART_MIN_SLOTS;
-        const char *pm = getenv("UTB_PARTITION_MIN_MSLOTS");      // threshold in Mi lookup slots (tuning)
-        if (pm && atoi(pm) > 0) b->part_min_slots = (uint64_t)atoi(pm) << 20;
-        if (npos * 2 >= b->part_min_slots) {                        // one region per (CTA, partition), 25 % head-room
-            b->p_total = (uint64_t)((double)(npos * 2) * 1.25) + (uint64_t)P_CTAS * NPART * 64;
+        b->part_min_pos = pe ? (atoi(pe) ? 0 : ~0ull) : PART_MIN_POS;
+        const char *pm = getenv("UTB_PARTITION_MIN_MPOS");         // threshold in Mi positions (tuning)
+        if (pm && atoi(pm) > 0) b->part_min_pos = (uint64_t)atoi(pm) << 20;
+        if (npos >= b->part_min_pos) {                              // one region per (CTA, partition), 25 % head-room
+            b->p_total = (uint64_t)((double)npos * 1.25) + (uint64_t)P_CTAS * NPART * 68;
             BK(cudaMalloc(&b->d_pwords, b->p_total * 8));
-            BK(cudaMalloc(&b->d_pslots, b->p_total * 4));
+            BK(cudaMalloc(&b->d_ppos, b->p_total * 4));
             BK(cudaMalloc(&b->d_pfill, (size_t)P_CTAS * NPART * 4));
+            BK(cudaMalloc(&b->d_pctr, NPART * 4));
         }
     }
     if (db->l2_window) {
@@ -1644,37 +1712,35 @@ static int launch_stages(utb_batch *b, bool timed) {
             // 1-bit-per-slot map, the vote reads the map and gathers only flagged slots
             CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st));
             if (timed) CK(cudaEventRecord(b->ev[4], b->st));
-            const unsigned pb = nb < 148u * FILT_MINB ? nb : 148u * FILT_MINB;   // persistent: FILT_MINB CTAs per SM
-            const char *dg = getenv("UTB_FILT_DIAG");
-            const int diag = dg ? atoi(dg) : 0;
-            if (b->d_pwords && !diag && (uint64_t)n_pos * nstr >= b->part_min_slots) {
-                const uint64_t n_slots = (uint64_t)n_pos * nstr;
-                const unsigned tiles = (unsigned)((n_slots + P_TILE - 1) / P_TILE);
+            const unsigned wb = (n_pos + 255u * FILT_ILP) / (256u * FILT_ILP);   // CTAs that cover every position once
+            const unsigned pb = wb < 148u * FILT_MINB ? wb : 148u * FILT_MINB;  // persistent: FILT_MINB CTAs per SM
+            if (b->d_pwords && (uint64_t)n_pos >= b->part_min_pos) {
+                const unsigned tiles = (unsigned)(((uint64_t)n_pos + P_TILE - 1) / P_TILE);
                 const unsigned gb = tiles < P_CTAS ? tiles : P_CTAS;
-                uint32_t cap_cp = (uint32_t)((double)n_slots / ((double)gb * NPART) * 1.25) + 64;   // <= p_total / (gb * NPART)
+                uint32_t cap_cp = ((uint32_t)((double)n_pos / ((double)gb * NPART) * 1.25) + 66u) & ~1u;   // even; <= p_total / (gb * NPART)
                 if (nstr == 2) {
                     CK(cudaFuncSetAttribute(partition_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                    partition_kernel<2><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_pslots, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
+                    partition_kernel<2><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
                 } else {
                     CK(cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                    partition_kernel<1><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_pslots, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
+                    partition_kernel<1><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
                 }
                 if (timed) CK(cudaEventRecord(b->ev[6], b->st));
                 b->used_partition = 1;
+                CK(cudaMemsetAsync(b->d_pctr, 0, NPART * 4, b->st));
                 // cooperative launch: the grid barrier between partitions needs every CTA resident
+                const void *pk_fn = nstr == 2 ? (const void *)probe_kernel<2> : (const void *)probe_kernel<1>;
                 int per_sm = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel, 256, 0));
-                if (per_sm > 6) per_sm = 6;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fn, 256, 0));
+                if (per_sm > 4) per_sm = 4;
                 unsigned pgrid = 148u * (unsigned)(per_sm > 0 ? per_sm : 1), n_ctas = gb;
                 DevDB dd = d;
-                void *args[] = {&dd, &b->d_pwords, &b->d_pslots, &b->d_pfill, &cap_cp, &n_ctas, &b->d_qwords, &b->d_qslots,
+                void *args[] = {&dd, &b->d_pwords, &b->d_ppos, &b->d_pfill, &cap_cp, &n_ctas, &b->d_pctr, &b->d_qwords, &b->d_qslots,
                                 &b->d_qcount, &b->q_cap, &b->d_hits, &b->d_hitmap, &b->d_counters};
-                CK(cudaLaunchCooperativeKernel((void *)probe_kernel, dim3(pgrid), dim3(256), args, 0, b->st));
+                CK(cudaLaunchCooperativeKernel(pk_fn, dim3(pgrid), dim3(256), args, 0, b->st));
                 b->launches++;
-            } else if (diag == 1) filter_kernel<2, 1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else if (diag == 2) filter_kernel<2, 2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else if (nstr == 2) filter_kernel<2, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else filter_kernel<1, 0><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            } else if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
             queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
             b->launches++;
@@ -1864,8 +1930,8 @@ extern "C" int utb_batch_last_ms(utb_batch *b, float ms[4]) {
 }
 extern "C" uint64_t utb_batch_launches(const utb_batch *b) { return b ? b->launches : 0; }
 // Two-phase detail of the LAST run (valid after wait): ms[0] filter kernel, ms[1] queue kernel (0/0 when the
-// single lookup kernel ran); sectors[0] = filter probes (one sector each), sectors[1] = sectors the exact
-// path touched for the survivors.
+// single lookup kernel ran); sectors[0] = lookups answered by the filter (one sector per position, both
+// strands), sectors[1] = sectors the exact path touched for the survivors.
 // ms[0] partition_kernel, ms[1] probe_kernel of the LAST run; both 0 when the direct filter kernel ran.
 extern "C" int utb_batch_partition_detail(utb_batch *b, float ms[2]) {
     if (!b || !ms) { utb_set_error("utb_batch_partition_detail: null argument"); return UTB_ERR_ARG; }
