@@ -147,6 +147,11 @@ int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len,
  * (itree.c:1028-1098). */
 int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off,
                   size_t n_reads, utb_result *results);
+/* The same vote through the representation the batch pipeline uses (slots of a
+ * read aligned to 32, 1-bit-per-slot hit map; thread-per-read kernel, with the
+ * warp and block kernels behind it for label-rich and long reads). */
+int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint64_t *off,
+                         size_t n_reads, utb_result *results);
 
 /* ---- host stages (no GPU involved; CPU tests drive them directly) --------- */
 /* The reference's record reader (itree.c:866-890) over a byte buffer: lines
@@ -158,6 +163,12 @@ int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off,
 int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t max_reads,
                       uint64_t *seq_off, uint32_t *seq_len, uint32_t *name_off, uint32_t *name_len,
                       size_t *n_reads, size_t *used, int *ref_exit);
+/* Host stage of the device-side framing (default when the output text is built
+ * on the device): the reader only counts the newlines of a chunk -- lines are
+ * read strictly in pairs (itree.c:869-871), so the count fixes the number of
+ * complete records -- and checks that no NUL byte occurs; the records are
+ * framed by the GPU.  UTB_HOST_FRAME=1 keeps the host framer. */
+int utb_count_newlines(const char *buf, size_t n, int threads, size_t *n_newlines, int *has_nul);
 /* The reference's output lines (itree.c:1032, 1040, 1096) for n_reads result
  * records; names are taken from bytes[name_off[r] .. +name_len[r]). */
 int utb_format_results(const utb_ctr *ctr, const char *bytes, const uint32_t *name_off, const uint32_t *name_len,

@@ -65,18 +65,23 @@ def test_pack_matches_oracle_words(gpu):
         assert np.array_equal(np.concatenate([fwd[valid == 1], rc[valid == 1][::-1]]), owords_rc), name
 
 
-def test_vote_matches_oracle(gpu):
-    """Vote on real hit lists, on permuted hit lists (SURVEY 0 #6) and on synthetic multisets."""
-    ctr, db, orc = gpu["toyA"]
+@pytest.mark.parametrize("sparse", [False, True])
+@pytest.mark.parametrize("dbname", ["toyA", "toyB_u32"])
+def test_vote_matches_oracle(gpu, dbname, sparse):
+    """Vote on real hit lists, on permuted hit lists and on synthetic multisets; dense
+    (warp/block kernels) and through the pipeline's sparse hit map (thread kernel first)."""
+    ctr, db, orc = gpu[dbname]
     rng = np.random.default_rng(9)
     lists = []
-    for name, seq in read_fasta(gold("toyA_reads.fa"))[:300] + read_fasta(gold("long_reads.fa")):
+    reads = read_fasta(gold("toyA_reads.fa"))[:300] + read_fasta(gold("long_reads.fa")) if dbname == "toyA" \
+        else read_fasta(gold("toyB_reads.fa"))[:600]
+    for name, seq in reads:
         h, _ = orc.slide(seq, do_rc=True)
         lists.append(h)
         if h.size > 2:
             lists.append(rng.permutation(h))
-    for k in range(300):      # random multisets over many labels (forces the block path too)
-        nl = int(rng.integers(1, min(ctr.max_ix, 90)))
+    for k in range(400):      # random multisets over few and many labels (forces the warp and block paths too)
+        nl = int(rng.integers(1, min(ctr.max_ix, 90 if k % 2 else 8)))
         labs = rng.choice(ctr.max_ix, nl, replace=False)
         cnt = rng.integers(1, 40, nl)
         h = np.repeat(labs, cnt).astype(np.uint32)
@@ -85,7 +90,7 @@ def test_vote_matches_oracle(gpu):
     off = np.zeros(len(lists) + 1, dtype=np.uint64)
     off[1:] = np.cumsum([l.size for l in lists])
     # sprinkle misses between the hits: they must be ignored
-    res = db.vote_hits(np.concatenate(lists), off)
+    res = db.vote_hits(np.concatenate(lists), off, sparse=sparse)
     for i, h in enumerate(lists):
         v = orc.vote(h)
         r = res[i]
@@ -344,22 +349,68 @@ def test_every_lookup_variant_gives_the_reference_output(ctrs, tmp_path, env, db
         s.destroy(); ctr.close()
 
 
-@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[5], CASES[7]])
-def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, reads, out, rc):
+@pytest.mark.parametrize("atoms", ["0", "1"])
+@pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[1], CASES[2], CASES[5], CASES[7]])
+def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, reads, out, rc, atoms):
     """UTB_PARTITION=1 forces the large-batch path (shared-memory counting sort into 64 filter-slice
-    partitions + cooperative probe sweep) on small inputs: identical bytes."""
+    partitions + cooperative probe sweep) on small inputs, with the match-ranked and the atomic-ranked
+    partitioner: identical bytes.  The input is repeated so that every partitioner CTA sees several tiles."""
     from utree_b200 import capi
     os.environ["UTB_PARTITION"] = "1"
+    os.environ["UTB_BLOOM"] = "1"
     try:
         ctr = capi.Ctr(ctrs[db_name])
         s = capi.Searcher(ctr, devices=(0,), host_threads=3)
     finally:
-        del os.environ["UTB_PARTITION"]
+        del os.environ["UTB_PARTITION"], os.environ["UTB_BLOOM"]
+    os.environ["UTB_PART_ATOMS"] = atoms
     try:
-        code, ref_exit, text, st = s.search_mem(open(gold(reads), "rb").read(), do_rc=bool(rc))
-        assert code == 0 and text == open(gold(out), "rb").read()
+        reps = 24 if reads != "long_reads.fa" else 2
+        data = open(gold(reads), "rb").read()
+        code, ref_exit, text, st = s.search_mem(data * reps, do_rc=bool(rc))
+        assert code == 0 and text == open(gold(out), "rb").read() * reps
     finally:
+        del os.environ["UTB_PART_ATOMS"]
         s.destroy(); ctr.close()
+
+
+@pytest.mark.parametrize("host_frame", [0, 1])
+def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, host_frame):
+    """Records framed on the GPU (the host only counts newlines): several batches with a carried tail,
+    CRLF / tab-in-header / empty-line records, and a malformed record deep in the input -- the reader
+    rewinds to that batch and the host framer reproduces the reference's partial output and exit code.
+    UTB_HOST_FRAME=1 (host framer throughout) must give the same bytes."""
+    from utree_b200 import capi
+    one = open(gold("toyA_reads.fa"), "rb").read()
+    want = open(gold("toyA_rc.out"), "rb").read()
+    reps = 180                                                      # 35.6 MB: two 33.5 MB batches
+    edge = open(gold("edge_reads.fa"), "rb").read()
+    if not edge.endswith(b"\n"):
+        edge += b"\n"
+    os.environ["UTB_BATCH_MB"] = "33"
+    if host_frame:
+        os.environ["UTB_HOST_FRAME"] = "1"
+    try:
+        s = capi.Searcher(gpu["toyA"][0], devices=(0, 0), host_threads=5)
+    finally:
+        os.environ.pop("UTB_BATCH_MB", None); os.environ.pop("UTB_HOST_FRAME", None)
+    try:
+        rc, ex, text, st = s.search_mem(one * reps, do_rc=True)
+        assert rc == 0 and st["batches"] >= 2 and st["reads"] == reps * one.count(b">")
+        assert text == want * reps
+        rc, ex, text, st = s.search_mem(edge, do_rc=True)
+        assert rc == 0 and text == open(gold("edge_rc.out"), "rb").read()
+        # no header '>' on a record of the second batch
+        rc, ex, text, st = s.search_mem(one * reps + b"ACGT\nACGT\n" + one, do_rc=True)
+        assert (rc, ex) == (3, 2) and text == want * reps
+        # sequence line begins '>' inside the first batch
+        rc, ex, text, st = s.search_mem(one + b">x\n>y\n" + one * reps, do_rc=True)
+        assert (rc, ex) == (3, 2) and text == want
+        # and the searcher is reusable afterwards
+        rc, ex, text, st = s.search_mem(one * 2, do_rc=True)
+        assert rc == 0 and text == want * 2
+    finally:
+        s.destroy()
 
 
 def test_empty_and_hitless_inputs(gpu, tmp_path):

@@ -48,7 +48,7 @@ EXPORTS = [
     "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
     "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
     "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail", "utb_batch_partition_detail",
-    "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_frame_records", "utb_format_results",
+    "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_vote_hits_sparse", "utb_frame_records", "utb_count_newlines", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
     "utb_main", "utb_measure_rand32", "utb_compress_ubt", "utb_compress_main",
 ]
@@ -153,6 +153,14 @@ def frame_records(buf: bytes, eof=True, threads=1, max_reads=None):
     return rc, ex.value, used.value, recs, (name_off[:n.value].copy(), name_len[:n.value].copy())
 
 
+def count_newlines(buf: bytes, threads=1):
+    """Host stage of the device-side framing (utb_count_newlines) -> (n_newlines, has_nul)."""
+    n, z = C.c_size_t(), C.c_int()
+    lib().utb_count_newlines.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
+    _ck(lib().utb_count_newlines(buf, len(buf), threads, C.byref(n), C.byref(z)))
+    return n.value, bool(z.value)
+
+
 def format_results(ctr, buf: bytes, name_off, name_len, results):
     """Host formatter (utb_format_results) -> bytes."""
     results = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
@@ -202,12 +210,15 @@ class Db:
         _ck(lib().utb_pack_sequence(self.h, seq, n, fwd.ctypes.data, rc.ctypes.data, valid.ctypes.data))
         return fwd, rc, valid
 
-    def vote_hits(self, hits, off):
+    def vote_hits(self, hits, off, sparse=False):
+        """sparse=True: through the pipeline's hit-map representation (thread -> warp -> block kernels)."""
         hits = np.ascontiguousarray(hits, dtype=np.uint32)
         off = np.ascontiguousarray(off, dtype=np.uint64)
         n = off.size - 1
         res = np.zeros(n, dtype=RESULT_DTYPE)
-        _ck(lib().utb_vote_hits(self.h, hits.ctypes.data, off.ctypes.data, n, res.ctypes.data))
+        fn = lib().utb_vote_hits_sparse if sparse else lib().utb_vote_hits
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        _ck(fn(self.h, hits.ctypes.data, off.ctypes.data, n, res.ctypes.data))
         return res
 
     def hbm_bytes(self):

@@ -106,8 +106,9 @@ __device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &badbits) {
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_off,
             const uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ grp_off,
-            uint32_t n_reads, uint32_t n_groups,
+            uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ n_groups_dev,
             uint64_t *__restrict__ pk, uint32_t *__restrict__ bad) {
+    if (n_groups_dev) n_groups = *n_groups_dev;                    // device-side framing: the host only knows an upper bound
     uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g > n_groups) return;
     if (g == n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; return; }   // guard group
@@ -151,8 +152,8 @@ pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_of
 __device__ __forceinline__ bool window_at(const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
                                           uint32_t pos, uint64_t &w) {
     uint32_t g = pos >> 5, o = pos & 31u;
-    uint64_t hi = __ldg(pk + g), lo = __ldg(pk + g + 1);
-    uint32_t bh = __ldg(bad + g), bl = __ldg(bad + g + 1);
+    uint64_t hi = pk[g], lo = pk[g + 1];                          // const __restrict__ global pointers still compile to LDG.CONSTANT
+    uint32_t bh = bad[g], bl = bad[g + 1];
     uint32_t wb = o ? ((bh >> o) | (bl << (32u - o))) : bh;
     w = o ? ((hi << (2u * o)) | (lo >> (64u - 2u * o))) : hi;
     return wb == 0;
@@ -481,7 +482,8 @@ bloom_build_kernel(DevDB db, uint32_t *__restrict__ bloom) {
 template <int NSTR, bool FAST, bool BLOOM>
 __global__ void __launch_bounds__(256, 6)
 lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
-              uint32_t n_pos, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+              uint32_t n_pos, const uint32_t *__restrict__ n_groups_dev, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
+    if (n_groups_dev) n_pos = *n_groups_dev * 32u;
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
     uint64_t w = 0;
@@ -599,9 +601,11 @@ __device__ __forceinline__ uint32_t filter_emit(const DevDB &db, WarpQueue &wq, 
 template <int NSTR>
 __global__ void __launch_bounds__(256, FILT_MINB)
 filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
+              const uint32_t *__restrict__ n_groups_dev,
               uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
               uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
               uint64_t q_cap, uint32_t *__restrict__ hitmap) {
+    if (n_groups_dev) n_pos = *n_groups_dev * 32u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     WarpQueue wq;
@@ -661,26 +665,58 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
 // scattered, and the output pass gathers through it.  No global atomics; the fill of every region is
 // stored at the end.  Hash partitions are uniform and every CTA sees the same share of the batch, so
 // regions fill evenly (cap_cp carries 25 % head-room; records of an overflowing tile are resolved inline).
-template <int NSTR>
-__global__ void __launch_bounds__(256, 4)
+// MATCH (kept as a measured alternative, UTB_PART_ATOMS=0): the rank of a record inside its partition comes
+// from warp match + a scanned (warp-row x partition) count table instead of one shared-memory atomic per
+// record.  Shared atomics with a return value run at ~2 cycles per LANE on the SM's load/store unit
+// (B300_MICROARCH "ATOMS spread-addr"), but MATCH.ANY over mostly distinct keys plus the table scan cost
+// more: 16.2 ms against 11.5 ms per 10 M reads, so the atomic variant is the default.
+#define P_ROWS (P_TILE / 32u)   // warp-rows of a tile
+#define P_SMEM_MATCH (P_SMEM + P_ROWS * NPART * 2u)
+template <int NSTR, bool MATCH>
+__global__ void __launch_bounds__(256, MATCH ? 3 : 4)
 partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
-                 unsigned long long *__restrict__ counters,
+                 const uint32_t *__restrict__ n_groups_dev, unsigned long long *__restrict__ counters,
                  uint64_t *__restrict__ p_words, uint32_t *__restrict__ p_pos, uint32_t *__restrict__ p_fill,
                  uint32_t cap_cp, uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
     extern __shared__ __align__(16) unsigned char p_smem[];
     uint64_t *s_w = reinterpret_cast<uint64_t *>(p_smem);
     uint32_t *s_ord = reinterpret_cast<uint32_t *>(p_smem + P_TILE * 8u);
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(p_smem + P_SMEM);   // MATCH: [P_ROWS][NPART] group sizes, then their prefix over the rows
+    __shared__ uint32_t s_q[4][NPART];                             // MATCH: per quarter of the rows: total, then base in the sorted order
     __shared__ uint32_t s_hist[NPART], s_start[NPART], s_cur[NPART];
     __shared__ uint64_t s_gbase[NPART];                            // region base + fill - start: global index = s_gbase[part] + sorted rank
     __shared__ uint32_t s_ovf;
+    __shared__ uint64_t s_pk[P_TILE / 32u + 4u];                  // the tile's packed groups (+ the one after)
+    __shared__ uint32_t s_bad[P_TILE / 32u + 4u];
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (n_groups_dev) n_pos = *n_groups_dev * 32u;
+    const uint32_t n_groups = n_pos >> 5;
     if (tid < NPART) s_cur[tid] = 0;
     uint32_t nv = 0, nh = 0;
     const uint64_t region0 = (uint64_t)blockIdx.x * NPART * cap_cp;
+    // The packed stream of a tile is 1.5 KB: it is fetched one tile ahead into registers (the loads complete
+    // under the three passes of the current tile) and parked in shared memory, so no pass waits on DRAM.
+    uint64_t pf_pk = 0;
+    uint32_t pf_bad = 0xFFFFFFFFu;
+    {
+        const uint64_t g = (uint64_t)blockIdx.x * (P_TILE / 32u) + tid;
+        if (tid <= P_TILE / 32u && g <= n_groups) { pf_pk = __ldg(pk + g); pf_bad = __ldg(bad + g); }   // group n_groups is the guard
+    }
     for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_pos; tile += (uint64_t)gridDim.x * P_TILE) {
         if (tid < NPART) s_hist[tid] = 0;
         if (tid == 0) s_ovf = 0;
+        if (tid <= P_TILE / 32u) { s_pk[tid] = pf_pk; s_bad[tid] = pf_bad; }
+        if (MATCH) {
+            uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
+#pragma unroll
+            for (uint32_t i = 0; i < P_ROWS * NPART * 2u / 16u / 256u; ++i) z[i * 256u + tid] = make_uint4(0, 0, 0, 0);
+        }
         __syncthreads();
+        {
+            const uint64_t g = (tile + (uint64_t)gridDim.x * P_TILE) / 32u + tid;
+            pf_pk = 0; pf_bad = 0xFFFFFFFFu;
+            if (tid <= P_TILE / 32u && g <= n_groups) { pf_pk = __ldg(pk + g); pf_bad = __ldg(bad + g); }
+        }
         // pass A: window, partition id and rank inside the tile.  A warp covers 32 consecutive positions = one
         // group of the packed stream, so its pk/bad loads are warp-uniform.
         uint32_t meta[P_PPT];                                      // rank << 6 | part, or 0xFFFFFFFF
@@ -688,17 +724,42 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
 #pragma unroll
         for (uint32_t k = 0; k < P_PPT; ++k) {
             const uint32_t local = k * 256u + tid;
-            const uint64_t pos = tile + local;
             uint64_t w = 0;
             meta[k] = 0xFFFFFFFFu;
-            if (pos < n_pos && window_at(pk, bad, (uint32_t)pos, w)) {
-                const uint32_t part = (uint32_t)(bloom_block_hash(w, revcomp_word(w)) >> 58);
+            const bool valid = window_at(s_pk, s_bad, local, w);   // positions past the batch lie in all-bad groups
+            uint32_t part = 64u + lane;                             // invalid lanes: a key of their own
+            if (valid) part = (uint32_t)(bloom_block_hash(w, revcomp_word(w)) >> 58);
+            if (MATCH) {
+                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, part);
+                const uint32_t lrank = __popc(peers & ((1u << lane) - 1u));
+                if (valid) {
+                    if (lrank == 0) s_cnt[(k * 8u + (tid >> 5)) * NPART + part] = (uint16_t)__popc(peers);
+                    meta[k] = (lrank << 6) | part;
+                    nv += NSTR;
+                }
+            } else if (valid) {
                 meta[k] = (atomicAdd(&s_hist[part], 1u) << 6) | part;
                 nv += NSTR;
             }
             s_w[local] = w;
         }
         __syncthreads();
+        if (MATCH) {
+            // prefix of the group sizes over the warp-rows, per partition: thread = (quarter of the rows, partition)
+            const uint32_t bin = tid & 63u, q = tid >> 6;
+            uint32_t run = 0;
+#pragma unroll 8
+            for (uint32_t i = 0; i < P_ROWS / 4u; ++i) {
+                uint16_t *c = s_cnt + (q * (P_ROWS / 4u) + i) * NPART + bin;
+                const uint32_t v = *c;
+                *c = (uint16_t)run;
+                run += v;
+            }
+            s_q[q][bin] = run;
+            __syncthreads();
+            if (tid < NPART) s_hist[tid] = s_q[0][tid] + s_q[1][tid] + s_q[2][tid] + s_q[3][tid];
+            __syncthreads();
+        }
         if (tid < 32) {                                            // exclusive scan of the 64 bins by one warp
             const uint32_t h0 = s_hist[2 * tid], h1 = s_hist[2 * tid + 1];
             uint32_t x = h0 + h1;
@@ -708,6 +769,14 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
             s_gbase[2 * tid] = region0 + (uint64_t)(2 * tid) * cap_cp + c0 - st0;
             s_gbase[2 * tid + 1] = region0 + (uint64_t)(2 * tid + 1) * cap_cp + c1 - st1;
             if (c0 + h0 > cap_cp || c1 + h1 > cap_cp) s_ovf = 1;
+            if (MATCH) {                                            // quarter totals -> bases in the sorted order
+#pragma unroll
+                for (uint32_t b2 = 0; b2 < 2; ++b2) {
+                    uint32_t base = b2 ? st1 : st0;
+#pragma unroll
+                    for (uint32_t q = 0; q < 4; ++q) { const uint32_t t = s_q[q][2 * tid + b2]; s_q[q][2 * tid + b2] = base; base += t; }
+                }
+            }
         }
         __syncthreads();
         // pass B: the sorted order (4 bytes per record scattered; the words stay where they are)
@@ -716,7 +785,10 @@ partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__re
             const uint32_t m = meta[k];
             if (m == 0xFFFFFFFFu) continue;
             const uint32_t part = m & 63u;
-            s_ord[s_start[part] + (m >> 6)] = (k * 256u + tid) | (part << 16);
+            uint32_t dst;
+            if (MATCH) { const uint32_t row = k * 8u + (tid >> 5); dst = s_q[row / (P_ROWS / 4u)][part] + s_cnt[row * NPART + part] + (m >> 6); }
+            else dst = s_start[part] + (m >> 6);
+            s_ord[dst] = (k * 256u + tid) | (part << 16);
         }
         __syncthreads();
         // pass C: contiguous runs out to the regions
@@ -784,15 +856,15 @@ probe_kernel(DevDB db, const uint64_t *__restrict__ p_words, const uint32_t *__r
             const uint32_t fill = __ldg(p_fill + c * NPART + part);
             const uint64_t base = ((uint64_t)c * NPART + part) * cap_cp;   // even: cap_cp is even
             const uint32_t j1 = min(fill, (sub + 1) * P_SUB);
+            // the records of step i+1 are requested before step i is probed (two DRAM round trips overlap)
+            ulonglong2 nxt = make_ulonglong2(0, 0);
+            if (sub * P_SUB + 2u * lane < j1) nxt = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + sub * P_SUB + 2u * lane));
             for (uint32_t j0 = sub * P_SUB; j0 < j1; j0 += 64) {
                 const uint32_t j = j0 + 2u * lane;
-                uint64_t w[2] = {0, 0}, rc[2], hc[2];
+                uint64_t w[2] = {nxt.x, nxt.y}, rc[2], hc[2];
                 uint4 v[2];
                 bool live[2] = {j < j1, j + 1u < j1};
-                if (live[0]) {                                     // j + 1 < cap_cp always: one aligned 16-byte load
-                    const ulonglong2 t = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + j));
-                    w[0] = t.x; w[1] = t.y;
-                }
+                if (j + 64u < j1) nxt = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + j + 64u));   // j + 1 < cap_cp always: aligned 16-byte loads
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     rc[u] = revcomp_word(w[u]);
@@ -981,15 +1053,11 @@ __device__ __forceinline__ void vote_range(const VoteIn &in, uint32_t r, uint64_
 // (warp-aggregated with match_any), sorted by label rank, then the walk.
 // Reads that are too long or have too many distinct labels are queued for
 // vote_block_kernel.
-__global__ void __launch_bounds__(VW_WARPS * 32)
-vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__ results,
-                 uint32_t *__restrict__ gen_list, uint32_t *__restrict__ gen_count,
-                 unsigned long long *__restrict__ counters) {
-    __shared__ uint32_t s_key[VW_WARPS][VW_SLOTS], s_cnt[VW_WARPS][VW_SLOTS];
-    __shared__ uint32_t s_rk[VW_WARPS][VW_SLOTS], s_lab[VW_WARPS][VW_SLOTS], s_tc[VW_WARPS][VW_SLOTS];
-    const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * VW_WARPS + wib;
-    if (r >= n_reads) return;
+struct VoteWarpSmem { uint32_t *key, *cnt, *rk, *lab, *tc; };
+__device__ void vote_warp_read(const DevDB &db, const VoteIn &in, uint32_t r, utb_result *__restrict__ results,
+                               uint32_t *__restrict__ gen_list, uint32_t *__restrict__ gen_count,
+                               unsigned long long *__restrict__ counters, const VoteWarpSmem &sm) {
+    const uint32_t lane = threadIdx.x & 31u;
     uint64_t start, count;
     vote_range(in, r, start, count);
     utb_result *out = results + r;
@@ -997,7 +1065,7 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
         if (lane == 0) gen_list[atomicAdd(gen_count, 1u)] = r;
         return;
     }
-    uint32_t *key = s_key[wib], *cnt = s_cnt[wib];
+    uint32_t *key = sm.key, *cnt = sm.cnt;
     key[lane] = UTB_BAD32; key[lane + 32] = UTB_BAD32;
     cnt[lane] = 0; cnt[lane + 32] = 0;
     __syncwarp();
@@ -1089,7 +1157,7 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
     }
     // sort the entries by label rank (strcmp order, itree.c:1041): compact the occupied slots first -- a read
     // typically holds 2-3 labels, so ranking costs uix compares per entry instead of a sweep over all 64 slots
-    uint32_t *rk = s_rk[wib], *T_lab = s_lab[wib], *T_cnt = s_tc[wib];
+    uint32_t *rk = sm.rk, *T_lab = sm.lab, *T_cnt = sm.tc;
     const uint32_t r0 = k0 != UTB_BAD32 ? __ldg(db.rank + k0) : UTB_BAD32;
     const uint32_t r1 = k1 != UTB_BAD32 ? __ldg(db.rank + k1) : UTB_BAD32;
     const uint32_t lt = (1u << lane) - 1u;
@@ -1103,6 +1171,145 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__
     if (k1 != UTB_BAD32) { T_lab[p1] = k1; T_cnt[p1] = cnt[lane + 32]; }
     __syncwarp();
     walk_warp(db, T_lab, T_cnt, uix, n, out);
+}
+// Persistent over `list` (reads deferred by vote_thread_kernel), or over all reads when list is null.
+__global__ void __launch_bounds__(VW_WARPS * 32)
+vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_count,
+                 utb_result *__restrict__ results, uint32_t *__restrict__ gen_list, uint32_t *__restrict__ gen_count,
+                 unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_key[VW_WARPS][VW_SLOTS], s_cnt[VW_WARPS][VW_SLOTS];
+    __shared__ uint32_t s_rk[VW_WARPS][VW_SLOTS], s_lab[VW_WARPS][VW_SLOTS], s_tc[VW_WARPS][VW_SLOTS];
+    const uint32_t wib = threadIdx.x >> 5;
+    const VoteWarpSmem sm = {s_key[wib], s_cnt[wib], s_rk[wib], s_lab[wib], s_tc[wib]};
+    const uint32_t total = list ? *list_count : n_reads;
+    for (uint32_t i = blockIdx.x * VW_WARPS + wib; i < total; i += gridDim.x * VW_WARPS) {
+        vote_warp_read(db, in, list ? list[i] : i, results, gen_list, gen_count, counters, sm);
+        __syncwarp();
+    }
+}
+
+// ---- thread per read (the common case) ----------------------------------------------
+// A 150-base read owns 10 words of the hit map and holds a handful of hits on 1-3 distinct labels;
+// a warp per read spends ~800 issue slots on it, almost all of them with one useful lane (the
+// aufbau walk compares two label strings character by character).  Here every lane walks its own
+// read: hit map words -> flagged slots -> (label, count) pairs kept sorted by label rank in
+// registers -> the same walk as walk_warp, scalar.  Reads with more than VT_K distinct labels or
+// more than VT_MAXWORDS hit-map words are deferred to vote_warp_kernel through `list`.
+#define VT_K 6u
+#define VT_THREADS 128
+#define VT_MAXWORDS 64u
+__device__ __forceinline__ void walk_thread(const DevDB &db, const uint32_t *T_lab, const uint32_t *T_cnt,   // [k * VT_THREADS]
+                                            uint32_t uix, uint32_t n, utb_result *out) {
+#define TL(z) T_lab[(z) * VT_THREADS]
+#define TC(z) T_cnt[(z) * VT_THREADS]
+    const uint32_t EMPTY = 0xFFFFFFFFu;
+    uint32_t cutoff = cutoff_of(n), st = 0, ed = uix, dv = EMPTY, orun = n, sl = 0, ol = 0;
+    for (;;) {                                                      // itree.c:1047
+        uint32_t run = TC(st), td = dv;
+        for (uint32_t z = st + 1; z < ed; ++z) {                    // itree.c:1050
+            const char *s1 = db.blob + __ldg(db.off + TL(z - 1));
+            const char *s2 = db.blob + __ldg(db.off + TL(z));
+            if (!s1[dv + (dv == EMPTY)]) {                          // itree.c:1052
+                run = TC(z); st = z;
+                orun -= TC(z - 1);
+                cutoff = cutoff_of(orun);
+                continue;
+            }
+            // itree.c:1060-1061: first td >= dv+1 with s1[td]==0 || s1[td]!=s2[td] || s1[td]==';'
+            uint32_t t = dv + 1u;
+            char a, b;
+            for (;; ++t) { a = s1[t]; b = s2[t]; if (a == 0 || a != b || a == ';') break; }
+            td = t;
+            if (a == b) run += TC(z);                               // itree.c:1062
+            else if ((!a && b == ';') ||
+                     ((a == ';' || !a) && td > 0 && s1[td - 1] == '_')) {   // itree.c:1063
+                run = TC(z); st = z;
+                orun -= TC(z - 1);
+                cutoff = cutoff_of(orun);
+            }
+            else if (run >= cutoff) { ed = z; break; }              // itree.c:1068
+            else { run = TC(z); st = z; }                           // itree.c:1069
+        }
+        sl = run; ol = orun;                                        // itree.c:1071
+        if (run < cutoff) break;                                    // itree.c:1072
+        if (st + 1 >= ed) {                                         // itree.c:1073-1080
+            if (TC(ed - 1) >= cutoff) dv = 0xFFFFFFFEu;
+            break;
+        }
+        orun = run; dv = td; cutoff = cutoff_of(run);               // itree.c:1082-1085
+    }
+    out->kind = UTB_WALK; out->label = TL(ed - 1); out->cut = dv;
+    out->found = n; out->uix = uix; out->sl = sl; out->ol = ol; out->_pad = 0;
+#undef TL
+#undef TC
+}
+__global__ void __launch_bounds__(VT_THREADS)
+vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__ results,
+                   uint32_t *__restrict__ list, uint32_t *__restrict__ list_count, unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_lab[VT_K * VT_THREADS], s_cnt[VT_K * VT_THREADS];
+    __shared__ uint32_t s_good;
+    const uint32_t tid = threadIdx.x, r = blockIdx.x * VT_THREADS + tid;
+    if (tid == 0) s_good = 0;
+    __syncthreads();
+    if (r < n_reads) {
+        uint64_t start, count;
+        vote_range(in, r, start, count);
+        const uint32_t nwords = (uint32_t)((count + 31) >> 5);
+        bool defer = nwords > VT_MAXWORDS;
+        uint32_t lab[VT_K], cnt[VT_K], n = 0, uix = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < VT_K; ++k) { lab[k] = UTB_BAD32; cnt[k] = 0; }
+        if (!defer) {
+            const uint32_t *hm = in.hitmap + (start >> 5);         // start is a multiple of 32 in batch mode
+            for (uint32_t w = 0; w < nwords && !defer; ++w) {
+                uint32_t m = __ldg(hm + w);
+                if (w == nwords - 1 && (count & 31u)) m &= (1u << (count & 31u)) - 1u;
+                while (m) {
+                    const uint32_t bit = __ffs(m) - 1; m &= m - 1;
+                    const uint32_t h = __ldg(in.hits + start + 32ull * w + bit);
+                    if (h >= db.max_ix) continue;
+                    ++n;
+                    bool seen = false;
+#pragma unroll
+                    for (uint32_t k = 0; k < VT_K; ++k) if (lab[k] == h) { ++cnt[k]; seen = true; }
+                    if (!seen) {
+                        if (uix == VT_K) { defer = true; break; }
+#pragma unroll
+                        for (uint32_t k = 0; k < VT_K; ++k) if (k == uix) { lab[k] = h; cnt[k] = 1; }
+                        ++uix;
+                    }
+                }
+            }
+        }
+        utb_result *out = results + r;
+        if (defer) list[atomicAdd(list_count, 1u)] = r;
+        else if (n == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        else {
+            atomicAdd(&s_good, 1u);                                 // good finds (itree.c:1029)
+            if (uix == 1) {                                         // itree.c:1031-1032, 1039-1040
+                out->kind = UTB_STAR; out->label = lab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0;
+            } else {
+                // sort by label rank (strcmp order, itree.c:1041): insertion sort over at most VT_K entries
+                uint32_t rk[VT_K];
+#pragma unroll
+                for (uint32_t k = 0; k < VT_K; ++k) rk[k] = k < uix ? __ldg(db.rank + lab[k]) : UTB_BAD32;
+#pragma unroll
+                for (uint32_t i = 1; i < VT_K; ++i)
+#pragma unroll
+                    for (uint32_t j = i; j > 0; --j)
+                        if (rk[j] < rk[j - 1]) {
+                            uint32_t t = rk[j]; rk[j] = rk[j - 1]; rk[j - 1] = t;
+                            t = lab[j]; lab[j] = lab[j - 1]; lab[j - 1] = t;
+                            t = cnt[j]; cnt[j] = cnt[j - 1]; cnt[j - 1] = t;
+                        }
+#pragma unroll
+                for (uint32_t k = 0; k < VT_K; ++k) { s_lab[k * VT_THREADS + tid] = lab[k]; s_cnt[k * VT_THREADS + tid] = cnt[k]; }
+                walk_thread(db, s_lab + tid, s_cnt + tid, uix, n, out);
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0 && s_good) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)s_good);
 }
 
 // Block per read for long queries / label-rich reads: global-memory histogram
@@ -1290,6 +1497,92 @@ slots_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, uint32_t *__restr
     uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) slots[r] = (seq_len[r] + 1u + 31u) / 32u;           // utb_read_slots
 }
+// ---- device-side framing ---------------------------------------------
+// The host only counts the newlines of a chunk (which fixes the number of complete
+// records and where the last one ends, itree.c:869-871: lines are read strictly in
+// pairs); everything per read -- where its header and sequence lines start, the name
+// (itree.c:879-882), the CR/LF trimming (itree.c:889-890) and the format checks
+// (itree.c:880, 886) -- happens here, on the bytes that were copied to the device
+// anyway.  Three kernels: newline count per 16 KB block, exclusive scan of the block
+// counts (scan_top_kernel), newline positions + record parse.
+#define FR_BPT 64u              // bytes per thread
+#define FR_BLOCK (256u * FR_BPT)
+#define FR_ERR_NONE 0xFFFFFFFFu
+enum { FRE_NOHEADER = 1, FRE_SEQ_GT = 2, FRE_TOOLONG = 4 };   // codes as in pipeline.c (FE_*)
+// bit j of the result: byte j of the 64 bytes at p is '\n' (bytes at or beyond n_bytes never match)
+__device__ __forceinline__ uint64_t nl_mask64(const uint8_t *__restrict__ raw, uint64_t at, uint64_t n_bytes) {
+    uint64_t m = 0;
+    if (at >= n_bytes) return 0;
+    const uint4 *p = reinterpret_cast<const uint4 *>(raw + at);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(p + q);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t e = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x01010101u;
+            m |= (uint64_t)((e * 0x01020408u) >> 24) << (16 * q + 4 * k);
+        }
+    }
+    const uint64_t left = n_bytes - at;
+    if (left < 64) m &= (1ull << left) - 1ull;
+    return m;
+}
+__global__ void __launch_bounds__(256)
+nl_count_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, uint32_t *__restrict__ blk_cnt) {
+    __shared__ uint32_t sh[8];
+    const uint64_t at = ((uint64_t)blockIdx.x * 256u + threadIdx.x) * FR_BPT;
+    uint32_t c = __popcll(nl_mask64(raw, at, n_bytes));
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += sh[w]; blk_cnt[blockIdx.x] = t; }
+}
+// blk_off: exclusive scan of blk_cnt.  nl[i] = position of newline i, for i < limit.
+__global__ void __launch_bounds__(256)
+nl_index_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, const uint32_t *__restrict__ blk_off,
+                uint32_t limit, uint32_t *__restrict__ nl) {
+    __shared__ uint32_t sh[8];
+    const uint64_t at = ((uint64_t)blockIdx.x * 256u + threadIdx.x) * FR_BPT;
+    uint64_t m = nl_mask64(raw, at, n_bytes);
+    const uint32_t c = __popcll(m), lane = threadIdx.x & 31u;
+    uint32_t x = c;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if (lane >= (uint32_t)o) x += t; }
+    if (lane == 31) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    uint32_t i = blk_off[blockIdx.x] + x - c;
+    for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) i += sh[w];
+    while (m && i < limit) {
+        nl[i++] = (uint32_t)(at + (uint32_t)(__ffsll((long long)m) - 1));
+        m &= m - 1;
+    }
+}
+// One thread per record r: header line = (nl[2r-1], nl[2r]], sequence line = (nl[2r], nl[2r+1]].
+// The first malformed record (smallest r) is reported in *err as r << 3 | code; the host then
+// re-frames from this batch on with its own exact reader, which reproduces the reference's message
+// and partial output.
+__global__ void __launch_bounds__(256)
+frame_parse_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ nl, uint32_t n_reads,
+                   uint64_t *__restrict__ seq_off, uint32_t *__restrict__ seq_len,
+                   uint32_t *__restrict__ name_off, uint32_t *__restrict__ name_len,
+                   uint32_t *__restrict__ slots, uint32_t *__restrict__ err) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const uint32_t hs = r ? nl[2 * r - 1] + 1u : 0u, hn = nl[2 * r], ss = hn + 1u, sn = nl[2 * r + 1];
+    uint32_t code = 0;
+    if (ss - hs >= UTB_LINELEN || sn + 1u - ss >= UTB_LINELEN) code = FRE_TOOLONG;
+    else if (raw[hs] != '>') code = FRE_NOHEADER;                  // itree.c:880
+    else if (raw[ss] == '>') code = FRE_SEQ_GT;                    // itree.c:886
+    if (code) atomicMin(err, (r << 3) | code);
+    uint32_t length = sn - ss;
+    if (length && raw[ss + length - 1] == '\r') --length;          // itree.c:890
+    uint32_t e = hs + 1u;                                          // name: up to the first ' ' or the newline (itree.c:881)
+    while (e < hn && raw[e] != ' ') ++e;
+    seq_off[r] = ss; seq_len[r] = length;
+    name_off[r] = hs + 1u; name_len[r] = e - hs - 1u;
+    slots[r] = (length + 1u + 31u) / 32u;                          // utb_read_slots
+}
+
 #define FW_WARPS 8
 __global__ void __launch_bounds__(FW_WARPS * 32)
 fmt_write_kernel(DevDB db, const utb_result *__restrict__ res, const uint8_t *__restrict__ raw,
@@ -1557,7 +1850,7 @@ struct utb_batch {
     // device
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
     uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
-    utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count;
+    utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count; uint32_t *d_warp_list; uint32_t *d_warp_count;
     uint32_t *d_name_off, *d_name_len, *d_line_len, *d_line_off, *d_scan_sums, *d_text_len; char *d_text;
     int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
@@ -1568,6 +1861,8 @@ struct utb_batch {
     // last submit
     size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom; int used_partition;
     uint64_t launches;
+    // device-side framing
+    uint32_t *d_nl, *d_blk, *d_frame_err, *d_ngroups, *h_frame_err; const uint32_t *ngroups_dev; int framed_on_device;
 };
 
 extern "C" uint64_t utb_read_slots(uint32_t len) { return ((uint64_t)len + 1 + 31) / 32; }
@@ -1590,10 +1885,11 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     if (b->text_len_ready) cudaEventDestroy(b->text_len_ready);
     cudaFree(b->d_raw); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_grp_off);
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
-    cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_counters);
+    cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_warp_list); cudaFree(b->d_warp_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_pwords); cudaFree(b->d_ppos); cudaFree(b->d_pfill); cudaFree(b->d_pctr);
+    cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFree(b->d_ngroups); cudaFreeHost(b->h_frame_err);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 7; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -1644,6 +1940,8 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_results, max_reads * sizeof(utb_result)));
     BK(cudaMalloc(&b->d_gen_list, max_reads * 4));
     BK(cudaMalloc(&b->d_gen_count, 4));
+    BK(cudaMalloc(&b->d_warp_list, max_reads * 4));
+    BK(cudaMalloc(&b->d_warp_count, 4));
     BK(cudaMalloc(&b->d_counters, 4 * COUNTER_SLOTS * 8));
     BK(cudaMalloc(&b->d_hist, (size_t)VB_BLOCKS * nl * 4));
     BK(cudaMalloc(&b->d_tlab, (size_t)VB_BLOCKS * nl * 4));
@@ -1696,7 +1994,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
         pack_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
-                                                                   n_reads, n_groups, b->d_pk, b->d_bad);
+                                                                   n_reads, n_groups, b->ngroups_dev, b->d_pk, b->d_bad);
         b->launches++;
     }
     if (timed) CK(cudaEventRecord(b->ev[1], b->st));
@@ -1718,13 +2016,15 @@ static int launch_stages(utb_batch *b, bool timed) {
                 const unsigned tiles = (unsigned)(((uint64_t)n_pos + P_TILE - 1) / P_TILE);
                 const unsigned gb = tiles < P_CTAS ? tiles : P_CTAS;
                 uint32_t cap_cp = ((uint32_t)((double)n_pos / ((double)gb * NPART) * 1.25) + 66u) & ~1u;   // even; <= p_total / (gb * NPART)
-                if (nstr == 2) {
-                    CK(cudaFuncSetAttribute(partition_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                    partition_kernel<2><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
-                } else {
-                    CK(cudaFuncSetAttribute(partition_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                    partition_kernel<1><<<gb, 256, P_SMEM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap);
-                }
+                // measured on B200 (10 M reads): atomic ranks 11.5 ms, match ranks 16.2 ms -> atomics by default
+                const char *pa = getenv("UTB_PART_ATOMS");                  // tests: 0 selects the match-ranked variant
+                const int part_atoms = !(pa && atoi(pa) == 0);
+#define LAUNCH_PART(NS, M, SM) do { \
+                    CK(cudaFuncSetAttribute(partition_kernel<NS, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
+                    partition_kernel<NS, M><<<gb, 256, SM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap); } while (0)
+                if (nstr == 2) { if (part_atoms) LAUNCH_PART(2, false, P_SMEM); else LAUNCH_PART(2, true, P_SMEM_MATCH); }
+                else { if (part_atoms) LAUNCH_PART(1, false, P_SMEM); else LAUNCH_PART(1, true, P_SMEM_MATCH); }
+#undef LAUNCH_PART
                 if (timed) CK(cudaEventRecord(b->ev[6], b->st));
                 b->used_partition = 1;
                 CK(cudaMemsetAsync(b->d_pctr, 0, NPART * 4, b->st));
@@ -1739,17 +2039,17 @@ static int launch_stages(utb_batch *b, bool timed) {
                                 &b->d_qcount, &b->q_cap, &b->d_hits, &b->d_hitmap, &b->d_counters};
                 CK(cudaLaunchCooperativeKernel(pk_fn, dim3(pgrid), dim3(256), args, 0, b->st));
                 b->launches++;
-            } else if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            } else if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
             queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
             b->launches++;
         } else if (b->db->use_interp) {
-            if (nstr == 2) lookup_kernel<2, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
-            else lookup_kernel<1, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+            if (nstr == 2) lookup_kernel<2, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
+            else lookup_kernel<1, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
         } else {
-            if (nstr == 2) lookup_kernel<2, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
-            else lookup_kernel<1, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->d_hits, b->d_counters);
+            if (nstr == 2) lookup_kernel<2, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
+            else lookup_kernel<1, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
         }
         b->launches++;
     }
@@ -1758,8 +2058,18 @@ static int launch_stages(utb_batch *b, bool timed) {
         VoteIn in;
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
         in.hitmap = b->used_bloom ? b->d_hitmap : nullptr;
-        vote_warp_kernel<<<(n_reads + VW_WARPS - 1) / VW_WARPS, VW_WARPS * 32, 0, b->st>>>(
-            d, in, n_reads, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
+        if (in.hitmap) {
+            // thread per read for the common case; label-rich or long reads fall through to the warp kernel
+            // (and from there to the block kernel) by way of device-side lists
+            CK(cudaMemsetAsync(b->d_warp_count, 0, 4, b->st));
+            vote_thread_kernel<<<(n_reads + VT_THREADS - 1) / VT_THREADS, VT_THREADS, 0, b->st>>>(
+                d, in, n_reads, b->d_results, b->d_warp_list, b->d_warp_count, b->d_counters);
+            vote_warp_kernel<<<148 * 6, VW_WARPS * 32, 0, b->st>>>(
+                d, in, n_reads, b->d_warp_list, b->d_warp_count, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
+            b->launches++;
+        } else
+            vote_warp_kernel<<<(n_reads + VW_WARPS - 1) / VW_WARPS, VW_WARPS * 32, 0, b->st>>>(
+                d, in, n_reads, nullptr, nullptr, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
         vote_block_kernel<<<VB_BLOCKS, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
                                                                b->d_hist, b->d_tlab, b->d_tcnt, b->d_counters);
         b->launches += 2;
@@ -1781,6 +2091,7 @@ static int ensure_text_buffers(utb_batch *b) {
 }
 
 static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
+static int finish_submit(utb_batch *b);
 extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
     return submit_impl(b, nullptr, n_bytes, n_reads, do_rc, 0, 0);
 }
@@ -1818,7 +2129,7 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
     if (g > b->max_groups) { utb_set_error("utb_batch_submit: %llu position groups exceed capacity %llu", (unsigned long long)g, (unsigned long long)b->max_groups); return UTB_ERR_LIMIT; }
     if (!total_groups) b->h_grp_off[n_reads] = (uint32_t)g;
     b->n_reads = n_reads; b->n_groups = (uint32_t)g; b->do_rc = do_rc ? 1 : 0;
-    b->want_text = want_text;
+    b->want_text = want_text; b->ngroups_dev = nullptr; b->framed_on_device = 0;
     if (want_text) {
         int rt = ensure_text_buffers(b);
         if (rt) return rt;
@@ -1841,6 +2152,13 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
             b->launches += 4;
         }
     }
+    return finish_submit(b);
+}
+
+// device stages + (text | result records) + counters back to the host, all on the batch's stream
+static int finish_submit(utb_batch *b) {
+    const size_t n_reads = b->n_reads;
+    const int want_text = b->want_text;
     int rc = launch_stages(b, true);
     if (rc) return rc;
     if (want_text) {
@@ -1870,6 +2188,55 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
     CK(cudaEventRecord(b->done, b->st));
     b->in_flight = 1;
     return UTB_OK;
+}
+
+// Raw submit (pipeline-internal): the first n_bytes of `src` (pinned host memory, or NULL for the batch's own
+// staging) hold exactly n_reads complete records = 2 * n_reads lines, each ended by '\n', and no NUL byte
+// (the host counted the newlines; that is all it looked at).  The records are framed on the device and the
+// output text is built there.  utb_batch_frame_error() tells after the wait whether a record was malformed.
+extern "C" int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc) {
+    if (!b || !n_reads || !n_bytes) { utb_set_error("utb_batch_submit_raw: bad argument"); return UTB_ERR_ARG; }
+    if (n_bytes > b->max_bytes || n_reads > b->max_reads) { utb_set_error("utb_batch_submit_raw: batch over capacity"); return UTB_ERR_LIMIT; }
+    CK(cudaSetDevice(b->db->device));
+    if (!b->d_nl) {
+        CK(cudaMalloc(&b->d_nl, (2 * b->max_reads + 2) * 4));
+        CK(cudaMalloc(&b->d_blk, (b->max_bytes / FR_BLOCK + 2) * 4));
+        CK(cudaMalloc(&b->d_frame_err, 4));
+        CK(cudaMalloc(&b->d_ngroups, 4));
+        CK(cudaMallocHost(&b->h_frame_err, 4));
+    }
+    int rt = ensure_text_buffers(b);
+    if (rt) return rt;
+    // every read owns ceil((len+1)/32) <= len/32 + 1 groups and its two lines hold at least 2 more bytes than its bases
+    uint64_t g_ub = (n_bytes - 2 * n_reads) / 32 + n_reads + 1;
+    if (n_bytes < 2 * n_reads || g_ub > b->max_groups) g_ub = b->max_groups;
+    b->n_reads = n_reads; b->n_groups = (uint32_t)g_ub; b->do_rc = do_rc ? 1 : 0;
+    b->want_text = 1; b->ngroups_dev = b->d_ngroups; b->framed_on_device = 1;
+    *b->h_frame_err = FR_ERR_NONE;
+    CK(cudaMemcpyAsync(b->d_raw, src ? src : b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
+    CK(cudaMemsetAsync(b->d_frame_err, 0xFF, 4, b->st));
+    const uint32_t n = (uint32_t)n_reads, fb = (uint32_t)((n_bytes + FR_BLOCK - 1) / FR_BLOCK), nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    nl_count_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk);
+    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_blk, fb, b->d_ngroups);          // total newlines (scratch use of the scalar)
+    nl_index_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, 2 * n, b->d_nl);
+    frame_parse_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_nl, n, b->d_seq_off, b->d_seq_len, b->d_name_off, b->d_name_len,
+                                                          b->d_line_len, b->d_frame_err);
+    // grp_off = exclusive scan of the per-read group counts; the total stays on the device
+    scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
+    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_ngroups);
+    scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_grp_off);
+    b->launches += 7;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(b->h_frame_err, b->d_frame_err, 4, cudaMemcpyDeviceToHost, b->st));
+    return finish_submit(b);
+}
+// After the wait of a raw submit: 0 if every record was well formed, else 1 with the index of the first
+// malformed record of the batch and its FE_* code (1 no header '>', 2 sequence begins '>', 4 line too long).
+extern "C" int utb_batch_frame_error(const utb_batch *b, size_t *record, int *code) {
+    if (!b || !b->framed_on_device || !b->h_frame_err || *b->h_frame_err == FR_ERR_NONE) return 0;
+    if (record) *record = *b->h_frame_err >> 3;
+    if (code) *code = (int)(*b->h_frame_err & 7u);
+    return 1;
 }
 
 extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
@@ -2010,7 +2377,7 @@ extern "C" int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len, uint
     CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_len, &len, 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_grp, grp, 8, cudaMemcpyHostToDevice));
-    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, d_pk, d_bad);
+    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad);
     expand_windows_kernel<<<(n_pos + 255) / 256, 256>>>(d_pk, d_bad, n_pos, d_f, d_r, d_v);
     CK(cudaGetLastError());
     CK(cudaMemcpy(fwd, d_f, (size_t)len * 8, cudaMemcpyDeviceToHost));
@@ -2035,12 +2402,56 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = nullptr;
-    vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, d_res, d_gl, d_gc, d_cnt);
+    vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, nullptr, d_res, d_gl, d_gc, d_cnt);
     vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
     CK(cudaGetLastError());
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
     cudaFree(d_hits); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_cnt);
     cudaFree(d_hist); cudaFree(d_tl); cudaFree(d_tc);
+    return UTB_OK;
+}
+
+// Same vote through the sparse representation the batch pipeline uses: every read's slots start at a
+// multiple of 32, a 1-bit-per-slot hit map flags the labels, and the reads go thread kernel -> warp
+// kernel -> block kernel by way of the device-side deferral lists.
+extern "C" int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint64_t *off, size_t n_reads, utb_result *results) {
+    if (!db || !off || !results || (!hits && n_reads && off[n_reads])) { utb_set_error("utb_vote_hits_sparse: null argument"); return UTB_ERR_ARG; }
+    if (!n_reads) return UTB_OK;
+    CK(cudaSetDevice(db->device));
+    uint64_t *poff = (uint64_t *)malloc((n_reads + 1) * 8);
+    if (!poff) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    uint64_t tot = 0;
+    for (size_t r = 0; r < n_reads; ++r) { poff[r] = tot; tot += (off[r + 1] - off[r] + 31) / 32 * 32; }
+    poff[n_reads] = tot;
+    uint32_t *ph = (uint32_t *)malloc((tot + 32) * 4), *pm = (uint32_t *)calloc(tot / 32 + 2, 4);
+    if (!ph || !pm) { free(poff); free(ph); free(pm); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    for (uint64_t i = 0; i < tot + 32; ++i) ph[i] = HIT_MISS;
+    for (size_t r = 0; r < n_reads; ++r)
+        for (uint64_t i = 0; i < off[r + 1] - off[r]; ++i) {
+            const uint32_t h = hits[off[r] + i];
+            ph[poff[r] + i] = h;
+            if (h < HIT_NOWIN) pm[(poff[r] + i) >> 5] |= 1u << ((poff[r] + i) & 31u);
+        }
+    const size_t nl = db->d.max_ix ? db->d.max_ix : 1;
+    uint32_t *d_hits, *d_map, *d_gl, *d_gc, *d_wl, *d_wc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
+    CK(cudaMalloc(&d_hits, (tot + 32) * 4)); CK(cudaMalloc(&d_map, (tot / 32 + 2) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
+    CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
+    CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_wl, n_reads * 4)); CK(cudaMalloc(&d_wc, 4));
+    CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
+    CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
+    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
+    CK(cudaMemcpy(d_hits, ph, (tot + 32) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_map, pm, (tot / 32 + 2) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off, poff, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    free(poff); free(ph); free(pm);
+    VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = d_map;
+    vote_thread_kernel<<<(unsigned)((n_reads + VT_THREADS - 1) / VT_THREADS), VT_THREADS>>>(db->d, in, (uint32_t)n_reads, d_res, d_wl, d_wc, d_cnt);
+    vote_warp_kernel<<<148 * 6, VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, d_wl, d_wc, d_res, d_gl, d_gc, d_cnt);
+    vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
+    cudaFree(d_hits); cudaFree(d_map); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_wl); cudaFree(d_wc);
+    cudaFree(d_cnt); cudaFree(d_hist); cudaFree(d_tl); cudaFree(d_tc);
     return UTB_OK;
 }
 

@@ -37,10 +37,12 @@ int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_reads, int do_r
 int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
 int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
+int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc);
+int utb_batch_frame_error(const utb_batch *b, size_t *record, int *code);
 
-#define SLOTS_PER_DEVICE 3
+#define SLOTS_PER_DEVICE 6                         /* measured on B200: 3 slots 89 ms, 4 slots 78 ms, 6 slots 71 ms per 10 M reads */
 #define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* large enough for the device's partitioned lookup pass on the full-size batches */
-#define RAMP_BYTES ((size_t)64 << 20)              /* first / last batches: small, so the pipeline fills and drains fast */
+#define RAMP_BYTES ((size_t)32 << 20)              /* first / last batches: small, so the pipeline fills and drains fast */
 #define MAX_TEAM 64
 
 /* ---- thread team: leader + helpers, fork/join with barriers ----------------- */
@@ -104,6 +106,7 @@ typedef struct {
     size_t n_bytes, n_reads;
     uint32_t *name_off, *name_len;
     uint64_t first_read;           /* global index of the slot's first read */
+    uint64_t src_off;              /* offset in the input stream of the batch's first byte */
     const char *host_bytes;        /* where this batch's raw bytes live on the host (staging, or the caller's pinned buffer) */
     int state;                     /* 0 free, 1 submitted */
 } slot_t;
@@ -116,10 +119,11 @@ struct utb_searcher {
     int n_slots;
     slot_t *slots;
     int host_threads;
-    size_t batch_bytes, batch_reads;
+    size_t batch_bytes, batch_reads, ramp_bytes;
     size_t max_label;              /* longest label incl. NUL */
     int verbose;                   /* CLI: progress lines on stdout */
     int device_format;             /* output lines built on the GPU (default) or by the host formatter team */
+    int device_frame;              /* records framed on the GPU (default with device_format): the host only counts newlines */
 };
 
 static double now_s(void) {
@@ -141,13 +145,19 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->batch_reads = s->batch_bytes / 64;
     e = getenv("UTB_HOST_FORMAT");
     s->device_format = !(e && atoi(e) != 0);
+    e = getenv("UTB_HOST_FRAME");
+    s->device_frame = s->device_format && !(e && atoi(e) != 0);
     for (uint32_t i = 0; i < ctr->max_ix; ++i) {
         size_t l = ctr->off[i + 1] - ctr->off[i];
         if (l > s->max_label) s->max_label = l;
     }
     s->devices = (int *)malloc(sizeof(int) * (size_t)n_devices);
     s->dbs = (utb_db **)calloc((size_t)n_devices, sizeof(utb_db *));
-    s->n_slots = n_devices * SLOTS_PER_DEVICE;
+    e = getenv("UTB_SLOTS");                                       /* stream slots per device (tuning) */
+    int spd = e && atoi(e) >= 2 && atoi(e) <= 8 ? atoi(e) : SLOTS_PER_DEVICE;
+    s->n_slots = n_devices * spd;
+    e = getenv("UTB_RAMP_MB");
+    s->ramp_bytes = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : RAMP_BYTES;
     s->slots = (slot_t *)calloc((size_t)s->n_slots, sizeof(slot_t));
     if (!s->devices || !s->dbs || !s->slots) { utb_searcher_destroy(s); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     for (int d = 0; d < n_devices; ++d) {
@@ -232,10 +242,24 @@ typedef struct {
     int failed;
 } sink_t;
 
+/* The mapping of the last output handed back through utb_free() is kept for the next search of the
+ * process: its pages are already faulted in, which is worth more than the copy itself (a fresh
+ * anonymous mapping costs one zero-fill per page on first touch). */
+#define SINK_CACHE_MAX ((size_t)8 << 30)
+static pthread_mutex_t g_sink_mu = PTHREAD_MUTEX_INITIALIZER;
+static char *g_sink_map;
+static size_t g_sink_cap;
+
 static int sink_reserve(sink_t *k, size_t upto) {
     if (k->fd >= 0) return 0;
     size_t need = upto + 64;
     if (need <= k->cap) return 0;
+    if (!k->map) {
+        pthread_mutex_lock(&g_sink_mu);
+        if (g_sink_map) { k->map = g_sink_map; k->cap = g_sink_cap; g_sink_map = NULL; g_sink_cap = 0; }
+        pthread_mutex_unlock(&g_sink_mu);
+        if (need <= k->cap) return 0;
+    }
     size_t nc = k->cap ? k->cap : (k->hint > ((size_t)1 << 24) ? k->hint : (size_t)1 << 24);
     while (nc < need) nc <<= 1;
     void *m = k->map ? mremap(k->map, k->cap, nc, MREMAP_MAYMOVE)
@@ -252,7 +276,11 @@ static int sink_reserve(sink_t *k, size_t upto) {
 void utb_free(void *p) {
     if (!p) return;
     sink_hdr *h = (sink_hdr *)((char *)p - 64);
-    if (h->magic == SINK_MAGIC) munmap(h, h->map_len);
+    if (h->magic != SINK_MAGIC) return;
+    pthread_mutex_lock(&g_sink_mu);
+    if (!g_sink_map && h->map_len <= SINK_CACHE_MAX) { g_sink_map = (char *)h; g_sink_cap = h->map_len; h = NULL; }
+    pthread_mutex_unlock(&g_sink_mu);
+    if (h) munmap(h, h->map_len);
 }
 
 /* ---- shared run state ------------------------------------------------------------------ */
@@ -263,6 +291,9 @@ typedef struct {
     pthread_mutex_t mu;
     pthread_cond_t cv;
     uint64_t submitted;     /* batches handed to the devices */
+    uint64_t consumed;      /* batches the formatter is done with */
+    int discard;            /* a device-framed batch held a malformed record: output from restart_seq on is dropped, */
+    uint64_t restart_seq;   /* the reader rewinds to that batch and frames the rest on the host (exact error path)    */
     int done_reading;
     int error;              /* sticky UTB_ERR_* from the device side */
     char errmsg[512];
@@ -378,6 +409,11 @@ static void *formatter_main(void *arg) {
         R->st.fm_wait_gpu += now_s() - tw;
         if (seq < 64) R->tl_gpu_done[seq] = now_s() - R->t0;
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
+        pthread_mutex_lock(&R->mu);
+        if (!rc && !R->discard && utb_batch_frame_error(sl->b, NULL, NULL)) { R->discard = 1; R->restart_seq = seq; }
+        const int discard = R->discard;
+        pthread_mutex_unlock(&R->mu);
+        if (discard) rc = -1;                                      /* nothing of this batch is emitted or counted */
         if (!rc && s->device_format) {
             double tf = now_s();
             if (text_len && !sink_reserve(R->sink, R->sink->off + text_len)) {
@@ -422,6 +458,7 @@ static void *formatter_main(void *arg) {
         if (seq < 64) R->tl_emitted[seq] = now_s() - R->t0;
         pthread_mutex_lock(&R->mu);
         sl->state = 0;
+        R->consumed = seq + 1;
         pthread_cond_broadcast(&R->cv);
         pthread_mutex_unlock(&R->mu);
     }
@@ -634,6 +671,45 @@ static void frame_indexed_part(void *c_, int part, int nparts) {
     c->groups[part] = groups;
 }
 
+/* Device-side framing: all the host needs is the number of newlines of the chunk (and that it
+ * holds no NUL byte, for which the reference's strlen() semantics would differ). */
+typedef struct { const char *buf; size_t fill; size_t cnt[MAX_TEAM]; int has_nul[MAX_TEAM]; } nlc_ctx;
+#if defined(__x86_64__)
+__attribute__((target("avx2")))
+static size_t nlc_avx2(const char *buf, size_t a, size_t b, int *has_nul) {
+    const __m256i nl = _mm256_set1_epi8('\n'), zero = _mm256_setzero_si256();
+    __m256i accz = zero, acc = zero;
+    size_t n = 0, i = a;
+    unsigned it = 0;
+    for (; i + 32 <= b; i += 32) {
+        __m256i v = _mm256_loadu_si256((const __m256i *)(buf + i));
+        acc = _mm256_sub_epi8(acc, _mm256_cmpeq_epi8(v, nl));       /* per-byte counters: +1 per match */
+        accz = _mm256_or_si256(accz, _mm256_cmpeq_epi8(v, zero));
+        if (++it == 255) {
+            __m256i sad = _mm256_sad_epu8(acc, zero);
+            n += (size_t)_mm256_extract_epi64(sad, 0) + (size_t)_mm256_extract_epi64(sad, 1) + (size_t)_mm256_extract_epi64(sad, 2) + (size_t)_mm256_extract_epi64(sad, 3);
+            acc = zero; it = 0;
+        }
+    }
+    __m256i sad = _mm256_sad_epu8(acc, zero);
+    n += (size_t)_mm256_extract_epi64(sad, 0) + (size_t)_mm256_extract_epi64(sad, 1) + (size_t)_mm256_extract_epi64(sad, 2) + (size_t)_mm256_extract_epi64(sad, 3);
+    int z = _mm256_movemask_epi8(accz) != 0;
+    for (; i < b; ++i) { n += buf[i] == '\n'; z |= !buf[i]; }
+    *has_nul = z;
+    return n;
+}
+#endif
+static void nlc_part(void *c_, int part, int nparts) {
+    nlc_ctx *c = (nlc_ctx *)c_;
+    size_t a = c->fill * (size_t)part / (size_t)nparts, b = c->fill * (size_t)(part + 1) / (size_t)nparts;
+#if defined(__x86_64__)
+    if (__builtin_cpu_supports("avx2")) { c->cnt[part] = nlc_avx2(c->buf, a, b, &c->has_nul[part]); return; }
+#endif
+    size_t n = 0; int z = 0;
+    for (size_t i = a; i < b; ++i) { n += c->buf[i] == '\n'; z |= !c->buf[i]; }
+    c->cnt[part] = n; c->has_nul[part] = z;
+}
+
 static const char *fe_text(int code) {
     switch (code) {
     case FE_NOHEADER: return "ERROR: no header '>'";
@@ -696,6 +772,20 @@ int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t ma
     return UTB_OK;
 }
 
+/* Host stage of the device-side framing: newline count and NUL detection of buf[0..n). */
+int utb_count_newlines(const char *buf, size_t n, int threads, size_t *n_newlines, int *has_nul) {
+    if ((!buf && n) || !n_newlines || !has_nul) { utb_set_error("utb_count_newlines: null argument"); return UTB_ERR_ARG; }
+    team_t team;
+    if (team_init(&team, threads)) { utb_set_error("cannot start worker threads"); return UTB_ERR_NOMEM; }
+    nlc_ctx C;
+    C.buf = buf; C.fill = n;
+    team_run(&team, nlc_part, &C);
+    *n_newlines = 0; *has_nul = 0;
+    for (int p = 0; p < team.n; ++p) { *n_newlines += C.cnt[p]; *has_nul |= C.has_nul[p]; }
+    team_destroy(&team);
+    return UTB_OK;
+}
+
 int utb_format_results(const utb_ctr *ctr, const char *bytes, const uint32_t *name_off, const uint32_t *name_len,
                        const utb_result *results, size_t n_reads, char *out, size_t out_cap, size_t *out_len) {
     if (!ctr || !bytes || !name_off || !name_len || !results || !out || !out_len) { utb_set_error("utb_format_results: null argument"); return UTB_ERR_ARG; }
@@ -727,7 +817,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     for (int i = 0; i < s->n_slots; ++i) { s->slots[i].state = 0; launches0 += utb_batch_launches(s->slots[i].b); }
     /* split the host threads between the two teams */
     /* with the lines built on the device the formatter only moves finished text: most threads frame */
-    int T = s->host_threads, n_fm = T >= 4 ? (s->device_format ? (3 * T + 7) / 8 : T / 2) : 1, n_rd = T >= 4 ? T - n_fm : 1;
+    int T = s->host_threads, n_fm = T >= 4 ? T / 2 : 1, n_rd = T >= 4 ? T - n_fm : 1;
     team_t rd_team;
     if (team_init(&rd_team, n_rd) || team_init(&R.fmt_team, n_fm)) { utb_set_error("cannot start worker threads"); return UTB_ERR_NOMEM; }
     pthread_t fmt;
@@ -744,14 +834,30 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
                           utb_host_ptr_is_pinned(src->mem + src->mem_len - 1);
     int rc = UTB_OK, fmt_err = 0;
     char fmt_msg[256] = "";
-    uint64_t seq = 0, n_reads_total = 0;
+    uint64_t seq = 0, n_reads_total = 0, consumed = 0;
+    /* device-side framing needs an input that can be rewound if a malformed record turns up */
+    int device_frame = s->device_frame && (src->fd < 0 || src->seekable);
     double rd_t[4] = {0, 0, 0, 0};
     if (!carry) { rc = UTB_ERR_NOMEM; utb_set_error("out of memory (carry)"); }
+read_loop:
     while (!rc) {
         slot_t *sl = &s->slots[seq % (uint64_t)s->n_slots];
         double tp = now_s();
         pthread_mutex_lock(&R.mu);
-        while (sl->state != 0) pthread_cond_wait(&R.cv, &R.mu);
+        while (sl->state != 0 && !R.discard) pthread_cond_wait(&R.cv, &R.mu);
+        if (R.discard) {
+            /* A device-framed batch held a malformed record.  Let the formatter drain (and drop) what is in
+             * flight, rewind the input to the start of that batch and frame the rest with the host reader,
+             * which reproduces the reference's partial output, message and exit code exactly. */
+            while (R.consumed < R.submitted) pthread_cond_wait(&R.cv, &R.mu);
+            const slot_t *ks = &s->slots[R.restart_seq % (uint64_t)s->n_slots];
+            consumed = ks->src_off; n_reads_total = ks->first_read;
+            if (src->fd >= 0) { src->file_off = (off_t)consumed; src->eof = src->file_off >= src->file_size; }
+            else { src->mem_pos = (size_t)consumed; src->eof = src->mem_pos >= src->mem_len; }
+            carry_len = 0; device_frame = 0; R.discard = 0;
+            pthread_mutex_unlock(&R.mu);
+            continue;
+        }
         int dev_err = R.error;
         pthread_mutex_unlock(&R.mu);
         rd_t[0] += now_s() - tp; tp = now_s();
@@ -759,11 +865,12 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         const char *buf = utb_batch_bytes(sl->b);
         size_t cap = utb_batch_max_bytes(sl->b), fill = carry_len;
         /* batch-size schedule: ramp up (64, 64, 128 MiB, then full) and, when the input size is known, down again */
-        if (cap > 2 * RAMP_BYTES) {
-            size_t want = seq < 2 ? RAMP_BYTES : seq == 2 ? 2 * RAMP_BYTES : cap;
+        const size_t RAMP = s->ramp_bytes;
+        if (cap > 2 * RAMP) {
+            size_t want = seq < 2 ? RAMP : seq == 2 ? 2 * RAMP : cap;
             size_t left = src->fd < 0 ? src->mem_len - src->mem_pos : src->seekable ? (size_t)(src->file_size - src->file_off) : (size_t)-1;
-            if (left != (size_t)-1 && left + carry_len <= 3 * RAMP_BYTES) want = RAMP_BYTES;
-            else if (left != (size_t)-1 && left + carry_len < want + 2 * RAMP_BYTES && want > 2 * RAMP_BYTES) want = left + carry_len - 2 * RAMP_BYTES;
+            if (left != (size_t)-1 && left + carry_len <= 3 * RAMP) want = RAMP;
+            else if (left != (size_t)-1 && left + carry_len < want + 2 * RAMP && want > 2 * RAMP) want = left + carry_len - 2 * RAMP;
             if (want < carry_len + 4096) want = carry_len + 4096;  /* a carried partial record must be able to complete */
             if (want < 2 * (size_t)UTB_LINELEN + 4096) want = 2 * (size_t)UTB_LINELEN + 4096;
             if (want < cap) cap = want;
@@ -782,6 +889,41 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         rd_t[1] += now_s() - tp; tp = now_s();
         if (!fill) break;                                          /* clean EOF */
 
+        sl->src_off = consumed;
+        if (device_frame && fill >= 2 && fill < 0xFFFFFFFFull) {
+            /* fast path: count the newlines; the records themselves are framed on the device */
+            nlc_ctx C;
+            C.buf = buf; C.fill = fill;
+            team_run(&rd_team, nlc_part, &C);
+            size_t n_lines = 0; int nul = 0;
+            for (int p = 0; p < rd_team.n; ++p) { n_lines += C.cnt[p]; nul |= C.has_nul[p]; }
+            const size_t n_rec = n_lines / 2;
+            /* left to the host reader: NUL bytes, a last line without '\n' or a dangling header at EOF, more
+             * records than the batch arrays hold, a record larger than the buffer */
+            if (!nul && n_rec >= 1 && n_rec <= utb_batch_max_reads(sl->b) && !(src->eof && (buf[fill - 1] != '\n' || (n_lines & 1)))) {
+                const char *last = (const char *)memrchr(buf, '\n', fill);
+                if (n_lines & 1) last = (const char *)memrchr(buf, '\n', (size_t)(last - buf));
+                const size_t used = (size_t)(last - buf) + 1;
+                sl->n_reads = n_rec; sl->host_bytes = buf; sl->n_bytes = used; sl->first_read = n_reads_total;
+                n_reads_total += n_rec; consumed += used;
+                if (zero_copy) { src->mem_pos += used; if (src->mem_pos < src->mem_len) src->eof = 0; }
+                else if (used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
+                rd_t[2] += now_s() - tp; tp = now_s();
+                if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = n_rec; }
+                int r2 = utb_batch_submit_raw(sl->b, zero_copy ? buf : NULL, used, n_rec, do_rc);
+                if (r2) { rc = r2; break; }
+                R.st.h2d_bytes += used + 4;
+                if (seq < 64) R.tl_submit[seq] = now_s() - t0;
+                pthread_mutex_lock(&R.mu);
+                sl->state = 1;
+                R.submitted = ++seq;
+                pthread_cond_broadcast(&R.cv);
+                pthread_mutex_unlock(&R.mu);
+                rd_t[3] += now_s() - tp;
+                if (src->eof && !carry_len) break;
+                continue;
+            }
+        }
         frame_ctx F;
         memset(&F, 0, sizeof F);
         F.buf = buf; F.fill = fill; F.eof = src->eof; F.max_rec = utb_batch_max_reads(sl->b);
@@ -824,6 +966,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         sl->n_bytes = fmt_err ? fill : used;
         sl->first_read = n_reads_total;
         n_reads_total += n;
+        consumed += fmt_err ? fill : used;
         if (zero_copy) { src->mem_pos += fmt_err ? fill : used; if (src->mem_pos < src->mem_len) src->eof = 0; }
         else if (!fmt_err && used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
         rd_t[2] += now_s() - tp; tp = now_s();
@@ -844,6 +987,14 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
         rd_t[3] += now_s() - tp;
         if (fmt_err) break;
         if (src->eof && !carry_len) break;
+    }
+    if (!rc && !fmt_err && device_frame) {
+        /* the input is exhausted, but a device-framed batch still in flight may hold a malformed record */
+        pthread_mutex_lock(&R.mu);
+        while (R.consumed < R.submitted) pthread_cond_wait(&R.cv, &R.mu);
+        const int again = R.discard;
+        pthread_mutex_unlock(&R.mu);
+        if (again) goto read_loop;                                 /* the top of the loop rewinds */
     }
     free(idx);
     pthread_mutex_lock(&R.mu);
