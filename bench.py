@@ -381,7 +381,7 @@ def main():
         if two_phase:
             cand.append(("queue_lookup_kernel (exact key-window search of the filter survivors)", surv_ms, 32.0 * det_sect[1], "rand32",
                          "32 B x the sectors the exact path touches (index pair, key windows, aux), counted on the device"))
-        cand.append(("vote_warp_kernel (+ vote_block_kernel; per-read label multiset and aufbau walk)", vote_ms,
+        cand.append(("vote_thread_kernel (+ vote_warp_kernel / vote_block_kernel for label-rich and long reads; label multiset and aufbau walk)", vote_ms,
                      det_sect[0] / 8.0 + 4.0 * hits + 32.0 * n_reads, "stream",
                      "1 bit per lookup slot of the hit map + 4 B per hit + one 32 B result per read"))
         k_name, k_ms, k_bytes, k_peak, k_alg = max(cand, key=lambda c: c[1])

@@ -3,10 +3,10 @@
 # one --set full capture of the hot kernels (each only after its plain run exited 0).
 mkdir -p gpurun_out
 T=${TAG:-r3}
-( time python -m pytest tests/test_gpu_parity.py -x -q --durations=5 ) > gpurun_out/${T}_parity.log 2>&1
+( time python -m pytest ${PYTEST_TARGET:-tests/test_gpu_parity.py} -m gpu -x -q --durations=8 ) > gpurun_out/${T}_parity.log 2>&1
 rc=$?; echo "parity rc=$rc"; tail -4 gpurun_out/${T}_parity.log
 [ $rc -ne 0 ] && { grep -n "Error\|assert\|FAILED" gpurun_out/${T}_parity.log | head -20; exit 1; }
-python bench.py --steps 3 --warmup 3 ${BENCH_FLAGS:---no-cpu} > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+python bench.py --steps 3 --warmup 3 ${BENCH_FLAGS---no-cpu} > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
 rc=$?; echo "bench rc=$rc"; [ $rc -ne 0 ] && { tail -20 gpurun_out/${T}_bench.err; exit 1; }
 python - <<E
 import json
@@ -20,7 +20,7 @@ E
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu > gpurun_out/${T}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
-ncu --set full --clock-control none --import-source on -k 'regex:partition_kernel|probe_kernel|queue_lookup_kernel|vote_warp_kernel' -c 4 \
+ncu --set full --clock-control none --import-source on -k 'regex:partition_kernel|probe_kernel|queue_lookup_kernel|vote_thread_kernel|vote_warp_kernel' -c 5 \
     -o gpurun_out/${T}_prof_resident -f python bench.py --steps 1 --warmup 1 --no-cpu --reads 2000000 > gpurun_out/${T}_ncu_a.log 2>&1
 echo "ncu resident rc=$?"
 ncu --set full --clock-control none --import-source on -k 'regex:filter_kernel' --launch-skip 6 -c 1 \

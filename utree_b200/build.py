@@ -49,7 +49,8 @@ def build(force=False, verbose=False):
     log = []
     objs = []
     o = os.path.join(CSRC, "kernels.o")
-    _run([NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, "kernels.cu"), "-o", o], log)
+    extra = os.environ.get("UTB_NVCC_EXTRA", "").split()        # tuning builds, e.g. "-DFILT_ILP=4 -DFILT_MINB=3"
+    _run([NVCC] + NVCC_FLAGS + extra + ["-c", os.path.join(CSRC, "kernels.cu"), "-o", o], log)
     objs.append(o)
     for f in C_SOURCES:
         o = os.path.join(CSRC, f[:-2] + ".o")

@@ -6,22 +6,28 @@
 //             (8 B when numNodes >= 2^32-1)                  itree.c:756-759
 //   recs    : the CTR record blob exactly as on disk, numNodes x SZ bytes,
 //             SZ = 5-byte suffix + IXTYPE id, + 32 B slack   itree.c:766
+//             (irregular CTRs only; regular ones are re-laid out once at upload
+//             into key / aux words, see DevDB, and get a Bloom filter)
 //   labels  : blob of NUL-terminated strings, off[], rank[], by_rank[]
 // Per batch (one stream slot):
 //   raw     : the FASTA bytes as read from the file (headers included)
-//   seq_off/seq_len/grp_off : where each read's sequence line sits, and the
-//             first 32-base group it owns in the packed "super-sequence"
+//   nl      : positions of the newlines (device-side framing)
+//   seq_off/seq_len/name_off/name_len/grp_off : where each read's lines sit, and
+//             the first 32-base group it owns in the packed "super-sequence"
 //   pk/bad  : 2-bit codes (u64 per 32 bases, first base most significant, the
 //             k-mer word order of itree.c:924) and a bad-base bit mask.  Every
 //             read is padded to a multiple of 32 positions with >= 1 bad
 //             position, so a 32-mer window can never straddle two reads.
-//   hits    : one u32 per (position, strand): label id, MISS or NOWIN
-//   results : one utb_result per read
+//   hits    : one u32 per (position, strand): label id; valid where hitmap is set
+//   results : one utb_result per read;  text : the output lines
 //
-// Kernels: pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926),
-// lookup_kernel (XT_getIX32 + xtSuffixBS with the reference's exact probe
-// sequence, itree.c:699-730), vote_warp_kernel / vote_block_kernel (full
-// aufbau vote, itree.c:1028-1098).
+// Kernels: nl_count / nl_index / frame_parse (XT_INITIATE_WS, itree.c:860-901),
+// pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926), filter_kernel or
+// partition_kernel + probe_kernel (membership pre-filter, one fetch per position
+// for both strands) and queue_lookup_kernel (XT_getIX32 + xtSuffixBS on the
+// survivors, itree.c:699-730), lookup_kernel (the same without pre-filter, or the
+// reference's exact probe sequence), vote_thread / vote_warp / vote_block (full
+// aufbau vote, itree.c:1028-1098), fmt_* (the fprintf lines, itree.c:1032-1096).
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
@@ -62,9 +68,10 @@ struct DevDB {
     const uint32_t *by_rank;
     uint32_t quirk_bin;        // bucket whose record 0 is the folded foreign record, else 0xFFFFFFFF
     // regular CTRs only: structure-of-arrays copy of the records (recs is then freed)
-    const uint32_t *keys;      // suffix >> 8
-    const uint32_t *aux32;     // suffix & 0xFF | id << 8   (IXTYPE uint16_t)
-    const uint64_t *aux64;     // same, IXTYPE uint32_t
+    const uint32_t *kv;        // IXTYPE uint16_t: blocks of 16 records = one 128-byte line, 16 keys (suffix >> 8) then their
+                               // 16 aux words (suffix & 0xFF | id << 8): the line a key window misses on also holds its aux
+    const uint32_t *keys;      // IXTYPE uint32_t: suffix >> 8 ...
+    const uint64_t *aux64;     // ... and suffix & 0xFF | id << 8 in a second array
     // membership pre-filter over all record words (register-blocked Bloom, 16-byte blocks)
     const uint4 *bloom;
     uint64_t bloom_blocks;
@@ -243,12 +250,13 @@ __device__ __forceinline__ uint32_t probe_end(const DevDB &db, const Probe &q) {
 // loads a warp has to wait for (profiles/r01_*: DRAM ~35 % busy, all warps
 // resident, ~8 serialized round trips per lookup).  For a regular CTR (every
 // bucket strictly sorted -- verified on the device at upload) the records are
-// therefore re-laid out once, at load time, as structure-of-arrays:
-//     keys[i] = suffix >> 8   (u32, 16 keys per 64-byte line)
-//     aux[i]  = suffix & 0xFF | id << 8
+// therefore re-laid out once, at load time, into 32-bit words:
+//     key[i] = suffix >> 8          aux[i] = suffix & 0xFF | id << 8
+// (uint16_t labels: blocks of 16 keys followed by their 16 aux words, one
+// 128-byte line per block; uint32_t labels: two arrays).
 // Suffixes are close to uniform inside a bucket, so record a + n*s/2^40 is
-// within a few slots of the answer: ONE aligned 64-byte vector load around it
-// holds the 16 candidate keys, which are ranked branch-free in registers.  A
+// within a few slots of the answer: ONE aligned 32-byte sector around it
+// holds 8 candidate keys, which are ranked branch-free in registers.  A
 // lookup is then index -> key line -> (hits only) aux: 2-3 dependent steps
 // instead of ~8, and ~1.3 random DRAM fetches instead of ~5.  On a strictly
 // sorted bucket any exact membership test returns what xtSuffixBS returns, so
@@ -280,8 +288,10 @@ __device__ __forceinline__ void fast_begin(const DevDB &db, uint64_t word, FastP
 // line in L2, so the neighbouring sectors a later step may need are L2 hits;
 // asking for them up front would cost as much as further misses
 // (profiles/r01_membench_ncu.txt).
+__device__ __forceinline__ uint64_t kv_index(uint64_t i) { return ((i >> 4) << 5) | (i & 15u); }   // u32 index of key i in db.kv
+__device__ __forceinline__ uint32_t key_at(const DevDB &db, uint64_t i) { return db.kv ? __ldg(db.kv + kv_index(i)) : __ldg(db.keys + i); }
 __device__ __forceinline__ void window_fetch(const DevDB &db, const FastProbe &q, uint4 &k0, uint4 &k1) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(db.keys + q.ws);
+    const uint4 *p = reinterpret_cast<const uint4 *>(db.kv ? db.kv + kv_index(q.ws) : db.keys + q.ws);   // ws is a multiple of 8
     k0 = __ldg(p); k1 = __ldg(p + 1);
 }
 __device__ __forceinline__ void window_rank(FastProbe &q, const uint4 &k0, const uint4 &k1) {
@@ -303,7 +313,7 @@ __device__ __forceinline__ void window_rank(FastProbe &q, const uint4 &k0, const
     } else { q.st = FW_FOUND; q.pos = wa + lt; q.cnt = eq; }       // eq > 1: k-mers of related genomes that differ in the last 4 bases
 }
 __device__ __forceinline__ uint64_t load_aux(const DevDB &db, uint64_t i) {
-    return db.aux32 ? (uint64_t)__ldg(db.aux32 + i) : __ldg(db.aux64 + i);
+    return db.kv ? (uint64_t)__ldg(db.kv + kv_index(i) + 16u) : __ldg(db.aux64 + i);
 }
 // rare: exact lower bound over the whole bucket on the full 40-bit suffix
 __device__ __noinline__ uint32_t fast_slow(const DevDB &db, uint64_t a, uint64_t b, uint32_t t, uint32_t lo8) {
@@ -311,12 +321,12 @@ __device__ __noinline__ uint32_t fast_slow(const DevDB &db, uint64_t a, uint64_t
     uint64_t lo = a, hi = b;
     while (lo < hi) {
         uint64_t mid = (lo + hi) >> 1;
-        uint64_t c = ((uint64_t)__ldg(db.keys + mid) << 8) | (load_aux(db, mid) & 0xFFu);
+        uint64_t c = ((uint64_t)key_at(db, mid) << 8) | (load_aux(db, mid) & 0xFFu);
         if (c < s) lo = mid + 1; else hi = mid;
     }
     if (lo >= b) return HIT_MISS;
     uint64_t ax = load_aux(db, lo);
-    if ((((uint64_t)__ldg(db.keys + lo) << 8) | (ax & 0xFFu)) != s) return HIT_MISS;
+    if ((((uint64_t)key_at(db, lo) << 8) | (ax & 0xFFu)) != s) return HIT_MISS;
     uint32_t ix = (uint32_t)(ax >> 8);
     return ix < db.max_ix ? ix : HIT_MISS;
 }
@@ -364,8 +374,8 @@ __device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)
             ++ns;
             const uint64_t wa = q[i].ws > q[i].a ? q[i].ws : q[i].a, wb = q[i].ws + KW < q[i].b ? q[i].ws + KW : q[i].b;
             uint32_t nbl = ~q[i].t, nbr = ~q[i].t;
-            if (q[i].pos == wa && wa > q[i].a) nbl = __ldg(db.keys + q[i].pos - 1);
-            if (q[i].pos + q[i].cnt == wb && wb < q[i].b) nbr = __ldg(db.keys + q[i].pos + q[i].cnt);
+            if (q[i].pos == wa && wa > q[i].a) nbl = key_at(db, q[i].pos - 1);
+            if (q[i].pos + q[i].cnt == wb && wb < q[i].b) nbr = key_at(db, q[i].pos + q[i].cnt);
             uint64_t ax[KW];
 #pragma unroll
             for (uint32_t j = 0; j < KW; ++j) ax[j] = j < q[i].cnt ? load_aux(db, q[i].pos + j) : 0;
@@ -383,14 +393,13 @@ __device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)
 
 // raw CTR records -> SoA (runs once at upload, only for regular CTRs)
 __global__ void __launch_bounds__(256)
-relayout_kernel(DevDB db, uint32_t *__restrict__ keys, uint32_t *__restrict__ aux32, uint64_t *__restrict__ aux64) {
+relayout_kernel(DevDB db, uint32_t *__restrict__ kv, uint32_t *__restrict__ keys, uint64_t *__restrict__ aux64) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= db.num_nodes) return;
     uint64_t suf = load_suffix(db.recs, i * db.sz);
     uint32_t ix = load_ix(db, i);
-    keys[i] = (uint32_t)(suf >> 8);
-    if (aux32) aux32[i] = (uint32_t)(suf & 0xFFu) | (ix << 8);
-    else aux64[i] = (suf & 0xFFu) | ((uint64_t)ix << 8);
+    if (kv) { kv[kv_index(i)] = (uint32_t)(suf >> 8); kv[kv_index(i) + 16u] = (uint32_t)(suf & 0xFFu) | (ix << 8); }
+    else { keys[i] = (uint32_t)(suf >> 8); aux64[i] = (suf & 0xFFu) | ((uint64_t)ix << 8); }
 }
 
 // Load-time check of the invariant the interpolation search relies on.
@@ -464,7 +473,7 @@ bloom_build_kernel(DevDB db, uint32_t *__restrict__ bloom) {
     if (a >= b || b > db.num_nodes) return;
     if (p == db.quirk_bin) ++a;                                    // the folded record is unreachable anyway
     for (uint64_t i = a; i < b; ++i) {
-        const uint64_t word = ((uint64_t)p << 40) | ((uint64_t)db.keys[i] << 8) | (load_aux(db, i) & 0xFFu);
+        const uint64_t word = ((uint64_t)p << 40) | ((uint64_t)key_at(db, i) << 8) | (load_aux(db, i) & 0xFFu);
         const uint64_t hc = bloom_block_hash(word, revcomp_word(word));
         uint32_t *blk = bloom + 4 * __umul64hi(hc, db.bloom_blocks);
         const uint4 m = bloom_masks(hc, word);
@@ -613,7 +622,7 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     uint32_t nv = 0, nh = 0;
     // every warp takes FILT_ILP x 32 consecutive positions per round (n_pos is a multiple of 32)
     for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * FILT_ILP; base < n_pos; base += stride * FILT_ILP) {
-        uint64_t w[FILT_ILP], rc[FILT_ILP], hc[FILT_ILP];
+        uint64_t w[FILT_ILP], hc[FILT_ILP];
         uint4 v[FILT_ILP];
         bool valid[FILT_ILP];
 #pragma unroll
@@ -621,15 +630,15 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
             const uint64_t pos = base + 32u * u + lane;
             w[u] = 0;
             valid[u] = pos < n_pos && window_at(pk, bad, (uint32_t)pos, w[u]);
-            rc[u] = revcomp_word(w[u]);
-            hc[u] = bloom_block_hash(w[u], rc[u]);
+            hc[u] = bloom_block_hash(w[u], revcomp_word(w[u]));
             v[u] = make_uint4(0, 0, 0, 0);
             if (valid[u]) v[u] = __ldg(db.bloom + __umul64hi(hc[u], db.bloom_blocks));
         }
 #pragma unroll
         for (int u = 0; u < FILT_ILP; ++u) {
             const uint32_t pos = (uint32_t)(base + 32u * u + lane);
-            nh += filter_emit<NSTR>(db, wq, lane, valid[u], w[u], rc[u], hc[u], v[u], pos, q_words, q_slots, q_count, q_cap, hits, hitmap);
+            // the reverse complement is recomputed rather than kept live across the loads (registers = probes in flight)
+            nh += filter_emit<NSTR>(db, wq, lane, valid[u], w[u], revcomp_word(w[u]), hc[u], v[u], pos, q_words, q_slots, q_count, q_cap, hits, hitmap);
             nv += valid[u] ? NSTR : 0;                             // hits[] is only valid where hitmap is set: nothing to store for misses
         }
     }
@@ -1760,22 +1769,30 @@ static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db) {
         db->use_interp = db->regular && !(lk && !strcmp(lk, "exact"));
     }
     if (db->use_interp) {
-        // one-time re-layout into key / aux arrays (16 keys of slack: the window load may overrun)
-        const size_t n = (size_t)ctr->num_nodes, aux_sz = ctr->ix_bytes == 2 ? 4 : 8;
-        CK(cudaMalloc(&db->keys, (n + 32) * 4));
-        CK(cudaMalloc(&db->aux, (n + 32) * aux_sz));
-        CK(cudaMemset((char *)db->keys + n * 4, 0xFF, 32 * 4));
-        relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, (uint32_t *)db->keys,
-                                                               ctr->ix_bytes == 2 ? (uint32_t *)db->aux : nullptr,
-                                                               ctr->ix_bytes == 2 ? nullptr : (uint64_t *)db->aux);
+        // one-time re-layout (slack after the last record: a window load may overrun into it)
+        const size_t n = (size_t)ctr->num_nodes;
+        size_t lay_bytes;
+        if (ctr->ix_bytes == 2) {                                  // key/aux interleaved per 128-byte line
+            const size_t blocks = (n + 15) / 16 + 2;
+            lay_bytes = blocks * 128;
+            CK(cudaMalloc(&db->keys, lay_bytes));
+            CK(cudaMemset(db->keys, 0xFF, lay_bytes));
+            relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, (uint32_t *)db->keys, nullptr, nullptr);
+        } else {
+            lay_bytes = (n + 32) * 12;
+            CK(cudaMalloc(&db->keys, (n + 32) * 4));
+            CK(cudaMalloc(&db->aux, (n + 32) * 8));
+            CK(cudaMemset((char *)db->keys + n * 4, 0xFF, 32 * 4));
+            relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, nullptr, (uint32_t *)db->keys, (uint64_t *)db->aux);
+        }
         CK(cudaGetLastError());
         CK(cudaDeviceSynchronize());
-        db->d.keys = (const uint32_t *)db->keys;
-        db->d.aux32 = ctr->ix_bytes == 2 ? (const uint32_t *)db->aux : nullptr;
+        db->d.kv = ctr->ix_bytes == 2 ? (const uint32_t *)db->keys : nullptr;
+        db->d.keys = ctr->ix_bytes == 2 ? nullptr : (const uint32_t *)db->keys;
         db->d.aux64 = ctr->ix_bytes == 2 ? nullptr : (const uint64_t *)db->aux;
         CK(cudaFree(db->recs));                                    // the byte-packed blob is no longer needed
         db->recs = nullptr; db->d.recs = nullptr;
-        db->hbm_bytes = nb_binix + (n + 32) * (4 + aux_sz) + ctr->blob_len + 3 * (nl + 1) * 4;
+        db->hbm_bytes = nb_binix + lay_bytes + ctr->blob_len + 3 * (nl + 1) * 4;
         const char *bm = getenv("UTB_BLOOM");                      // 0 off, 1 always, default auto
         db->bloom_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
         if (db->bloom_mode) {
