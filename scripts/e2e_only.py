@@ -12,7 +12,7 @@ pinned = torch.empty(n * rec, dtype=torch.uint8, pin_memory=True)
 reads = pinned.numpy()
 bench.make_reads(cfg, 0, n, 0, out=reads)
 ctr = capi.Ctr(ctr_path)
-s = capi.Searcher(ctr, devices=(0,), host_threads=os.cpu_count())
+s = capi.Searcher(ctr, devices=(0,), host_threads=int(os.environ.get("E2E_THREADS", os.cpu_count())))
 for i in range(reps):
     t = time.time()
     rc, ex, nbytes, st = s.search_mem(None, do_rc=True, ptr=reads.ctypes.data, n=reads.size, copy=False)

@@ -374,11 +374,12 @@ def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, read
         s.destroy(); ctr.close()
 
 
-@pytest.mark.parametrize("host_frame", [0, 1])
-def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, host_frame):
+@pytest.mark.parametrize("mode", ["device_count", "host_count", "host_frame"])
+def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, mode):
     """Records framed on the GPU (the host only counts newlines): several batches with a carried tail,
     CRLF / tab-in-header / empty-line records, and a malformed record deep in the input -- the reader
     rewinds to that batch and the host framer reproduces the reference's partial output and exit code.
+    The newline count comes from the device (default) or from the host threads (UTB_HOST_COUNT=1);
     UTB_HOST_FRAME=1 (host framer throughout) must give the same bytes."""
     from utree_b200 import capi
     one = open(gold("toyA_reads.fa"), "rb").read()
@@ -388,12 +389,14 @@ def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, host_fra
     if not edge.endswith(b"\n"):
         edge += b"\n"
     os.environ["UTB_BATCH_MB"] = "33"
-    if host_frame:
+    if mode == "host_frame":
         os.environ["UTB_HOST_FRAME"] = "1"
+    if mode == "host_count":
+        os.environ["UTB_HOST_COUNT"] = "1"
     try:
         s = capi.Searcher(gpu["toyA"][0], devices=(0, 0), host_threads=5)
     finally:
-        os.environ.pop("UTB_BATCH_MB", None); os.environ.pop("UTB_HOST_FRAME", None)
+        os.environ.pop("UTB_BATCH_MB", None); os.environ.pop("UTB_HOST_FRAME", None); os.environ.pop("UTB_HOST_COUNT", None)
     try:
         rc, ex, text, st = s.search_mem(one * reps, do_rc=True)
         assert rc == 0 and st["batches"] >= 2 and st["reads"] == reps * one.count(b">")
@@ -406,6 +409,18 @@ def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, host_fra
         # sequence line begins '>' inside the first batch
         rc, ex, text, st = s.search_mem(one + b">x\n>y\n" + one * reps, do_rc=True)
         assert (rc, ex) == (3, 2) and text == want
+        # a NUL byte in the chunk: the count flags it and the exact host reader takes the batch
+        # (strlen() semantics, itree.c:887: the sequence ends at the NUL)
+        first = one.split(b"\n", 2)
+        cut = first[0] + b"\n" + first[1][:60] + b"\0" + first[1][60:] + b"\n" + first[2]
+        rc, ex, text, st = s.search_mem(cut, do_rc=True)
+        orc = gpu["toyA"][2]
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            fa, out = os.path.join(d, "n.fa"), os.path.join(d, "n.out")
+            open(fa, "wb").write(cut)
+            orc.search_file(fa, out, do_rc=True)
+            assert rc == 0 and text == open(out, "rb").read()
         # and the searcher is reusable afterwards
         rc, ex, text, st = s.search_mem(one * 2, do_rc=True)
         assert rc == 0 and text == want * 2

@@ -1518,9 +1518,11 @@ slots_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, uint32_t *__restr
 #define FR_BLOCK (256u * FR_BPT)
 #define FR_ERR_NONE 0xFFFFFFFFu
 enum { FRE_NOHEADER = 1, FRE_SEQ_GT = 2, FRE_TOOLONG = 4 };   // codes as in pipeline.c (FE_*)
-// bit j of the result: byte j of the 64 bytes at p is '\n' (bytes at or beyond n_bytes never match)
-__device__ __forceinline__ uint64_t nl_mask64(const uint8_t *__restrict__ raw, uint64_t at, uint64_t n_bytes) {
-    uint64_t m = 0;
+// bit j of the result: byte j of the 64 bytes at p is '\n' (bytes at or beyond n_bytes never match);
+// *nul (optional): whether one of those bytes is 0
+__device__ __forceinline__ uint64_t nl_mask64(const uint8_t *__restrict__ raw, uint64_t at, uint64_t n_bytes, bool *nul = nullptr) {
+    uint64_t m = 0, z = 0;
+    if (nul) *nul = false;
     if (at >= n_bytes) return 0;
     const uint4 *p = reinterpret_cast<const uint4 *>(raw + at);
 #pragma unroll
@@ -1531,17 +1533,21 @@ __device__ __forceinline__ uint64_t nl_mask64(const uint8_t *__restrict__ raw, u
         for (int k = 0; k < 4; ++k) {
             const uint32_t e = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x01010101u;
             m |= (uint64_t)((e * 0x01020408u) >> 24) << (16 * q + 4 * k);
+            if (nul) { const uint32_t e0 = __vcmpeq4(w[k], 0u) & 0x01010101u; z |= (uint64_t)((e0 * 0x01020408u) >> 24) << (16 * q + 4 * k); }
         }
     }
     const uint64_t left = n_bytes - at;
-    if (left < 64) m &= (1ull << left) - 1ull;
+    if (left < 64) { m &= (1ull << left) - 1ull; z &= (1ull << left) - 1ull; }
+    if (nul) *nul = z != 0;
     return m;
 }
 __global__ void __launch_bounds__(256)
-nl_count_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, uint32_t *__restrict__ blk_cnt) {
+nl_count_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, uint32_t *__restrict__ blk_cnt, uint32_t *__restrict__ nul_flag) {
     __shared__ uint32_t sh[8];
     const uint64_t at = ((uint64_t)blockIdx.x * 256u + threadIdx.x) * FR_BPT;
-    uint32_t c = __popcll(nl_mask64(raw, at, n_bytes));
+    bool nul;
+    uint32_t c = __popcll(nl_mask64(raw, at, n_bytes, &nul));
+    if (__any_sync(0xFFFFFFFFu, nul) && (threadIdx.x & 31) == 0) atomicOr(nul_flag, 1u);
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = c;
     __syncthreads();
@@ -1880,6 +1886,7 @@ struct utb_batch {
     uint64_t launches;
     // device-side framing
     uint32_t *d_nl, *d_blk, *d_frame_err, *d_ngroups, *h_frame_err; const uint32_t *ngroups_dev; int framed_on_device;
+    uint32_t *d_frame_info, *h_frame_info; cudaEvent_t count_ready; size_t raw_bytes;   // [0] newlines of the chunk, [1] NUL seen
 };
 
 extern "C" uint64_t utb_read_slots(uint32_t len) { return ((uint64_t)len + 1 + 31) / 32; }
@@ -1907,6 +1914,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_pwords); cudaFree(b->d_ppos); cudaFree(b->d_pfill); cudaFree(b->d_pctr);
     cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFree(b->d_ngroups); cudaFreeHost(b->h_frame_err);
+    cudaFree(b->d_frame_info); cudaFreeHost(b->h_frame_info); if (b->count_ready) cudaEventDestroy(b->count_ready);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 7; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -2207,34 +2215,63 @@ static int finish_submit(utb_batch *b) {
     return UTB_OK;
 }
 
-// Raw submit (pipeline-internal): the first n_bytes of `src` (pinned host memory, or NULL for the batch's own
-// staging) hold exactly n_reads complete records = 2 * n_reads lines, each ended by '\n', and no NUL byte
-// (the host counted the newlines; that is all it looked at).  The records are framed on the device and the
-// output text is built there.  utb_batch_frame_error() tells after the wait whether a record was malformed.
-extern "C" int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc) {
-    if (!b || !n_reads || !n_bytes) { utb_set_error("utb_batch_submit_raw: bad argument"); return UTB_ERR_ARG; }
-    if (n_bytes > b->max_bytes || n_reads > b->max_reads) { utb_set_error("utb_batch_submit_raw: batch over capacity"); return UTB_ERR_LIMIT; }
+// Raw submit (pipeline-internal), in two steps so that the host need not look at the bytes at all:
+//   utb_batch_raw_begin  copies the chunk to the device and counts its newlines there (and notes a NUL byte);
+//   utb_batch_raw_count  blocks until that count is on the host (only this batch's copy and one small kernel
+//                        are waited for; the other stream slots keep the GPU busy meanwhile);
+//   utb_batch_raw_finish the caller has derived from the count that the first n_bytes hold exactly n_reads
+//                        complete records = 2 * n_reads lines, each ended by '\n', and no NUL byte: the records
+//                        are framed on the device, searched, and the output text is built there.
+// utb_batch_submit_raw = begin + finish for a caller that counted the newlines itself.
+// utb_batch_frame_error() tells after the wait whether a record was malformed.
+extern "C" int utb_batch_raw_begin(utb_batch *b, const char *src, size_t n_bytes) {
+    if (!b || !n_bytes) { utb_set_error("utb_batch_raw_begin: bad argument"); return UTB_ERR_ARG; }
+    if (n_bytes > b->max_bytes) { utb_set_error("utb_batch_raw_begin: batch over capacity"); return UTB_ERR_LIMIT; }
     CK(cudaSetDevice(b->db->device));
     if (!b->d_nl) {
         CK(cudaMalloc(&b->d_nl, (2 * b->max_reads + 2) * 4));
         CK(cudaMalloc(&b->d_blk, (b->max_bytes / FR_BLOCK + 2) * 4));
         CK(cudaMalloc(&b->d_frame_err, 4));
         CK(cudaMalloc(&b->d_ngroups, 4));
+        CK(cudaMalloc(&b->d_frame_info, 8));
         CK(cudaMallocHost(&b->h_frame_err, 4));
+        CK(cudaMallocHost(&b->h_frame_info, 8));
+        CK(cudaEventCreateWithFlags(&b->count_ready, cudaEventDisableTiming));
     }
     int rt = ensure_text_buffers(b);
     if (rt) return rt;
+    b->raw_bytes = n_bytes;
+    CK(cudaMemcpyAsync(b->d_raw, src ? src : b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
+    CK(cudaMemsetAsync(b->d_frame_err, 0xFF, 4, b->st));
+    CK(cudaMemsetAsync(b->d_frame_info, 0, 8, b->st));
+    const uint32_t fb = (uint32_t)((n_bytes + FR_BLOCK - 1) / FR_BLOCK);
+    nl_count_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, b->d_frame_info + 1);
+    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_blk, fb, b->d_frame_info);       // block counts -> exclusive offsets, total newlines
+    b->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(b->h_frame_info, b->d_frame_info, 8, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaEventRecord(b->count_ready, b->st));
+    return UTB_OK;
+}
+extern "C" int utb_batch_raw_count(utb_batch *b, size_t *n_newlines, int *has_nul) {
+    if (!b || !b->count_ready || !n_newlines || !has_nul) { utb_set_error("utb_batch_raw_count: bad argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    CK(cudaEventSynchronize(b->count_ready));
+    *n_newlines = b->h_frame_info[0]; *has_nul = b->h_frame_info[1] != 0;
+    return UTB_OK;
+}
+extern "C" int utb_batch_raw_finish(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
+    if (!b || !n_reads || !n_bytes || n_bytes > b->raw_bytes) { utb_set_error("utb_batch_raw_finish: bad argument"); return UTB_ERR_ARG; }
+    if (n_reads > b->max_reads) { utb_set_error("utb_batch_raw_finish: batch over capacity"); return UTB_ERR_LIMIT; }
+    CK(cudaSetDevice(b->db->device));
     // every read owns ceil((len+1)/32) <= len/32 + 1 groups and its two lines hold at least 2 more bytes than its bases
     uint64_t g_ub = (n_bytes - 2 * n_reads) / 32 + n_reads + 1;
     if (n_bytes < 2 * n_reads || g_ub > b->max_groups) g_ub = b->max_groups;
     b->n_reads = n_reads; b->n_groups = (uint32_t)g_ub; b->do_rc = do_rc ? 1 : 0;
     b->want_text = 1; b->ngroups_dev = b->d_ngroups; b->framed_on_device = 1;
     *b->h_frame_err = FR_ERR_NONE;
-    CK(cudaMemcpyAsync(b->d_raw, src ? src : b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
-    CK(cudaMemsetAsync(b->d_frame_err, 0xFF, 4, b->st));
-    const uint32_t n = (uint32_t)n_reads, fb = (uint32_t)((n_bytes + FR_BLOCK - 1) / FR_BLOCK), nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    nl_count_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk);
-    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_blk, fb, b->d_ngroups);          // total newlines (scratch use of the scalar)
+    // the block offsets were scanned over the whole chunk; newlines at or beyond n_bytes have index >= 2 * n_reads
+    const uint32_t n = (uint32_t)n_reads, fb = (uint32_t)((b->raw_bytes + FR_BLOCK - 1) / FR_BLOCK), nb = (n + SCAN_TILE - 1) / SCAN_TILE;
     nl_index_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, 2 * n, b->d_nl);
     frame_parse_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_nl, n, b->d_seq_off, b->d_seq_len, b->d_name_off, b->d_name_len,
                                                           b->d_line_len, b->d_frame_err);
@@ -2242,10 +2279,14 @@ extern "C" int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_byte
     scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
     scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_ngroups);
     scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_grp_off);
-    b->launches += 7;
+    b->launches += 5;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(b->h_frame_err, b->d_frame_err, 4, cudaMemcpyDeviceToHost, b->st));
     return finish_submit(b);
+}
+extern "C" int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc) {
+    int rc = utb_batch_raw_begin(b, src, n_bytes);
+    return rc ? rc : utb_batch_raw_finish(b, n_bytes, n_reads, do_rc);
 }
 // After the wait of a raw submit: 0 if every record was well formed, else 1 with the index of the first
 // malformed record of the batch and its FE_* code (1 no header '>', 2 sequence begins '>', 4 line too long).

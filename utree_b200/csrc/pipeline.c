@@ -39,6 +39,9 @@ int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
 int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc);
 int utb_batch_frame_error(const utb_batch *b, size_t *record, int *code);
+int utb_batch_raw_begin(utb_batch *b, const char *src, size_t n_bytes);
+int utb_batch_raw_count(utb_batch *b, size_t *n_newlines, int *has_nul);
+int utb_batch_raw_finish(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
 
 #define SLOTS_PER_DEVICE 6                         /* measured on B200: 3 slots 89 ms, 4 slots 78 ms, 6 slots 71 ms per 10 M reads */
 #define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* large enough for the device's partitioned lookup pass on the full-size batches */
@@ -123,7 +126,8 @@ struct utb_searcher {
     size_t max_label;              /* longest label incl. NUL */
     int verbose;                   /* CLI: progress lines on stdout */
     int device_format;             /* output lines built on the GPU (default) or by the host formatter team */
-    int device_frame;              /* records framed on the GPU (default with device_format): the host only counts newlines */
+    int device_frame;              /* records framed on the GPU (default with device_format): the host only needs the newline count */
+    int host_count;                /* ... and counts them itself (UTB_HOST_COUNT=1) instead of waiting for the device's count */
 };
 
 static double now_s(void) {
@@ -147,6 +151,8 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->device_format = !(e && atoi(e) != 0);
     e = getenv("UTB_HOST_FRAME");
     s->device_frame = s->device_format && !(e && atoi(e) != 0);
+    e = getenv("UTB_HOST_COUNT");
+    s->host_count = e && atoi(e) != 0;
     for (uint32_t i = 0; i < ctr->max_ix; ++i) {
         size_t l = ctr->off[i + 1] - ctr->off[i];
         if (l > s->max_label) s->max_label = l;
@@ -891,12 +897,20 @@ read_loop:
 
         sl->src_off = consumed;
         if (device_frame && fill >= 2 && fill < 0xFFFFFFFFull) {
-            /* fast path: count the newlines; the records themselves are framed on the device */
-            nlc_ctx C;
-            C.buf = buf; C.fill = fill;
-            team_run(&rd_team, nlc_part, &C);
+            /* fast path: all the framing needs from here is the newline count of the chunk.  By default the
+             * device counts too -- the chunk goes to the GPU right away and this thread only waits for two
+             * numbers; UTB_HOST_COUNT=1 counts on the host threads instead (utb_count_newlines). */
             size_t n_lines = 0; int nul = 0;
-            for (int p = 0; p < rd_team.n; ++p) { n_lines += C.cnt[p]; nul |= C.has_nul[p]; }
+            if (!s->host_count) {
+                int r1 = utb_batch_raw_begin(sl->b, zero_copy ? buf : NULL, fill);
+                if (!r1) r1 = utb_batch_raw_count(sl->b, &n_lines, &nul);
+                if (r1) { rc = r1; break; }
+            } else {
+                nlc_ctx C;
+                C.buf = buf; C.fill = fill;
+                team_run(&rd_team, nlc_part, &C);
+                for (int p = 0; p < rd_team.n; ++p) { n_lines += C.cnt[p]; nul |= C.has_nul[p]; }
+            }
             const size_t n_rec = n_lines / 2;
             /* left to the host reader: NUL bytes, a last line without '\n' or a dangling header at EOF, more
              * records than the batch arrays hold, a record larger than the buffer */
@@ -910,9 +924,10 @@ read_loop:
                 else if (used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
                 rd_t[2] += now_s() - tp; tp = now_s();
                 if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = n_rec; }
-                int r2 = utb_batch_submit_raw(sl->b, zero_copy ? buf : NULL, used, n_rec, do_rc);
+                int r2 = s->host_count ? utb_batch_submit_raw(sl->b, zero_copy ? buf : NULL, used, n_rec, do_rc)
+                                       : utb_batch_raw_finish(sl->b, used, n_rec, do_rc);
                 if (r2) { rc = r2; break; }
-                R.st.h2d_bytes += used + 4;
+                R.st.h2d_bytes += (s->host_count ? used : fill) + 4;
                 if (seq < 64) R.tl_submit[seq] = now_s() - t0;
                 pthread_mutex_lock(&R.mu);
                 sl->state = 1;
