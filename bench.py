@@ -340,6 +340,10 @@ def main():
             pass
         stream_peak = peaks.get("hbm_gbs", 6650.0)
         rand32 = capi.measure_rand32(local, ws_bytes=8 << 30, loads=1 << 28, iters=3)
+        try:        # the same gather over an L2-resident working set: the ceiling of scattered L2 HITS (probe_kernel's regime)
+            l2_scatter = capi.measure_rand32(local, ws_bytes=32 << 20, loads=1 << 28, iters=3)
+        except Exception:
+            l2_scatter = None
         n_sect = min(n_reads, 100_000)
         sect = oracle_sector_stats(ctr_path, reads_np, rec_bytes, n_sect, ncpu)
         # parity of this very run against the CPU checker on the sample
@@ -408,6 +412,13 @@ def main():
                                  "peak": c[3]} for c in cand],
                     "filter_probes_per_s": round(probes / (part_ms[1] / args.steps * 1e-3), 1) if partitioned else
                                            (round(probes / (det_ms[0] / args.steps * 1e-3), 1) if two_phase else None),
+                    # probe_kernel's probes are L2 hits scattered over a 34 MB filter slice: their hardware ceiling is the
+                    # scattered-sector rate of an L2-resident working set, measured live with the same gather kernel as
+                    # rand32 on 32 MiB
+                    "l2_scatter": ({"sectors_per_s": round(l2_scatter * 1e9 / 32.0, 1), "gbs": round(l2_scatter, 1),
+                                    "probe_kernel_frac": round(probes / (part_ms[1] / args.steps * 1e-3) / (l2_scatter * 1e9 / 32.0), 4)
+                                                         if partitioned else None,
+                                    "how": "utb_measure_rand32 over 32 MiB"} if l2_scatter else None),
                     "phase_a_ms": {"partition_kernel": round(float(part_ms[0] / args.steps), 3), "probe_kernel": round(float(part_ms[1] / args.steps), 3)}
                                   if partitioned else {"filter_kernel": round(float(det_ms[0] / args.steps), 3)},
                     "stream_peak": stream_peak, "stream_peak_kind": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
