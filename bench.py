@@ -8,12 +8,17 @@ of the hot path (pack -> lookup -> vote) over the 10 M reads.
 
   value   : reads/s with the FASTA bytes already resident in HBM, device time
             from CUDA events on the launching stream (utb_batch_rerun_device)
-  e2e     : reads/s through the C ABI with HOST buffers (utb_search_mem:
-            framing, H2D, kernels, D2H, text formatting), wall clock
-  roofline: lookup_kernel, algorithmic bytes (32 B x the sectors the
-            reference's own probe sequence touches, counted by the oracle on a
-            sample) / its CUDA-event time, against the measured random
-            32-byte-sector gather bandwidth of this GPU
+  e2e     : reads/s through the C ABI with HOST buffers (utb_search_mem: H2D of
+            the raw FASTA, framing + search + output formatting on the device,
+            D2H of the text, copy into the caller's buffer), wall clock
+  roofline: the LONGEST kernel of the resident step (every stage kernel is
+            listed in roofline.kernels): algorithmic bytes per launch / its
+            CUDA-event time, against MEASURED_PEAKS.json hbm_gbs for streaming
+            kernels or the live random 32-byte-sector gather bandwidth
+            (utb_measure_rand32) for gather kernels; reference_layout_equiv is
+            SURVEY 8d's figure (32 B x the sectors the reference's own probe
+            sequence touches, counted by the oracle on a sample) over the
+            lookup stage's time
   cpu_baseline / --impl reference: the UNMODIFIED reference binary
             (oracle/_ref/utree-search_gg) on the host cores, same CTR + reads
 
