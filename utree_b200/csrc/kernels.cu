@@ -2058,7 +2058,9 @@ static int launch_stages(utb_batch *b, bool timed) {
                 int per_sm = 0;
                 CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fn, 256, 0));
                 if (per_sm > 4) per_sm = 4;
-                unsigned pgrid = 148u * (unsigned)(per_sm > 0 ? per_sm : 1), n_ctas = gb;
+                int sms = 148;                                      // B200; a co-resident grid must not assume more than the device has
+                if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->db->device) != cudaSuccess || sms < 1) { cudaGetLastError(); sms = 148; }
+                unsigned pgrid = (unsigned)sms * (unsigned)(per_sm > 0 ? per_sm : 1), n_ctas = gb;
                 DevDB dd = d;
                 void *args[] = {&dd, &b->d_pwords, &b->d_ppos, &b->d_pfill, &cap_cp, &n_ctas, &b->d_pctr, &b->d_qwords, &b->d_qslots,
                                 &b->d_qcount, &b->q_cap, &b->d_hits, &b->d_hitmap, &b->d_counters};
