@@ -289,7 +289,7 @@ def main():
         batch.rerun_device(1)
     barrier()
     ms_sum = np.zeros(4)
-    det_ms, det_sect, part_ms = np.zeros(2), [0, 0], np.zeros(2)
+    det_ms, det_sect = np.zeros(2), [0, 0]
     launches = 0
     for _ in range(args.steps):
         ms, l = batch.rerun_device(1)
@@ -297,7 +297,6 @@ def main():
         launches += l
         dm, det_sect = batch.lookup_detail()
         det_ms += np.array(dm)
-        part_ms += np.array(batch.partition_detail())
     barrier()
     dev_s = ms_sum[3] / 1e3
     lookup_mode, hbm_bytes = db.lookup_mode(), int(db.hbm_bytes())
@@ -359,37 +358,29 @@ def main():
         # Reference-layout figure of SURVEY 8d: bytes the reference's own probe sequence would touch.
         ref_bytes = sect["bytes_per_lookup"] * lookups
         ref_equiv = ref_bytes / (lookup_ms * 1e-3) / 1e9
-        partitioned = part_ms[1] > 0
-        filter_bytes = 16.0 * (ctr.num_nodes // 8 + 1024)          # the Bloom filter, read once per partition sweep
+        sieve_lines = ctr.num_nodes // 32 + 1024                    # 128-byte lines of the sieve (SV_RPL records per line)
         n_pos = 32.0 * ((cfg["read_len"] + 1 + 31) // 32) * n_reads  # positions of the packed stream (padded reads)
-        probes = det_sect[0] / 2.0                                  # ONE filter fetch per position serves both strands
+        probes = det_sect[0] / 2.0                                  # ONE sieve fetch per position serves both strands
         surv_ms = det_ms[1] / args.steps
         vote_ms = ms_sum[2] / args.steps
         # candidates: (kernel, ms per launch, algorithmic bytes per launch, peak it is held against)
         cand = []
-        if two_phase and partitioned:
-            pm, qm = part_ms[0] / args.steps, part_ms[1] / args.steps
-            cand.append(("partition_kernel<2> (shared-memory counting sort of positions into 64 filter-slice partitions)", pm,
-                         12.0 * probes + 0.375 * n_pos, "stream",
-                         "packed bases in (0.375 B/position) + one 12 B (word, position) record per valid position out"))
-            cand.append(("probe_kernel<2> (Bloom probes, cooperative sweep of 64 L2-resident filter slices)", qm,
-                         8.0 * probes + filter_bytes + 16.0 * hits, "stream",
-                         "8 B word per valid position + the 2.2 GB filter once + survivors (4 B position in, 12 B queue entry out); "
-                         "the probes themselves are L2 hits"))
-            stage_bytes = 20.0 * probes + 0.375 * n_pos + filter_bytes + 32.0 * det_sect[1]
-        elif two_phase:
-            cand.append(("filter_kernel<2> (Bloom pre-filter, one fetch per position for both strands)", det_ms[0] / args.steps,
-                         32.0 * probes, "rand32", "32 B x one filter sector per valid position"))
-            stage_bytes = 32.0 * (probes + det_sect[1])
+        if two_phase:
+            cand.append(("sieve_kernel<2> (minimizer-keyed blocked Bloom: one 16 B block per position serves both strands, "
+                         "one DRAM line per minimizer run)", det_ms[0] / args.steps,
+                         16.0 * probes + 0.375 * n_pos + 12.0 * det_sect[1], "stream",
+                         "16 B sieve block per valid position + packed bases in (0.375 B/position) + one 12 B queue entry per survivor"))
+            stage_bytes = 16.0 * probes + 0.375 * n_pos + 12.0 * det_sect[1] + 32.0 * det_sect[1]
         elif lookup_mode:
-            cand.append(("lookup_kernel<2,true,false> (key-window search)", lookup_ms, ref_bytes, "rand32", "SURVEY 8d reference-layout bytes"))
-            stage_bytes = ref_bytes
+            cand.append(("lookup_kernel<2,true> (sector hash table, sieve off)", lookup_ms, 32.0 * det_sect[1], "rand32",
+                         "32 B x the table sectors touched, counted on the device"))
+            stage_bytes = 32.0 * det_sect[1]
         else:
-            cand.append(("lookup_kernel<2,false,false> (reference probe sequence)", lookup_ms, ref_bytes, "rand32", "SURVEY 8d reference-layout bytes"))
+            cand.append(("lookup_kernel<2,false> (reference probe sequence)", lookup_ms, ref_bytes, "rand32", "SURVEY 8d reference-layout bytes"))
             stage_bytes = ref_bytes
         if two_phase:
-            cand.append(("queue_lookup_kernel (exact key-window search of the filter survivors)", surv_ms, 32.0 * det_sect[1], "rand32",
-                         "32 B x the sectors the exact path touches (index pair, key windows, aux), counted on the device"))
+            cand.append(("queue_lookup_kernel (exact sector-hash-table lookup of the sieve survivors)", surv_ms, 32.0 * det_sect[1], "rand32",
+                         "32 B x the table sectors the exact lookup touches, counted on the device"))
         cand.append(("vote_thread_kernel (+ vote_warp_kernel / vote_block_kernel for label-rich and long reads; label multiset and aufbau walk)", vote_ms,
                      det_sect[0] / 8.0 + 4.0 * hits + 32.0 * n_reads, "stream",
                      "1 bit per lookup slot of the hit map + 4 B per hit + one 32 B result per read"))
@@ -415,17 +406,11 @@ def main():
                     "kernels": [{"kernel": c[0].split(" ")[0], "ms": round(float(c[1]), 3), "alg_gbs": round(c[2] / (c[1] * 1e-3) / 1e9, 1) if c[1] > 0 else None,
                                  "frac": round(c[2] / (c[1] * 1e-3) / 1e9 / (stream_peak if c[3] == "stream" else rand32), 4) if c[1] > 0 else None,
                                  "peak": c[3]} for c in cand],
-                    "filter_probes_per_s": round(probes / (part_ms[1] / args.steps * 1e-3), 1) if partitioned else
-                                           (round(probes / (det_ms[0] / args.steps * 1e-3), 1) if two_phase else None),
-                    # probe_kernel's probes are L2 hits scattered over a 34 MB filter slice: their hardware ceiling is the
-                    # scattered-sector rate of an L2-resident working set, measured live with the same gather kernel as
-                    # rand32 on 32 MiB
+                    "sieve_probes_per_s": round(probes / (det_ms[0] / args.steps * 1e-3), 1) if two_phase else None,
+                    "sieve_lines": int(sieve_lines),
                     "l2_scatter": ({"sectors_per_s": round(l2_scatter * 1e9 / 32.0, 1), "gbs": round(l2_scatter, 1),
-                                    "probe_kernel_frac": round(probes / (part_ms[1] / args.steps * 1e-3) / (l2_scatter * 1e9 / 32.0), 4)
-                                                         if partitioned else None,
                                     "how": "utb_measure_rand32 over 32 MiB"} if l2_scatter else None),
-                    "phase_a_ms": {"partition_kernel": round(float(part_ms[0] / args.steps), 3), "probe_kernel": round(float(part_ms[1] / args.steps), 3)}
-                                  if partitioned else {"filter_kernel": round(float(det_ms[0] / args.steps), 3)},
+                    "phase_a_ms": {"sieve_kernel": round(float(det_ms[0] / args.steps), 3)} if two_phase else None,
                     "stream_peak": stream_peak, "stream_peak_kind": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback",
                     "kernel_ms": round(float(k_ms), 3), "kernel_share_of_step": round(float(k_ms * args.steps / ms_sum[3]), 4),
                     "lookups_per_launch": lookups,

@@ -13,11 +13,11 @@
  *   XT_read32()            itree.c:733-828   utb_ctr_open + utb_db_upload
  *   readSamplesFPdelim()   itree.c:1202-1223 (inside utb_ctr_open)
  *   XT_doSearch32()        itree.c:833-1108  utb_search_file / utb_search_mem
- *     XT_INITIATE_WS       itree.c:860-901     host framer (pipeline.c)
- *     XT_WORD_SEARCH       itree.c:903-933     pack + lookup kernels
- *     XT_getIX32/xtSuffixBS itree.c:699-730    lookup kernel
+ *     XT_INITIATE_WS       itree.c:860-901     framing kernels (exact host reader behind them)
+ *     XT_WORD_SEARCH       itree.c:903-933     pack + sieve kernels
+ *     XT_getIX32/xtSuffixBS itree.c:699-730    table lookup kernel (or the probe sequence verbatim)
  *     full aufbau vote     itree.c:1028-1098   vote kernels
- *     fprintf lines        itree.c:1032-1096   host formatter (pipeline.c)
+ *     fprintf lines        itree.c:1032-1096   format kernels (host formatter behind them)
  *   main() search branch   itree.c:1357-1377 utb_main
  */
 #ifndef UTREE_B200_H
@@ -65,9 +65,14 @@ int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out);
 void utb_db_free(utb_db *db);
 uint64_t utb_db_hbm_bytes(const utb_db *db);
 /* 1 when every bucket of the CTR is strictly sorted (what utree-compress
- * emits; the first-bin quirk is handled) and the interpolation-start lookup
- * is in use, 0 when the reference's probe sequence is emulated verbatim. */
+ * emits; the first-bin quirk is handled), so the record words are distinct
+ * and the sector hash table (+ sieve) is in use; 0 when the reference's probe
+ * sequence is emulated verbatim on the on-disk image. */
 int utb_db_lookup_mode(const utb_db *db);
+/* A second GPU gets the finished tables from an uploaded one by peer copy
+ * (NVLink) instead of a second upload. */
+int utb_db_clone(const utb_db *src, int device, utb_db **out);
+int utb_db_device(const utb_db *db);
 
 /* ---- per-read result record (what the vote leaves for the formatter) ------ */
 enum { UTB_NONE = 0, UTB_STAR = 1, UTB_WALK = 2 };
@@ -123,15 +128,12 @@ int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len, uint64_t *
 int utb_batch_rerun_device(utb_batch *b, int iters, float ms[4], uint64_t *launches);
 /* Counters of the last submit: valid 32-mer windows x strands (= lookups). */
 int utb_batch_counts(utb_batch *b, uint64_t *lookups, uint64_t *hits);
-/* Two-phase lookup detail of the last run: ms[0] filter kernel, ms[1] survivor
- * kernel; sectors[0] lookups the filter answered (one 32-byte filter sector is
- * fetched per POSITION and serves both strands), sectors[1] sectors the exact
- * search touched for the survivors.  All zero when the single lookup
- * kernel ran (pre-filter off). */
+/* Two-phase lookup detail of the last run: ms[0] sieve kernel, ms[1] survivor
+ * kernel; sectors[0] lookups the sieve answered (one 16-byte block is fetched
+ * per POSITION and serves both strands), sectors[1] table sectors the exact
+ * lookup touched.  ms and sectors[0] are zero when the single lookup kernel
+ * ran (sieve off). */
 int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]);
-/* Large batches split phase A into partition_kernel + probe_kernel (ms[0], ms[1]);
- * both 0 when the direct filter kernel ran. */
-int utb_batch_partition_detail(utb_batch *b, float ms[2]);
 
 /* ---- stage-level entry points (parity tests call the kernels 1:1) --------- */
 /* words[n] (host) -> ix[n] (host): label id or 0xFFFFFFFF, exactly
@@ -163,11 +165,10 @@ int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint64_t *off,
 int utb_frame_records(const char *buf, size_t n, int eof, int threads, size_t max_reads,
                       uint64_t *seq_off, uint32_t *seq_len, uint32_t *name_off, uint32_t *name_len,
                       size_t *n_reads, size_t *used, int *ref_exit);
-/* Host stage of the device-side framing (default when the output text is built
- * on the device): the reader only counts the newlines of a chunk -- lines are
- * read strictly in pairs (itree.c:869-871), so the count fixes the number of
- * complete records -- and checks that no NUL byte occurs; the records are
- * framed by the GPU.  UTB_HOST_FRAME=1 keeps the host framer. */
+/* Newline count and NUL detection of a buffer on the host threads (AVX2).  The
+ * search pipeline no longer needs it -- records are framed on the GPU, the
+ * host only cuts chunks before a line that begins with '>' -- it is kept as a
+ * host stage the CPU tests check the device-side count against. */
 int utb_count_newlines(const char *buf, size_t n, int threads, size_t *n_newlines, int *has_nul);
 /* The reference's output lines (itree.c:1032, 1040, 1096) for n_reads result
  * records; names are taken from bytes[name_off[r] .. +name_len[r]). */
@@ -203,8 +204,12 @@ void utb_searcher_destroy(utb_searcher *s);
  * record, as the reference does. */
 int utb_search_file(utb_searcher *s, const char *fasta_path, const char *out_path,
                     int do_rc, utb_stats *stats, int *ref_exit);
-/* Same with host buffers: fasta[n] in, malloc'ed *out (caller frees with
- * utb_free) of *out_len bytes. */
+/* Same with host buffers: fasta[n] in (a page-locked buffer is copied to the
+ * devices from where it lies), *out / *out_len = the output text.  The text
+ * lives in a page-locked arena that BELONGS TO THE SEARCHER (the devices copy
+ * their lines straight into it): it stays valid until the next search on this
+ * searcher or utb_searcher_destroy, and is kept between searches.  utb_free is
+ * a no-op kept for the round-1 ABI. */
 int utb_search_mem(utb_searcher *s, const char *fasta, size_t n, int do_rc,
                    char **out, size_t *out_len, utb_stats *stats, int *ref_exit);
 void utb_free(void *p);

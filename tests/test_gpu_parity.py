@@ -329,10 +329,10 @@ def test_zero_copy_from_pinned_caller_buffer(gpu, host_format):
         s.destroy()
 
 
-@pytest.mark.parametrize("env", [{"UTB_BLOOM": "0"}, {"UTB_BLOOM": "1"}, {"UTB_LOOKUP": "exact"}])
+@pytest.mark.parametrize("env", [{"UTB_SIEVE": "0"}, {"UTB_SIEVE": "1"}, {"UTB_LOOKUP": "exact"}])
 @pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[2], CASES[5], CASES[7]])
 def test_every_lookup_variant_gives_the_reference_output(ctrs, tmp_path, env, db_name, reads, out, rc):
-    """Whole search with the pre-filter forced off (fused key-window kernel), forced on (two-phase),
+    """Whole search with the sieve forced off (one table lookup per window), forced on (two-phase),
     and with the reference probe sequence: identical bytes."""
     from utree_b200 import capi
     os.environ.update(env)
@@ -349,37 +349,36 @@ def test_every_lookup_variant_gives_the_reference_output(ctrs, tmp_path, env, db
         s.destroy(); ctr.close()
 
 
-@pytest.mark.parametrize("atoms", ["0", "1"])
+@pytest.mark.parametrize("qcap", ["128", "1024"])
 @pytest.mark.parametrize("db_name,reads,out,rc", [CASES[0], CASES[1], CASES[2], CASES[5], CASES[7]])
-def test_partitioned_filter_pass_matches_reference(ctrs, tmp_path, db_name, reads, out, rc, atoms):
-    """UTB_PARTITION=1 forces the large-batch path (shared-memory counting sort into 64 filter-slice
-    partitions + cooperative probe sweep) on small inputs, with the match-ranked and the atomic-ranked
-    partitioner: identical bytes.  The input is repeated so that every partitioner CTA sees several tiles."""
+def test_survivor_queue_overflow_resolves_inline(ctrs, tmp_path, db_name, reads, out, rc, qcap):
+    """UTB_QCAP shrinks the survivor queue to one / eight chunks, so almost every sieve survivor takes the
+    overflow path (exact lookup inside the sieve kernel) and the consumer sees a full queue whose capacity
+    is a whole number of chunks: identical bytes, no entry read that was never written.  The input is
+    repeated so that every persistent warp walks several tiles."""
     from utree_b200 import capi
-    os.environ["UTB_PARTITION"] = "1"
-    os.environ["UTB_BLOOM"] = "1"
+    os.environ["UTB_QCAP"] = qcap
+    os.environ["UTB_SIEVE"] = "1"
     try:
         ctr = capi.Ctr(ctrs[db_name])
         s = capi.Searcher(ctr, devices=(0,), host_threads=3)
     finally:
-        del os.environ["UTB_PARTITION"], os.environ["UTB_BLOOM"]
-    os.environ["UTB_PART_ATOMS"] = atoms
+        del os.environ["UTB_QCAP"], os.environ["UTB_SIEVE"]
     try:
         reps = 24 if reads != "long_reads.fa" else 2
         data = open(gold(reads), "rb").read()
         code, ref_exit, text, st = s.search_mem(data * reps, do_rc=bool(rc))
         assert code == 0 and text == open(gold(out), "rb").read() * reps
     finally:
-        del os.environ["UTB_PART_ATOMS"]
         s.destroy(); ctr.close()
 
 
-@pytest.mark.parametrize("mode", ["device_count", "host_count", "host_frame"])
+@pytest.mark.parametrize("mode", ["device", "host_frame"])
 def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, mode):
-    """Records framed on the GPU (the host only counts newlines): several batches with a carried tail,
-    CRLF / tab-in-header / empty-line records, and a malformed record deep in the input -- the reader
-    rewinds to that batch and the host framer reproduces the reference's partial output and exit code.
-    The newline count comes from the device (default) or from the host threads (UTB_HOST_COUNT=1);
+    """Records framed on the GPU (the host only cuts chunks before a line that begins with '>' and never waits
+    for the device): several batches with a carried tail, CRLF / tab-in-header / empty-line records, and
+    malformed input deep in the stream -- the device flags the chunk or the record, the reader rewinds to
+    that batch and the host framer reproduces the reference's partial output and exit code.
     UTB_HOST_FRAME=1 (host framer throughout) must give the same bytes."""
     from utree_b200 import capi
     one = open(gold("toyA_reads.fa"), "rb").read()
@@ -391,12 +390,10 @@ def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, mode):
     os.environ["UTB_BATCH_MB"] = "33"
     if mode == "host_frame":
         os.environ["UTB_HOST_FRAME"] = "1"
-    if mode == "host_count":
-        os.environ["UTB_HOST_COUNT"] = "1"
     try:
         s = capi.Searcher(gpu["toyA"][0], devices=(0, 0), host_threads=5)
     finally:
-        os.environ.pop("UTB_BATCH_MB", None); os.environ.pop("UTB_HOST_FRAME", None); os.environ.pop("UTB_HOST_COUNT", None)
+        os.environ.pop("UTB_BATCH_MB", None); os.environ.pop("UTB_HOST_FRAME", None)
     try:
         rc, ex, text, st = s.search_mem(one * reps, do_rc=True)
         assert rc == 0 and st["batches"] >= 2 and st["reads"] == reps * one.count(b">")
@@ -409,6 +406,18 @@ def test_device_framing_across_batches_and_restart_on_a_bad_record(gpu, mode):
         # sequence line begins '>' inside the first batch
         rc, ex, text, st = s.search_mem(one + b">x\n>y\n" + one * reps, do_rc=True)
         assert (rc, ex) == (3, 2) and text == want
+        # an EARLIER malformed record decides, also when the reader itself stops on a later error (dangling header
+        # without newline in the final, host-framed chunk)
+        rc, ex, text, st = s.search_mem(one * reps + b"ACGT\nACGT\n" + one * reps + b">dangling", do_rc=True)
+        assert (rc, ex) == (3, 2) and text == want * reps
+        assert b"no header" in capi.lib().utb_last_error()
+        # a stray empty line shifts the pairing (the line count of the chunk before the next '>' is odd): header
+        # "" of the next pair has no '>' (itree.c:880)
+        rc, ex, text, st = s.search_mem(one + b"\n" + one * reps, do_rc=True)
+        assert (rc, ex) == (3, 2) and text == want
+        # two anomalies that keep the line count even: ">x" takes ">y" as its sequence
+        rc, ex, text, st = s.search_mem(one * 3 + b">x\n>y\nACGT\n>z\n" + one * reps, do_rc=True)
+        assert (rc, ex) == (3, 2) and text == want * 3
         # a NUL byte in the chunk: the count flags it and the exact host reader takes the batch
         # (strlen() semantics, itree.c:887: the sequence ends at the NUL)
         first = one.split(b"\n", 2)

@@ -47,7 +47,7 @@ EXPORTS = [
     "utb_device_count", "utb_db_upload", "utb_db_free", "utb_db_hbm_bytes", "utb_db_lookup_mode",
     "utb_batch_create", "utb_batch_destroy", "utb_batch_bytes", "utb_batch_seq_off", "utb_batch_seq_len",
     "utb_batch_max_bytes", "utb_batch_max_reads", "utb_read_slots", "utb_batch_max_slots",
-    "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail", "utb_batch_partition_detail",
+    "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail", "utb_db_clone", "utb_db_device",
     "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_vote_hits_sparse", "utb_frame_records", "utb_count_newlines", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
     "utb_main", "utb_measure_rand32", "utb_compress_ubt", "utb_compress_main",
@@ -225,9 +225,17 @@ class Db:
         return lib().utb_db_hbm_bytes(self.h)
 
     def lookup_mode(self):
-        """1: interpolation-start search (regular CTR); 0: reference probe sequence."""
+        """1: sector hash table (+ sieve) on a regular CTR; 0: reference probe sequence."""
         lib().utb_db_lookup_mode.argtypes = [C.c_void_p]
         return lib().utb_db_lookup_mode(self.h)
+
+    def clone(self, device):
+        """The finished tables copied to another GPU (peer copy; utb_db_clone)."""
+        other = Db.__new__(Db)
+        other.ctr, other.h = self.ctr, C.c_void_p()
+        lib().utb_db_clone.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        _ck(lib().utb_db_clone(self.h, device, C.byref(other.h)))
+        return other
 
     def free(self):
         if self.h:
@@ -277,12 +285,6 @@ class Batch:
         lib().utb_batch_lookup_detail.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
         _ck(lib().utb_batch_lookup_detail(self.h, ms, sec))
         return [ms[0], ms[1]], [sec[0], sec[1]]
-
-    def partition_detail(self):
-        ms = (C.c_float * 2)()
-        lib().utb_batch_partition_detail.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
-        _ck(lib().utb_batch_partition_detail(self.h, ms))
-        return [ms[0], ms[1]]
 
     def destroy(self):
         if self.h:

@@ -6,8 +6,9 @@
 //             (8 B when numNodes >= 2^32-1)                  itree.c:756-759
 //   recs    : the CTR record blob exactly as on disk, numNodes x SZ bytes,
 //             SZ = 5-byte suffix + IXTYPE id, + 32 B slack   itree.c:766
-//             (irregular CTRs only; regular ones are re-laid out once at upload
-//             into key / aux words, see DevDB, and get a Bloom filter)
+//             (kept for irregular CTRs only; regular ones are re-keyed once at
+//             upload into ktab, a sector hash table, and get the sieve, a
+//             minimizer-keyed blocked Bloom filter -- see DevDB)
 //   labels  : blob of NUL-terminated strings, off[], rank[], by_rank[]
 // Per batch (one stream slot):
 //   raw     : the FASTA bytes as read from the file (headers included)
@@ -22,21 +23,19 @@
 //   results : one utb_result per read;  text : the output lines
 //
 // Kernels: nl_count / nl_index / frame_parse (XT_INITIATE_WS, itree.c:860-901),
-// pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926), filter_kernel or
-// partition_kernel + probe_kernel (membership pre-filter, one fetch per position
-// for both strands) and queue_lookup_kernel (XT_getIX32 + xtSuffixBS on the
+// pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926), sieve_kernel
+// (membership pre-filter, one 16-byte fetch per position for both strands, one DRAM
+// line per ~9 positions) and queue_lookup_kernel (XT_getIX32 + xtSuffixBS on the
 // survivors, itree.c:699-730), lookup_kernel (the same without pre-filter, or the
 // reference's exact probe sequence), vote_thread / vote_warp / vote_block (full
 // aufbau vote, itree.c:1028-1098), fmt_* (the fprintf lines, itree.c:1032-1096).
 #include <cuda_runtime.h>
-#include <cooperative_groups.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "utb_internal.h"
 
-namespace cg = cooperative_groups;
 #define SUFMASK 0xFFFFFFFFFFull
 #define HIT_MISS 0xFFFFFFFFu   // looked up, not found (BAD_IX widened)
 #define HIT_NOWIN 0xFFFFFFFEu  // no valid 32-mer window here: no lookup made
@@ -55,7 +54,7 @@ namespace cg = cooperative_groups;
 // device-side database view (passed by value to kernels)
 // ---------------------------------------------------------------------------
 struct DevDB {
-    const uint32_t *binix32;   // one of binix32 / binix64 is non-null
+    const uint32_t *binix32;   // one of binix32 / binix64 is non-null while the on-disk image is resident
     const uint64_t *binix64;
     const uint8_t *recs;
     uint64_t num_nodes;
@@ -67,28 +66,29 @@ struct DevDB {
     const uint32_t *rank;
     const uint32_t *by_rank;
     uint32_t quirk_bin;        // bucket whose record 0 is the folded foreign record, else 0xFFFFFFFF
-    // regular CTRs only: structure-of-arrays copy of the records (recs is then freed)
-    const uint32_t *kv;        // IXTYPE uint16_t: blocks of 16 records = one 128-byte line, 16 keys (suffix >> 8) then their
-                               // 16 aux words (suffix & 0xFF | id << 8): the line a key window misses on also holds its aux
-    const uint32_t *keys;      // IXTYPE uint32_t: suffix >> 8 ...
-    const uint64_t *aux64;     // ... and suffix & 0xFF | id << 8 in a second array
-    // membership pre-filter over all record words (register-blocked Bloom, 16-byte blocks)
-    const uint4 *bloom;
-    uint64_t bloom_blocks;
+    // regular CTRs only: the records re-keyed into a sector hash table (binix / recs are then freed)
+    const uint64_t *ktab;      // kt_sectors x 4 entries of 8 bytes
+    const uint32_t *kvals;     // IXTYPE uint32_t: the label ids, parallel to ktab (null for uint16_t: the id is in the entry)
+    uint64_t kt_sectors;
+    // membership pre-filter over all record words: blocked Bloom, line chosen by the word's minimizer
+    const uint2 *sieve;        // sv_lines x 16 blocks of 8 bytes
+    uint64_t sv_lines;
 };
 
 struct utb_db {
     int device;
     DevDB d;
-    int regular;               // every bucket strictly sorted (modulo quirk_bin): interpolation search is exact
-    int use_interp;            // lookup kernel variant in use
-    void *binix, *recs, *blob, *off, *rank, *by_rank, *keys, *aux, *bloom;
-    int bloom_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
+    int regular;               // every bucket strictly sorted (modulo quirk_bin): the record words are distinct, a hash table is exact
+    int use_table;             // lookup variant in use: 1 sector hash table (+ sieve), 0 the reference's probe sequence
+    void *binix, *recs, *blob, *off, *rank, *by_rank, *ktab, *kvals, *sieve;
+    int sieve_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
     volatile double ema_hit_rate;   // of the batches seen so far (written by the formatter thread, read at submit)
     size_t max_label;          // longest label, bytes
-    volatile double text_per_read;  // running estimate of output bytes per read (sizes the speculative text D2H)
+    volatile double text_per_byte;  // running estimate of output bytes per input byte (sizes the speculative text D2H)
     uint64_t hbm_bytes;
-    int l2_window;             // persisting-L2 window over binix configured
+    int sm_count;              // multiprocessors of the device (grid sizing)
+    size_t nb_binix, nb_recs, nb_blob, nb_lab, nb_ktab, nb_kvals, nb_sieve;   // bytes behind the device pointers (utb_db_clone)
+    int l2_window;             // reference probe sequence only: persisting-L2 window over binix configured
     size_t l2_window_bytes;
     float l2_hit_ratio;
 };
@@ -110,47 +110,56 @@ __device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &badbits) {
     return ((code & 3u) << 6) | (((code >> 8) & 3u) << 4) | (((code >> 16) & 3u) << 2) | ((code >> 24) & 3u);
 }
 
+// reverse complement of a 32-mer word: reverse the 2-bit fields of ~w
+__device__ __forceinline__ uint64_t revcomp_word(uint64_t w) {
+    uint64_t x = __brevll(~w);
+    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+}
+// pkr (optional): the reverse complement of every packed group, so that the reverse-complement window of a
+// position is a funnel shift of two pkr words exactly as the forward window is one of two pk words
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_off,
             const uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ grp_off,
-            uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ n_groups_dev,
-            uint64_t *__restrict__ pk, uint32_t *__restrict__ bad) {
-    if (n_groups_dev) n_groups = *n_groups_dev;                    // device-side framing: the host only knows an upper bound
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g > n_groups) return;
-    if (g == n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; return; }   // guard group
-    // read owning group g: largest r with grp_off[r] <= g
-    uint32_t lo = 0, hi = n_reads;                     // invariant: grp_off[lo] <= g < grp_off[hi]
-    while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(grp_off + mid) <= g) lo = mid; else hi = mid;
-    }
-    uint32_t k = g - __ldg(grp_off + lo);
-    uint32_t len = __ldg(seq_len + lo);
-    uint32_t b0 = k * 32u;
-    uint32_t nv = len > b0 ? min(32u, len - b0) : 0u;  // real bases in this group
-    uint64_t word = 0;
-    uint32_t badm = 0;
-    if (nv) {
-        uint64_t a = __ldg(seq_off + lo) + b0;
-        const uint32_t *p = reinterpret_cast<const uint32_t *>(raw + (a & ~3ull));
-        uint32_t sh = (uint32_t)(a & 3u) * 8u;
-        uint32_t nw = (nv + 3u) >> 2;                  // 4-byte words that hold real bases
-        uint32_t prev = __ldg(p);
-#pragma unroll
-        for (uint32_t j = 0; j < 8; ++j) {
-            uint32_t cur = (j < nw) ? __ldg(p + j + 1) : 0u;   // p[j+1] only if word j is needed
-            uint32_t w = __funnelshift_r(prev, cur, sh);
-            prev = cur;
-            uint32_t bb;
-            uint32_t c = classify4(w, bb);
-            word = (word << 8) | c;
-            badm |= bb << (4u * j);
+            uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ dims,
+            uint64_t *__restrict__ pk, uint32_t *__restrict__ bad, uint64_t *__restrict__ pkr) {
+    if (dims) { n_reads = dims[0]; n_groups = dims[1]; }          // device-side framing: the host only knows upper bounds
+    for (uint64_t g64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g64 <= n_groups; g64 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)g64;
+        if (g == n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; break; }   // guard group
+        // read owning group g: largest r with grp_off[r] <= g
+        uint32_t lo = 0, hi = n_reads;                     // invariant: grp_off[lo] <= g < grp_off[hi]
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(grp_off + mid) <= g) lo = mid; else hi = mid;
         }
+        uint32_t k = g - __ldg(grp_off + lo);
+        uint32_t len = __ldg(seq_len + lo);
+        uint32_t b0 = k * 32u;
+        uint32_t nv = len > b0 ? min(32u, len - b0) : 0u;  // real bases in this group
+        uint64_t word = 0;
+        uint32_t badm = 0;
+        if (nv) {
+            uint64_t a = __ldg(seq_off + lo) + b0;
+            const uint32_t *p = reinterpret_cast<const uint32_t *>(raw + (a & ~3ull));
+            uint32_t sh = (uint32_t)(a & 3u) * 8u;
+            uint32_t nw = (nv + 3u) >> 2;                  // 4-byte words that hold real bases
+            uint32_t prev = __ldg(p);
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j) {
+                uint32_t cur = (j < nw) ? __ldg(p + j + 1) : 0u;   // p[j+1] only if word j is needed
+                uint32_t w = __funnelshift_r(prev, cur, sh);
+                prev = cur;
+                uint32_t bb;
+                uint32_t c = classify4(w, bb);
+                word = (word << 8) | c;
+                badm |= bb << (4u * j);
+            }
+        }
+        if (nv < 32u) badm |= 0xFFFFFFFFu << nv;           // padding positions are bad
+        pk[g] = word;
+        bad[g] = badm;
+        if (pkr) pkr[g] = revcomp_word(word);
     }
-    if (nv < 32u) badm |= 0xFFFFFFFFu << nv;           // padding positions are bad
-    pk[g] = word;
-    bad[g] = badm;
 }
 
 // ---------------------------------------------------------------------------
@@ -166,11 +175,6 @@ __device__ __forceinline__ bool window_at(const uint64_t *__restrict__ pk, const
     return wb == 0;
 }
 
-// reverse complement of a 32-mer word: reverse the 2-bit fields of ~w
-__device__ __forceinline__ uint64_t revcomp_word(uint64_t w) {
-    uint64_t x = __brevll(~w);
-    return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
-}
 
 // ---------------------------------------------------------------------------
 // lookup: XT_getIX32 + xtSuffixBS, the reference's probe sequence verbatim
@@ -245,164 +249,94 @@ __device__ __forceinline__ uint32_t probe_end(const DevDB &db, const Probe &q) {
 }
 
 
-// ---- key-window search (regular CTRs only) -----------------------------------
-// What bounds the exact-probe kernel is not bytes but the chain of dependent
-// loads a warp has to wait for (profiles/r01_*: DRAM ~35 % busy, all warps
-// resident, ~8 serialized round trips per lookup).  For a regular CTR (every
-// bucket strictly sorted -- verified on the device at upload) the records are
-// therefore re-laid out once, at load time, into 32-bit words:
-//     key[i] = suffix >> 8          aux[i] = suffix & 0xFF | id << 8
-// (uint16_t labels: blocks of 16 keys followed by their 16 aux words, one
-// 128-byte line per block; uint32_t labels: two arrays).
-// Suffixes are close to uniform inside a bucket, so record a + n*s/2^40 is
-// within a few slots of the answer: ONE aligned 32-byte sector around it
-// holds 8 candidate keys, which are ranked branch-free in registers.  A
-// lookup is then index -> key line -> (hits only) aux: 2-3 dependent steps
-// instead of ~8, and ~1.3 random DRAM fetches instead of ~5.  On a strictly
-// sorted bucket any exact membership test returns what xtSuffixBS returns, so
-// the result is identical; CTRs that are not regular keep the exact kernel.
-enum { FW_MISS = 0, FW_FOUND = 1, FW_LEFT = 2, FW_RIGHT = 3, FW_SLOW = 4 };
-#define KW 8u                   // keys per window = one 32-byte sector
-struct FastProbe {
-    uint64_t a, b;      // bucket [a,b), quirk-adjusted
-    uint64_t ws;        // first key of the current window (multiple of KW)
-    uint64_t pos;       // FW_FOUND: index of the first key equal to t in the window
-    uint32_t cnt;       // FW_FOUND: length of the run of equal keys (records that differ only in the suffix's low byte)
-    uint32_t t, lo8;    // target key and the suffix's low byte
-    int st;
-};
-__device__ __forceinline__ void fast_begin(const DevDB &db, uint64_t word, FastProbe &q) {
-    uint64_t p = word >> 40;
-    uint64_t a, b;
-    if (db.binix32) { a = __ldg(db.binix32 + p); b = __ldg(db.binix32 + p + 1); }
-    else { a = __ldg(db.binix64 + p); b = __ldg(db.binix64 + p + 1); }
-    uint64_t suf = word & SUFMASK;
-    q.t = (uint32_t)(suf >> 8); q.lo8 = (uint32_t)(suf & 0xFFu);
-    bool live = a < b && b <= db.num_nodes;                        // itree.c:726 (+ bounds guard)
-    if (live && (uint32_t)p == db.quirk_bin) { a += 1; live = a < b; }   // record 0 is unreachable for xtSuffixBS
-    q.a = a; q.b = b; q.pos = 0; q.cnt = 0;
-    q.st = live ? FW_LEFT : FW_MISS;                               // any non-final state: "window pending"
-    q.ws = live ? ((a + __umul64hi(suf << 24, b - a)) & ~(uint64_t)(KW - 1)) : 0;   // a + floor(n*s/2^40) < b
+// ---- sector hash table (regular CTRs only) -----------------------------------
+// What bounds an exact lookup on the device is the chain of dependent random
+// DRAM accesses (profiles/r01_*: the reference's bisection makes ~8 round trips,
+// index -> interpolated key window -> aux still 3).  For a regular CTR (every
+// bucket strictly sorted -- verified on the device at upload -- so all record
+// words are distinct and any exact membership test returns what xtSuffixBS
+// returns) the records are therefore re-keyed once, at load time, into an open-
+// addressing table whose bucket is one 32-byte sector:
+//     h = mix64(word)  (a bijection)      home sector = floor(h * S / 2^64)
+//     entry (8 B) = low 48 bits of h << 16 | tag        4 entries per sector
+// uint16_t labels: tag = 0xFFFF - id (never 0: 0xFFFE/0xFFFF are the builder's
+// sentinels, itree.c:105-107); uint32_t labels: tag = 1 and the id sits in a
+// parallel u32 array.  An entry that does not fit its home sector goes to the
+// next one (linear probing over sectors, displacement <= KT_MAXD, load <= 0.5),
+// so a lookup is ONE random 32-byte access (1.06 on average) with no index in
+// front of it.  Uniqueness of the 48-bit remainder: an entry found within
+// KT_MAXD sectors of the probe's home has a hash within (KT_MAXD+1) * 2^64 / S
+// <= 2^48 of the probe's (S >= KT_MIN_SECTORS), so equal low 48 bits mean equal
+// hashes, hence equal words.
+#define KT_MAXD 63u
+#define KT_MIN_SECTORS ((uint64_t)(KT_MAXD + 1u) << 16)
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {           // murmur3 finaliser: invertible
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
+    return x ^ (x >> 33);
 }
-// One sector of keys around the estimate.  The miss fills the whole 128-byte
-// line in L2, so the neighbouring sectors a later step may need are L2 hits;
-// asking for them up front would cost as much as further misses
-// (profiles/r01_membench_ncu.txt).
-__device__ __forceinline__ uint64_t kv_index(uint64_t i) { return ((i >> 4) << 5) | (i & 15u); }   // u32 index of key i in db.kv
-__device__ __forceinline__ uint32_t key_at(const DevDB &db, uint64_t i) { return db.kv ? __ldg(db.kv + kv_index(i)) : __ldg(db.keys + i); }
-__device__ __forceinline__ void window_fetch(const DevDB &db, const FastProbe &q, uint4 &k0, uint4 &k1) {
-    const uint4 *p = reinterpret_cast<const uint4 *>(db.kv ? db.kv + kv_index(q.ws) : db.keys + q.ws);   // ws is a multiple of 8
-    k0 = __ldg(p); k1 = __ldg(p + 1);
-}
-__device__ __forceinline__ void window_rank(FastProbe &q, const uint4 &k0, const uint4 &k1) {
-    const uint32_t kk[KW] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
-    const uint64_t wa = q.ws > q.a ? q.ws : q.a, wb = q.ws + KW < q.b ? q.ws + KW : q.b;
-    const uint32_t j0 = (uint32_t)(wa - q.ws), j1 = (uint32_t)(wb - q.ws);   // in-bucket slots [j0, j1)
-    uint32_t lt = 0, eq = 0;
+// sect (optional): 32-byte sectors this lookup touched
+__device__ __forceinline__ uint32_t kt_lookup(const DevDB &db, uint64_t word, uint32_t *sect = nullptr) {
+    const uint64_t h = mix64(word), rem = h << 16;
+    uint64_t s = __umul64hi(h, db.kt_sectors);
+    uint32_t ns = 0, r = HIT_MISS;
+    for (uint32_t d = 0; d <= KT_MAXD; ++d) {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(db.ktab + s * 4);
+        const ulonglong2 a = __ldg(p), b = __ldg(p + 1);
+        const uint64_t e[4] = {a.x, a.y, b.x, b.y};
+        ++ns;
+        int at = -1;
+        uint32_t tag = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < KW; ++j) {
-        bool in = j >= j0 && j < j1;
-        lt += in && kk[j] < q.t;
-        eq += in && kk[j] == q.t;
-    }
-    const bool left_open = wa > q.a, right_open = wb < q.b;
-    if (eq == 0) {
-        if (lt == 0 && left_open) { q.st = FW_LEFT; q.ws -= KW; }             // every key here is larger
-        else if (lt == j1 - j0 && right_open) { q.st = FW_RIGHT; q.ws += KW; } // every key here is smaller
-        else q.st = FW_MISS;
-    } else { q.st = FW_FOUND; q.pos = wa + lt; q.cnt = eq; }       // eq > 1: k-mers of related genomes that differ in the last 4 bases
-}
-__device__ __forceinline__ uint64_t load_aux(const DevDB &db, uint64_t i) {
-    return db.kv ? (uint64_t)__ldg(db.kv + kv_index(i) + 16u) : __ldg(db.aux64 + i);
-}
-// rare: exact lower bound over the whole bucket on the full 40-bit suffix
-__device__ __noinline__ uint32_t fast_slow(const DevDB &db, uint64_t a, uint64_t b, uint32_t t, uint32_t lo8) {
-    const uint64_t s = ((uint64_t)t << 8) | lo8;
-    uint64_t lo = a, hi = b;
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        uint64_t c = ((uint64_t)key_at(db, mid) << 8) | (load_aux(db, mid) & 0xFFu);
-        if (c < s) lo = mid + 1; else hi = mid;
-    }
-    if (lo >= b) return HIT_MISS;
-    uint64_t ax = load_aux(db, lo);
-    if ((((uint64_t)key_at(db, lo) << 8) | (ax & 0xFFu)) != s) return HIT_MISS;
-    uint32_t ix = (uint32_t)(ax >> 8);
-    return ix < db.max_ix ? ix : HIT_MISS;
-}
-#define FW_MAX_STEPS 4          // sectors inspected before giving up on the estimate
-// sect: 32-byte sectors this lookup had to touch (index pair, key windows, aux)
-template <int N>
-__device__ __forceinline__ void fast_lookup(const DevDB &db, const uint64_t (&w)[N], uint32_t (&r)[N], uint32_t *sect = nullptr) {
-    FastProbe q[N];
-    uint32_t ns = 0;
-#pragma unroll
-    for (int i = 0; i < N; ++i) fast_begin(db, w[i], q[i]);
-    int dir[N];
-    bool act[N];
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        ns += ((w[i] >> 40) & 7u) == 7u ? 2u : 1u;                 // BinIx[p], BinIx[p+1]: 4-byte entries, 8 per sector
-        dir[i] = 0; act[i] = q[i].st != FW_MISS;                   // empty bucket: nothing to search
-    }
-    // the N searches advance in lock-step: all key sectors of a step are requested before any is ranked
-    for (int step = 0; step < FW_MAX_STEPS; ++step) {
-        bool any = false;
-#pragma unroll
-        for (int i = 0; i < N; ++i) any |= act[i];
-        if (!any) break;
-        uint4 k0[N], k1[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) if (act[i]) { ++ns; window_fetch(db, q[i], k0[i], k1[i]); }
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            if (!act[i]) continue;
-            window_rank(q[i], k0[i], k1[i]);
-            if (q[i].st != FW_LEFT && q[i].st != FW_RIGHT) act[i] = false;
-            else if (dir[i] && q[i].st != dir[i]) { q[i].st = FW_MISS; act[i] = false; }   // turned around: between two adjacent windows
-            else dir[i] = q[i].st;
+        for (int j = 0; j < 4; ++j) if (e[j] && ((e[j] ^ rem) >> 16) == 0) { at = j; tag = (uint32_t)(e[j] & 0xFFFFu); }
+        if (at >= 0) {
+            uint32_t ix;
+            if (db.kvals) { ix = __ldg(db.kvals + s * 4 + at); ++ns; }
+            else ix = 0xFFFFu - tag;
+            r = ix < db.max_ix ? ix : HIT_MISS;                    // itree.c:929
+            break;
         }
-    }
-#pragma unroll
-    for (int i = 0; i < N; ++i) if (q[i].st == FW_LEFT || q[i].st == FW_RIGHT) q[i].st = FW_SLOW;   // estimate off by several sectors
-    // matches fetch low byte + id of every record in the run of equal keys (one sector of aux); a neighbour key is
-    // checked when the run touches an open window edge, because it could continue outside
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-        r[i] = HIT_MISS;
-        if (q[i].st == FW_FOUND) {
-            ++ns;
-            const uint64_t wa = q[i].ws > q[i].a ? q[i].ws : q[i].a, wb = q[i].ws + KW < q[i].b ? q[i].ws + KW : q[i].b;
-            uint32_t nbl = ~q[i].t, nbr = ~q[i].t;
-            if (q[i].pos == wa && wa > q[i].a) nbl = key_at(db, q[i].pos - 1);
-            if (q[i].pos + q[i].cnt == wb && wb < q[i].b) nbr = key_at(db, q[i].pos + q[i].cnt);
-            uint64_t ax[KW];
-#pragma unroll
-            for (uint32_t j = 0; j < KW; ++j) ax[j] = j < q[i].cnt ? load_aux(db, q[i].pos + j) : 0;
-            if (nbl == q[i].t || nbr == q[i].t) q[i].st = FW_SLOW; // the run of equal keys crosses the window
-            else {
-#pragma unroll
-                for (uint32_t j = 0; j < KW; ++j)
-                    if (j < q[i].cnt && (uint32_t)(ax[j] & 0xFFu) == q[i].lo8) { const uint32_t ix = (uint32_t)(ax[j] >> 8); r[i] = ix < db.max_ix ? ix : HIT_MISS; }
-            }
-        }
-        if (q[i].st == FW_SLOW) { r[i] = fast_slow(db, q[i].a, q[i].b, q[i].t, q[i].lo8); ns += 8; }
+        if (!(e[0] && e[1] && e[2] && e[3])) break;                // a free slot: the word was never displaced past here
+        if (++s == db.kt_sectors) s = 0;
     }
     if (sect) *sect = ns;
+    return r;
 }
-
-// raw CTR records -> SoA (runs once at upload, only for regular CTRs)
+// G lanes per prefix bin walk the bin's records (bins are taken as the index gives them, itree.c:722-726)
+template <int G>
 __global__ void __launch_bounds__(256)
-relayout_kernel(DevDB db, uint32_t *__restrict__ kv, uint32_t *__restrict__ keys, uint64_t *__restrict__ aux64) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= db.num_nodes) return;
-    uint64_t suf = load_suffix(db.recs, i * db.sz);
-    uint32_t ix = load_ix(db, i);
-    if (kv) { kv[kv_index(i)] = (uint32_t)(suf >> 8); kv[kv_index(i) + 16u] = (uint32_t)(suf & 0xFFu) | (ix << 8); }
-    else { keys[i] = (uint32_t)(suf >> 8); aux64[i] = (suf & 0xFFu) | ((uint64_t)ix << 8); }
+ktab_build_kernel(DevDB db, unsigned long long *__restrict__ ktab, uint32_t *__restrict__ kvals, uint64_t n_sectors,
+                  uint32_t *__restrict__ overflow) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p = t / G;
+    const uint32_t gl = (uint32_t)(t % G);
+    if (p >= UTB_NUMBINS - 1) return;
+    uint64_t a, b;
+    if (db.binix32) { a = db.binix32[p]; b = db.binix32[p + 1]; }
+    else { a = db.binix64[p]; b = db.binix64[p + 1]; }
+    if (a >= b || b > db.num_nodes) return;
+    if ((uint32_t)p == db.quirk_bin) ++a;                          // the folded record is unreachable for xtSuffixBS
+    for (uint64_t i = a + gl; i < b; i += G) {
+        const uint64_t word = (p << 40) | load_suffix(db.recs, i * db.sz);
+        const uint32_t ix = load_ix(db, i);
+        const uint64_t h = mix64(word);
+        const unsigned long long entry = (h << 16) | (kvals ? 1ull : (unsigned long long)(0xFFFFu - (ix & 0xFFFFu)));
+        if (!kvals && ix >= 0xFFFEu) continue;                     // sentinel ids never pass ix < maxIX (itree.c:929)
+        uint64_t s = __umul64hi(h, n_sectors);
+        bool placed = false;
+        for (uint32_t d = 0; d <= KT_MAXD && !placed; ++d) {
+#pragma unroll
+            for (int j = 0; j < 4 && !placed; ++j) {
+                if (ktab[s * 4 + j]) continue;
+                if (atomicCAS(ktab + s * 4 + j, 0ull, entry) == 0ull) { placed = true; if (kvals) kvals[s * 4 + j] = ix; }
+            }
+            if (!placed && ++s == n_sectors) s = 0;
+        }
+        if (!placed) atomicAdd(overflow, 1u);
+    }
 }
 
-// Load-time check of the invariant the interpolation search relies on.
+// Load-time check of the invariant the table relies on.
 // out[0] buckets with a disorder past their first pair (or an index beyond the blob)
 // out[1] buckets whose only disorder is record0 >= record1   out[2] smallest such bin
 // out[3] first non-empty bin
@@ -427,68 +361,98 @@ verify_kernel(DevDB db, unsigned long long *__restrict__ out) {
     else if (first_bad) { atomicAdd(out + 1, 1ull); atomicMin(out + 2, (unsigned long long)p); }
 }
 
-// ---- membership pre-filter ----------------------------------------------------
-// Most 32-mers of a read are not in a sampled tree (complevel 2 keeps 1/16 of
-// the k-mers), and every miss costs the exact path ~2.6 random DRAM fetches.
-// A register-blocked Bloom filter over the record words, built on the device
-// at upload, answers "certainly absent" with ONE 16-byte load: block =
-// 4 x u32, two bits per word, all eight tests on registers.  No false negatives,
-// so a filtered miss is a miss of XT_getIX32 too; positives take the exact path.
-//
-// The BLOCK of a word x is chosen by its strand-neutral form c = min(x, revcomp(x)),
-// the eight BITS by x itself.  A read position looks up x and revcomp(x)
-// (itree.c:887-898 appends the reverse complement, so both strands of every
-// window are searched): both share c, hence both tests are served by the same
-// 16-byte load -- one scattered fetch per POSITION instead of one per lookup.
-// Each record still sets eight bits of one block, so the false-positive rate is
-// that of the plain blocked filter (~0.1 % at 16 bits per record).
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
-    x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
-    return x ^ (x >> 33);
+// ---- minimizer-keyed sieve (membership pre-filter) -------------------------------
+// Most 32-mers of a read are not in a sampled tree (complevel 2 keeps 1/16 of the
+// k-mers), so a blocked Bloom filter over the record words, built on the device at
+// upload, answers "certainly absent" before the exact table is touched.  No false
+// negatives, so a filtered miss is a miss of XT_getIX32 too; positives take the
+// exact path.  What one random filter probe per position costs on B200 is one
+// 128-byte DRAM line fill (profiles/r01_membench*): 47.5 G fills/s, 25 ms for the
+// 1.19 G positions of 10 M reads.  So the LINE of a word is not chosen by the word
+// but by its MINIMIZER: the smallest hash among the canonical 16-mers (min of a
+// 16-mer and its reverse complement) inside the 32-mer.  Consecutive windows of a
+// read share their minimizer for 9 positions on average (density 2/(w+1), w = 17),
+// and lane = position, so the 32 probes of a warp instruction fall into ~4.4 lines
+// which the L1 coalesces into as many requests: one DRAM line per ~9 positions, no
+// partitioning pass, nothing that depends on the batch size.  The minimizer is
+// strand-neutral (itree.c:887-898 makes every window be searched on both strands),
+// so x and revcomp(x) share the line; inside it the 8-byte BLOCK (16 per line) is
+// chosen by a strand-neutral hash and the eight BITS, one in each byte of the
+// block, by x itself: one 8-byte load per position answers both strands, and the
+// two mask words of a strand cost two PRMTs (byte table 1 << n, selected by 3-bit
+// fields of a hash) -- the kernel is bound by the integer pipe, not by memory
+// (profiles/r02_*).  Lines hold SV_RPL records on average (~43 bits per record:
+// ~0.04 % false positives, the spread of the line loads included).
+#define SV_W 17u                // 16-mers per 32-mer
+#define SV_RPL 24u              // records per 128-byte line
+__device__ __forceinline__ uint32_t sv_mhash(uint32_t m, uint32_t r) {   // order key of a 16-mer m with reverse complement r
+    uint32_t a = m < r ? m : r;
+    a *= 0x9E3779B1u; a ^= a >> 15; a *= 0x85EBCA77u;
+    return a;
 }
-// hc = mix64(min(x, revcomp(x))); the mask hash folds the word back in, so x and revcomp(x) get unrelated bits
-__device__ __forceinline__ uint4 bloom_masks(uint64_t hc, uint64_t x) {
-    const uint64_t g = ((hc ^ x) * 0x9E3779B97F4A7C15ull) >> 24;   // 8 x 5 bits: two bits in each of the 4 words
-    return make_uint4((1u << (g & 31)) | (1u << ((g >> 5) & 31)), (1u << ((g >> 10) & 31)) | (1u << ((g >> 15) & 31)),
-                      (1u << ((g >> 20) & 31)) | (1u << ((g >> 25) & 31)), (1u << ((g >> 30) & 31)) | (1u << ((g >> 35) & 31)));
+__device__ __forceinline__ uint64_t sv_line(uint32_t mv, uint64_t n_lines) {   // n_lines < 2^32
+    uint32_t t = mv * 0xB5297A4Du; t ^= t >> 16; t *= 0x68E31DA5u;           // the minimum of 17 hashes is small: spread it again
+    return ((uint64_t)t * n_lines) >> 32;
 }
-__device__ __forceinline__ bool bloom_test(const uint4 &v, const uint4 &m) {
-    return ((v.x & m.x) == m.x) & ((v.y & m.y) == m.y) & ((v.z & m.z) == m.z) & ((v.w & m.w) == m.w);
+// xh / rh: upper halves (first 16 bases) of the word and of its reverse complement -- symmetric in the two
+__device__ __forceinline__ uint32_t sv_block(uint32_t xh, uint32_t rh) { return ((xh ^ rh) * 0x9E3779B1u) >> 28; }
+// the word's two mask words: one bit in each of the block's 8 bytes
+__device__ __forceinline__ uint2 sv_masks(uint32_t xh, uint32_t xl) {
+    uint32_t e = xh * 0xC2B2AE3Du + xl * 0x27D4EB2Fu;
+    e ^= e >> 15;
+    const uint32_t s0 = __umulhi(e, 0x165667B1u) & 0x7777u, s1 = __umulhi(e, 0x9E3779B1u) & 0x7777u;   // 4 x 3-bit byte selectors each
+    return make_uint2(__byte_perm(0x08040201u, 0x80402010u, s0), __byte_perm(0x08040201u, 0x80402010u, s1));
 }
-__device__ __forceinline__ uint64_t bloom_block_hash(uint64_t x, uint64_t rc) { return mix64(x < rc ? x : rc); }
-__device__ __forceinline__ bool bloom_maybe(const DevDB &db, uint64_t word) {
-    const uint64_t hc = bloom_block_hash(word, revcomp_word(word));
-    const uint4 v = __ldg(db.bloom + __umul64hi(hc, db.bloom_blocks));   // ONE request for ONE line (profiles/r01_membench*)
-    return bloom_test(v, bloom_masks(hc, word));
+__device__ __forceinline__ bool sv_test(const uint2 &v, uint32_t xh, uint32_t xl) {
+    const uint2 m = sv_masks(xh, xl);
+    return ((~v.x & m.x) | (~v.y & m.y)) == 0u;
 }
-// one thread per prefix bin: inserts the words of the bin's records
+// minimizer of one word, the slow way (build, stage-level lookups): all 17 16-mers
+__device__ __forceinline__ uint32_t sv_minimizer(uint64_t x, uint64_t rc) {
+    uint32_t mv = 0xFFFFFFFFu;
+#pragma unroll
+    for (uint32_t j = 0; j < SV_W; ++j) {
+        const uint32_t h = sv_mhash((uint32_t)(x >> (32u - 2u * j)), (uint32_t)(rc >> (2u * j)));
+        mv = h < mv ? h : mv;
+    }
+    return mv;
+}
+__device__ __forceinline__ uint64_t sv_index(const DevDB &db, uint32_t mv, uint32_t blk) { return sv_line(mv, db.sv_lines) * 16u + blk; }
+__device__ __forceinline__ bool sv_maybe(const DevDB &db, uint64_t word) {
+    const uint64_t rc = revcomp_word(word);
+    const uint2 v = __ldg(db.sieve + sv_index(db, sv_minimizer(word, rc), sv_block((uint32_t)(word >> 32), (uint32_t)(rc >> 32))));
+    return sv_test(v, (uint32_t)(word >> 32), (uint32_t)word);
+}
+template <int G>
 __global__ void __launch_bounds__(256)
-bloom_build_kernel(DevDB db, uint32_t *__restrict__ bloom) {
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+sieve_build_kernel(DevDB db, uint32_t *__restrict__ sieve) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p = t / G;
+    const uint32_t gl = (uint32_t)(t % G);
     if (p >= UTB_NUMBINS - 1) return;
     uint64_t a, b;
     if (db.binix32) { a = db.binix32[p]; b = db.binix32[p + 1]; }
     else { a = db.binix64[p]; b = db.binix64[p + 1]; }
     if (a >= b || b > db.num_nodes) return;
-    if (p == db.quirk_bin) ++a;                                    // the folded record is unreachable anyway
-    for (uint64_t i = a; i < b; ++i) {
-        const uint64_t word = ((uint64_t)p << 40) | ((uint64_t)key_at(db, i) << 8) | (load_aux(db, i) & 0xFFu);
-        const uint64_t hc = bloom_block_hash(word, revcomp_word(word));
-        uint32_t *blk = bloom + 4 * __umul64hi(hc, db.bloom_blocks);
-        const uint4 m = bloom_masks(hc, word);
-        atomicOr(blk + 0, m.x); atomicOr(blk + 1, m.y); atomicOr(blk + 2, m.z); atomicOr(blk + 3, m.w);
+    if ((uint32_t)p == db.quirk_bin) ++a;                          // the folded record is unreachable anyway
+    for (uint64_t i = a + gl; i < b; i += G) {
+        const uint64_t word = (p << 40) | load_suffix(db.recs, i * db.sz);
+        const uint64_t rc = revcomp_word(word);
+        uint32_t *blk = sieve + 2u * sv_index(db, sv_minimizer(word, rc), sv_block((uint32_t)(word >> 32), (uint32_t)(rc >> 32)));
+        const uint2 m = sv_masks((uint32_t)(word >> 32), (uint32_t)word);
+        atomicOr(blk + 0, m.x); atomicOr(blk + 1, m.y);
     }
 }
 
 // One thread per (position, strand) of the packed super-sequence: lanes 2k and
 // 2k+1 look up the forward and the reverse-complement word of window k, so the
-// hit slots of a warp are 32 consecutive u32.  No block-level synchronisation:
-// a warp that is done leaves (the profile of the first version showed a third
-// of the resident warps parked on a bookkeeping barrier); lookups and hits are
-// counted per warp into COUNTER_SLOTS spread counters that the host sums.
+// hit slots of a warp are 32 consecutive u32.  No block-level synchronisation;
+// lookups and hits are counted per warp into COUNTER_SLOTS spread counters that
+// the host sums.  TABLE: the sector hash table (regular CTRs with the sieve
+// switched off: dense trees where most lookups hit); else the reference's probe
+// sequence on the on-disk records (irregular CTRs, UTB_LOOKUP=exact).
 #define COUNTER_SLOTS 1024
-template <int NSTR, bool FAST, bool BLOOM>
+template <int NSTR, bool TABLE>
 __global__ void __launch_bounds__(256, 6)
 lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad,
               uint32_t n_pos, const uint32_t *__restrict__ n_groups_dev, uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters) {
@@ -497,16 +461,11 @@ lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     const uint32_t pos = (uint32_t)(NSTR == 2 ? slot >> 1 : slot);
     uint64_t w = 0;
     const bool valid = pos < n_pos && window_at(pk, bad, pos, w);
-    uint32_t r = HIT_NOWIN;
+    uint32_t r = HIT_NOWIN, ns = 0;
     if (valid) {
         if (NSTR == 2 && (slot & 1)) w = revcomp_word(w);
-        if (BLOOM && !bloom_maybe(db, w)) r = HIT_MISS;
-        else if (FAST) {
-            uint64_t ww[1] = {w};
-            uint32_t rr[1];
-            fast_lookup<1>(db, ww, rr);
-            r = rr[0];
-        } else {
+        if (TABLE) r = kt_lookup(db, w, &ns);
+        else {
             Probe q[1];
             probe_begin(db, w, q[0]);
             probe_run<1>(db, q);
@@ -516,36 +475,24 @@ lookup_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     if (pos < n_pos) hits[slot] = r;
     const uint32_t nv = __popc(__ballot_sync(0xFFFFFFFFu, valid));
     const uint32_t nh = __popc(__ballot_sync(0xFFFFFFFFu, r < HIT_NOWIN));
+    for (int o = 16; o; o >>= 1) ns += __shfl_xor_sync(0xFFFFFFFFu, ns, o);
     if ((threadIdx.x & 31u) == 0) {
         const uint32_t c = blockIdx.x & (COUNTER_SLOTS - 1);
         if (nv) atomicAdd(counters + c, (unsigned long long)nv);
         if (nh) atomicAdd(counters + COUNTER_SLOTS + c, (unsigned long long)nh);
+        if (ns) atomicAdd(counters + 3 * COUNTER_SLOTS + c, (unsigned long long)ns);
     }
 }
 
-// ---- two-phase lookup (pre-filter on) -------------------------------------------
+// ---- two-phase lookup (sieve on) ----------------------------------------------------
 // In one fused kernel every warp waits for its slowest lane, i.e. for the one
-// or two lanes per warp whose word passes the filter and walks the whole
-// index -> key line -> aux chain, while the other ~30 lanes idle: the kernel
-// is bound by warp latency, not by DRAM.  So the work is split into two dense
-// passes: phase A tests every window against the filter (one fetch per POSITION
-// serves both strands, no chain) and appends the survivors to a queue with a
-// warp-aggregated atomic; phase B runs the exact search over the queue with
-// every lane busy.
-__device__ __noinline__ uint32_t fast_lookup_cold(const DevDB &db, uint64_t w) {
-    uint64_t ww[1] = {w};
-    uint32_t rr[1];
-    fast_lookup<1>(db, ww, rr);
-    return rr[0];
-}
+// or two lanes per warp whose word passes the sieve and goes on to the table,
+// while the other ~30 lanes idle.  So the work is split into two dense passes:
+// phase A (sieve_kernel) tests every window against the sieve and appends the
+// survivors to a queue through per-warp chunks; phase B (queue_lookup_kernel)
+// runs the exact lookup over the queue with every lane busy.
 #define Q_CHUNK 128u              // queue slots a warp reserves per atomic (>= 64: two ballots per step)
-#ifndef FILT_ILP
-#define FILT_ILP 2                // filter probes in flight per lane
-#endif
 #define Q_INVALID 0xFFFFFFFFu
-#ifndef FILT_MINB
-#define FILT_MINB 4               // CTAs per SM the register budget is sized for
-#endif
 // A warp's private window into the survivor queue: the global counter sees one
 // atomic per Q_CHUNK survivors instead of one per warp-step.
 struct WarpQueue {
@@ -557,7 +504,7 @@ __device__ __forceinline__ void wq_init(WarpQueue &q) { q.base = 0; q.used = Q_C
 __device__ __forceinline__ void wq_retire(const WarpQueue &q, uint32_t lane, uint32_t *__restrict__ q_slots) {
     if (q.have) for (uint32_t j = q.used + lane; j < Q_CHUNK; j += 32) q_slots[q.base + j] = Q_INVALID;   // pad the tail
 }
-// make room for c more entries (warp-uniform call)
+// make room for c more entries (warp-uniform call); q_cap is a multiple of Q_CHUNK
 __device__ __forceinline__ void wq_reserve(WarpQueue &q, uint32_t c, uint32_t lane, uint32_t *__restrict__ q_slots,
                                            unsigned long long *__restrict__ q_count, uint64_t q_cap) {
     if (q.used + c <= Q_CHUNK) return;
@@ -568,24 +515,20 @@ __device__ __forceinline__ void wq_reserve(WarpQueue &q, uint32_t c, uint32_t la
     q.used = 0;
     q.have = q.base + Q_CHUNK <= q_cap;                            // beyond capacity: the caller resolves inline
 }
-// queue overflow / region overflow: the exact search right here (rare)
+// queue overflow: the exact lookup right here (rare)
 __device__ __noinline__ uint32_t resolve_inline(const DevDB &db, uint64_t w, uint32_t slot, uint32_t *__restrict__ hits,
                                                 uint32_t *__restrict__ hitmap) {
-    const uint32_t r = fast_lookup_cold(db, w);
+    const uint32_t r = kt_lookup(db, w);
     if (r == HIT_MISS) return 0;
     hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u));
     return 1;
 }
-// Tests one position (both strands when NSTR == 2) against its filter block v and appends the survivors.
-// Warp-uniform call; `valid` lanes hold a window w with reverse complement rc and block hash hc.
+// Appends the survivors of one warp step (warp-uniform call).
 template <int NSTR>
-__device__ __forceinline__ uint32_t filter_emit(const DevDB &db, WarpQueue &wq, uint32_t lane, bool valid, uint64_t w, uint64_t rc,
-                                                uint64_t hc, const uint4 &v, uint32_t pos,
-                                                uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots,
-                                                unsigned long long *__restrict__ q_count, uint64_t q_cap,
-                                                uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
-    const bool passF = valid && bloom_test(v, bloom_masks(hc, w));
-    const bool passR = NSTR == 2 && valid && bloom_test(v, bloom_masks(hc, rc));
+__device__ __forceinline__ uint32_t emit_survivors(const DevDB &db, WarpQueue &wq, uint32_t lane, bool passF, bool passR, uint64_t w, uint64_t rc,
+                                                   uint32_t pos, uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots,
+                                                   unsigned long long *__restrict__ q_count, uint64_t q_cap,
+                                                   uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
     const uint32_t bF = __ballot_sync(0xFFFFFFFFu, passF);
     const uint32_t bR = NSTR == 2 ? __ballot_sync(0xFFFFFFFFu, passR) : 0u;
     const uint32_t cF = __popc(bF), c = cF + __popc(bR);
@@ -605,41 +548,116 @@ __device__ __forceinline__ uint32_t filter_emit(const DevDB &db, WarpQueue &wq, 
     return nh;
 }
 
-// Direct filter pass (batches too small for the partitioned pass): persistent warps, one lane per
-// position, FILT_ILP positions of a lane in flight together.
+// Phase A.  Persistent warps; every warp owns a contiguous range of 32-position steps (one step = one
+// group of the packed stream, lane = position) and walks it SV_U steps at a time.  Per step a lane
+// builds its window and the reverse complement of it -- funnel shifts of two consecutive words of
+// the packed stream pk, resp. of its reverse-complement twin pkr, all in 32-bit halves -- and the hash
+// of the canonical 16-mer that STARTS at its position; the minimizer of a window is the minimum of
+// the 17 hashes at positions p .. p+16, taken across lanes with shuffles (doubling: 2, 4, 8, 16, 17),
+// where positions beyond lane 31 belong to the next step -- which is computed one tile ahead and
+// carried over, so nothing is computed twice.
+#ifndef SV_U
+#define SV_U 4                    // steps per tile = filter loads in flight per lane
+#endif
+#ifndef SV_MINB
+#define SV_MINB 3                 // CTAs per SM the register budget is sized for
+#endif
+struct SvStep { uint32_t wh, wl, rh, rl, h, blk; bool valid; };   // window, its reverse complement (halves), 16-mer hash, block in the line
+struct SvWords { uint64_t hi, lo, rhi, rlo; uint32_t bh, bl; };   // groups s and s + 1 of pk / pkr / bad
+__device__ __forceinline__ void sv_step(const SvWords &g, bool upper, uint32_t r2, uint32_t lane, SvStep &s) {
+    // forward window: the 128 bits hi:lo shifted left by 2 * lane, upper 64 bits
+    const uint32_t b0 = (uint32_t)(g.hi >> 32), b1 = (uint32_t)g.hi, b2 = (uint32_t)(g.lo >> 32), b3 = (uint32_t)g.lo;
+    const uint32_t x0 = upper ? b1 : b0, x1 = upper ? b2 : b1, x2 = upper ? b3 : b2;
+    s.wh = __funnelshift_l(x1, x0, r2); s.wl = __funnelshift_l(x2, x1, r2);
+    // its reverse complement: the 128 bits revcomp(lo):revcomp(hi) shifted right by 2 * lane, lower 64 bits
+    const uint32_t a0 = (uint32_t)(g.rlo >> 32), a1 = (uint32_t)g.rlo, a2 = (uint32_t)(g.rhi >> 32), a3 = (uint32_t)g.rhi;
+    const uint32_t z0 = upper ? a2 : a3, z1 = upper ? a1 : a2, z2 = upper ? a0 : a1;
+    s.rl = __funnelshift_r(z0, z1, r2); s.rh = __funnelshift_r(z1, z2, r2);
+    s.valid = __funnelshift_r(g.bh, g.bl, lane) == 0u;             // no bad base in the 32 positions from here
+    s.h = sv_mhash(s.wh, s.rl);
+    s.blk = sv_block(s.wh, s.rh);
+}
+// value of the (virtual) array x[0..SV_U] at index 32 * u + lane + D
+template <int D>
+__device__ __forceinline__ void sv_shift_min(uint32_t (&x)[SV_U + 1], uint32_t lane) {
+    uint32_t rot[SV_U + 1];
+#pragma unroll
+    for (int u = 0; u <= SV_U; ++u) rot[u] = __shfl_sync(0xFFFFFFFFu, x[u], (lane + D) & 31u);
+    const bool same = lane + D < 32u;
+#pragma unroll
+    for (int u = 0; u < SV_U; ++u) { const uint32_t y = same ? rot[u] : rot[u + 1]; x[u] = y < x[u] ? y : x[u]; }
+    x[SV_U] = rot[SV_U] < x[SV_U] ? rot[SV_U] : x[SV_U];          // only its low lanes are ever used (no step beyond it is needed)
+}
 template <int NSTR>
-__global__ void __launch_bounds__(256, FILT_MINB)
-filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
-              const uint32_t *__restrict__ n_groups_dev,
-              uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
-              uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
-              uint64_t q_cap, uint32_t *__restrict__ hitmap) {
+__global__ void __launch_bounds__(256, SV_MINB)
+sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint64_t *__restrict__ pkr, uint32_t n_pos,
+             const uint32_t *__restrict__ n_groups_dev,
+             uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
+             uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
+             uint64_t q_cap, uint32_t *__restrict__ hitmap) {
     if (n_groups_dev) n_pos = *n_groups_dev * 32u;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const bool upper = lane >= 16u;
+    const uint32_t r2 = 2u * (lane & 15u);
+    const uint32_t n_steps = n_pos >> 5;                           // n_pos is a multiple of 32; group n_steps is the guard group
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    uint32_t per = (n_steps + n_warps - 1) / n_warps;
+    per = (per + SV_U - 1) / SV_U * SV_U;
+    const uint64_t s0 = (uint64_t)wid * per;
+    const uint32_t s1 = s0 + per < n_steps ? (uint32_t)(s0 + per) : n_steps;
     WarpQueue wq;
     wq_init(wq);
     uint32_t nv = 0, nh = 0;
-    // every warp takes FILT_ILP x 32 consecutive positions per round (n_pos is a multiple of 32)
-    for (uint64_t base = ((uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) * FILT_ILP; base < n_pos; base += stride * FILT_ILP) {
-        uint64_t w[FILT_ILP], hc[FILT_ILP];
-        uint4 v[FILT_ILP];
-        bool valid[FILT_ILP];
+    if (s0 < s1) {
+        SvStep st[SV_U + 1];
+        // groups s and s + 1 feed step s; the pair is carried from step to step (two 8-byte and one 4-byte load per step)
+        SvWords g;
+        g.hi = __ldg(pk + s0); g.rhi = __ldg(pkr + s0); g.bh = __ldg(bad + s0);
+        g.lo = __ldg(pk + s0 + 1); g.rlo = __ldg(pkr + s0 + 1); g.bl = __ldg(bad + s0 + 1);
+        sv_step(g, upper, r2, lane, st[0]);
+        for (uint32_t s = (uint32_t)s0; s < s1; s += SV_U) {
 #pragma unroll
-        for (int u = 0; u < FILT_ILP; ++u) {
-            const uint64_t pos = base + 32u * u + lane;
-            w[u] = 0;
-            valid[u] = pos < n_pos && window_at(pk, bad, (uint32_t)pos, w[u]);
-            hc[u] = bloom_block_hash(w[u], revcomp_word(w[u]));
-            v[u] = make_uint4(0, 0, 0, 0);
-            if (valid[u]) v[u] = __ldg(db.bloom + __umul64hi(hc[u], db.bloom_blocks));
-        }
+            for (int u = 1; u <= SV_U; ++u) {
+                g.hi = g.lo; g.rhi = g.rlo; g.bh = g.bl;
+                const uint32_t gi = s + u + 1;                     // groups up to n_steps + 1 exist (guard + slack)
+                if (gi <= n_steps + 1) { g.lo = __ldg(pk + gi); g.rlo = __ldg(pkr + gi); g.bl = __ldg(bad + gi); }
+                else { g.lo = 0; g.rlo = 0; g.bl = 0xFFFFFFFFu; }
+                if (s + u <= n_steps) sv_step(g, upper, r2, lane, st[u]);
+                else { st[u].wh = st[u].wl = st[u].rh = st[u].rl = 0; st[u].h = 0xFFFFFFFFu; st[u].blk = 0; st[u].valid = false; }
+            }
+            uint32_t x[SV_U + 1], h16[SV_U + 1];
 #pragma unroll
-        for (int u = 0; u < FILT_ILP; ++u) {
-            const uint32_t pos = (uint32_t)(base + 32u * u + lane);
-            // the reverse complement is recomputed rather than kept live across the loads (registers = probes in flight)
-            nh += filter_emit<NSTR>(db, wq, lane, valid[u], w[u], revcomp_word(w[u]), hc[u], v[u], pos, q_words, q_slots, q_count, q_cap, hits, hitmap);
-            nv += valid[u] ? NSTR : 0;                             // hits[] is only valid where hitmap is set: nothing to store for misses
+            for (int u = 0; u <= SV_U; ++u) { x[u] = st[u].h; h16[u] = st[u].h; }
+            sv_shift_min<1>(x, lane);                              // min over [q, q+1]
+            sv_shift_min<2>(x, lane);                              // [q, q+3]
+            sv_shift_min<4>(x, lane);                              // [q, q+7]
+            sv_shift_min<8>(x, lane);                              // [q, q+15]
+            {                                                      // [q, q+16]
+                uint32_t rot[SV_U + 1];
+#pragma unroll
+                for (int u = 0; u <= SV_U; ++u) rot[u] = __shfl_sync(0xFFFFFFFFu, h16[u], (lane + 16u) & 31u);
+#pragma unroll
+                for (int u = 0; u < SV_U; ++u) { const uint32_t y = lane < 16u ? rot[u] : rot[u + 1]; x[u] = y < x[u] ? y : x[u]; }
+            }
+            uint2 v[SV_U];
+            bool live[SV_U];
+#pragma unroll
+            for (int u = 0; u < SV_U; ++u) {
+                live[u] = st[u].valid && s + u < s1;
+                v[u] = make_uint2(0, 0);
+                if (live[u]) v[u] = __ldg(db.sieve + sv_index(db, x[u], st[u].blk));
+            }
+#pragma unroll
+            for (int u = 0; u < SV_U; ++u) {
+                if (__any_sync(0xFFFFFFFFu, live[u])) {            // the padding group behind every read holds no window at all
+                    const bool passF = live[u] && sv_test(v[u], st[u].wh, st[u].wl);
+                    const bool passR = NSTR == 2 && live[u] && sv_test(v[u], st[u].rh, st[u].rl);
+                    nh += emit_survivors<NSTR>(db, wq, lane, passF, passR, ((uint64_t)st[u].wh << 32) | st[u].wl, ((uint64_t)st[u].rh << 32) | st[u].rl,
+                                               (s + u) * 32u + lane, q_words, q_slots, q_count, q_cap, hits, hitmap);
+                    nv += live[u] ? NSTR : 0;                      // hits[] is only valid where hitmap is set: nothing to store for misses
+                }
+            }
+            st[0] = st[SV_U];
         }
     }
     wq_retire(wq, lane, q_slots);
@@ -651,284 +669,21 @@ filter_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restr
     }
 }
 
-// ---- partitioned filter pass ----------------------------------------------------------
-// One random 128-byte DRAM line per probe is what bounds filter_kernel.  Here the
-// positions of a batch are first bucketed by the top 6 bits of the filter's block
-// hash (64 partitions = 64 contiguous ~34 MB slices of the filter): partition_kernel
-// streams (forward word, position) records into per-partition arrays (12 B per
-// position = 6 B per lookup with both strands, sequential), then probe_kernel sweeps
-// the partitions in order with the whole grid, so the slice being probed stays
-// resident in the 126 MB L2 and each of its lines is fetched from HBM once per batch
-// instead of once per probe.
-#define NPART 64u
-#define PART_MIN_POS (256ull << 20)  // positions in a batch from which the partitioned pass is used (~1.6 M reads of 150 bp); below it the
-                                     // direct filter wins: 64 grid barriers per batch and a cooperative launch that cannot overlap other slots
-#define P_CTAS (148u * 4u)      // partitioner CTAs; each owns one output region per partition
-#define P_TILE 4096u            // positions a CTA sorts in shared memory at a time
-#define P_PPT (P_TILE / 256u)   // positions per thread and tile
-#define P_SMEM (P_TILE * 8u + P_TILE * 4u)   // words in tile order + sorted order (local index | partition << 16)
-// Partitioner: every CTA counting-sorts one 4096-position tile at a time and appends each partition's
-// run to its own region [(c*NPART+p)*cap_cp, +cap_cp), so the global stores are contiguous runs (~47
-// records) instead of one transaction per record (scattered 8-byte stores cost as much as scattered
-// sector reads, profiles/).  The words stay in tile order in shared memory; only a 4-byte index is
-// scattered, and the output pass gathers through it.  No global atomics; the fill of every region is
-// stored at the end.  Hash partitions are uniform and every CTA sees the same share of the batch, so
-// regions fill evenly (cap_cp carries 25 % head-room; records of an overflowing tile are resolved inline).
-// MATCH (kept as a measured alternative, UTB_PART_ATOMS=0): the rank of a record inside its partition comes
-// from warp match + a scanned (warp-row x partition) count table instead of one shared-memory atomic per
-// record.  Shared atomics with a return value run at ~2 cycles per LANE on the SM's load/store unit
-// (B300_MICROARCH "ATOMS spread-addr"), but MATCH.ANY over mostly distinct keys plus the table scan cost
-// more: 16.2 ms against 11.5 ms per 10 M reads, so the atomic variant is the default.
-#define P_ROWS (P_TILE / 32u)   // warp-rows of a tile
-#define P_SMEM_MATCH (P_SMEM + P_ROWS * NPART * 2u)
-template <int NSTR, bool MATCH>
-__global__ void __launch_bounds__(256, MATCH ? 3 : 4)
-partition_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
-                 const uint32_t *__restrict__ n_groups_dev, unsigned long long *__restrict__ counters,
-                 uint64_t *__restrict__ p_words, uint32_t *__restrict__ p_pos, uint32_t *__restrict__ p_fill,
-                 uint32_t cap_cp, uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
-    extern __shared__ __align__(16) unsigned char p_smem[];
-    uint64_t *s_w = reinterpret_cast<uint64_t *>(p_smem);
-    uint32_t *s_ord = reinterpret_cast<uint32_t *>(p_smem + P_TILE * 8u);
-    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(p_smem + P_SMEM);   // MATCH: [P_ROWS][NPART] group sizes, then their prefix over the rows
-    __shared__ uint32_t s_q[4][NPART];                             // MATCH: per quarter of the rows: total, then base in the sorted order
-    __shared__ uint32_t s_hist[NPART], s_start[NPART], s_cur[NPART];
-    __shared__ uint64_t s_gbase[NPART];                            // region base + fill - start: global index = s_gbase[part] + sorted rank
-    __shared__ uint32_t s_ovf;
-    __shared__ uint64_t s_pk[P_TILE / 32u + 4u];                  // the tile's packed groups (+ the one after)
-    __shared__ uint32_t s_bad[P_TILE / 32u + 4u];
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    if (n_groups_dev) n_pos = *n_groups_dev * 32u;
-    const uint32_t n_groups = n_pos >> 5;
-    if (tid < NPART) s_cur[tid] = 0;
-    uint32_t nv = 0, nh = 0;
-    const uint64_t region0 = (uint64_t)blockIdx.x * NPART * cap_cp;
-    // The packed stream of a tile is 1.5 KB: it is fetched one tile ahead into registers (the loads complete
-    // under the three passes of the current tile) and parked in shared memory, so no pass waits on DRAM.
-    uint64_t pf_pk = 0;
-    uint32_t pf_bad = 0xFFFFFFFFu;
-    {
-        const uint64_t g = (uint64_t)blockIdx.x * (P_TILE / 32u) + tid;
-        if (tid <= P_TILE / 32u && g <= n_groups) { pf_pk = __ldg(pk + g); pf_bad = __ldg(bad + g); }   // group n_groups is the guard
-    }
-    for (uint64_t tile = (uint64_t)blockIdx.x * P_TILE; tile < n_pos; tile += (uint64_t)gridDim.x * P_TILE) {
-        if (tid < NPART) s_hist[tid] = 0;
-        if (tid == 0) s_ovf = 0;
-        if (tid <= P_TILE / 32u) { s_pk[tid] = pf_pk; s_bad[tid] = pf_bad; }
-        if (MATCH) {
-            uint4 *z = reinterpret_cast<uint4 *>(s_cnt);
-#pragma unroll
-            for (uint32_t i = 0; i < P_ROWS * NPART * 2u / 16u / 256u; ++i) z[i * 256u + tid] = make_uint4(0, 0, 0, 0);
-        }
-        __syncthreads();
-        {
-            const uint64_t g = (tile + (uint64_t)gridDim.x * P_TILE) / 32u + tid;
-            pf_pk = 0; pf_bad = 0xFFFFFFFFu;
-            if (tid <= P_TILE / 32u && g <= n_groups) { pf_pk = __ldg(pk + g); pf_bad = __ldg(bad + g); }
-        }
-        // pass A: window, partition id and rank inside the tile.  A warp covers 32 consecutive positions = one
-        // group of the packed stream, so its pk/bad loads are warp-uniform.
-        uint32_t meta[P_PPT];                                      // rank << 6 | part, or 0xFFFFFFFF
-        const uint32_t tile_pos = (uint32_t)tile;
-#pragma unroll
-        for (uint32_t k = 0; k < P_PPT; ++k) {
-            const uint32_t local = k * 256u + tid;
-            uint64_t w = 0;
-            meta[k] = 0xFFFFFFFFu;
-            const bool valid = window_at(s_pk, s_bad, local, w);   // positions past the batch lie in all-bad groups
-            uint32_t part = 64u + lane;                             // invalid lanes: a key of their own
-            if (valid) part = (uint32_t)(bloom_block_hash(w, revcomp_word(w)) >> 58);
-            if (MATCH) {
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, part);
-                const uint32_t lrank = __popc(peers & ((1u << lane) - 1u));
-                if (valid) {
-                    if (lrank == 0) s_cnt[(k * 8u + (tid >> 5)) * NPART + part] = (uint16_t)__popc(peers);
-                    meta[k] = (lrank << 6) | part;
-                    nv += NSTR;
-                }
-            } else if (valid) {
-                meta[k] = (atomicAdd(&s_hist[part], 1u) << 6) | part;
-                nv += NSTR;
-            }
-            s_w[local] = w;
-        }
-        __syncthreads();
-        if (MATCH) {
-            // prefix of the group sizes over the warp-rows, per partition: thread = (quarter of the rows, partition)
-            const uint32_t bin = tid & 63u, q = tid >> 6;
-            uint32_t run = 0;
-#pragma unroll 8
-            for (uint32_t i = 0; i < P_ROWS / 4u; ++i) {
-                uint16_t *c = s_cnt + (q * (P_ROWS / 4u) + i) * NPART + bin;
-                const uint32_t v = *c;
-                *c = (uint16_t)run;
-                run += v;
-            }
-            s_q[q][bin] = run;
-            __syncthreads();
-            if (tid < NPART) s_hist[tid] = s_q[0][tid] + s_q[1][tid] + s_q[2][tid] + s_q[3][tid];
-            __syncthreads();
-        }
-        if (tid < 32) {                                            // exclusive scan of the 64 bins by one warp
-            const uint32_t h0 = s_hist[2 * tid], h1 = s_hist[2 * tid + 1];
-            uint32_t x = h0 + h1;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((int)tid >= o) x += t; }
-            const uint32_t st0 = x - h0 - h1, st1 = x - h1, c0 = s_cur[2 * tid], c1 = s_cur[2 * tid + 1];
-            s_start[2 * tid] = st0; s_start[2 * tid + 1] = st1;
-            s_gbase[2 * tid] = region0 + (uint64_t)(2 * tid) * cap_cp + c0 - st0;
-            s_gbase[2 * tid + 1] = region0 + (uint64_t)(2 * tid + 1) * cap_cp + c1 - st1;
-            if (c0 + h0 > cap_cp || c1 + h1 > cap_cp) s_ovf = 1;
-            if (MATCH) {                                            // quarter totals -> bases in the sorted order
-#pragma unroll
-                for (uint32_t b2 = 0; b2 < 2; ++b2) {
-                    uint32_t base = b2 ? st1 : st0;
-#pragma unroll
-                    for (uint32_t q = 0; q < 4; ++q) { const uint32_t t = s_q[q][2 * tid + b2]; s_q[q][2 * tid + b2] = base; base += t; }
-                }
-            }
-        }
-        __syncthreads();
-        // pass B: the sorted order (4 bytes per record scattered; the words stay where they are)
-#pragma unroll
-        for (uint32_t k = 0; k < P_PPT; ++k) {
-            const uint32_t m = meta[k];
-            if (m == 0xFFFFFFFFu) continue;
-            const uint32_t part = m & 63u;
-            uint32_t dst;
-            if (MATCH) { const uint32_t row = k * 8u + (tid >> 5); dst = s_q[row / (P_ROWS / 4u)][part] + s_cnt[row * NPART + part] + (m >> 6); }
-            else dst = s_start[part] + (m >> 6);
-            s_ord[dst] = (k * 256u + tid) | (part << 16);
-        }
-        __syncthreads();
-        // pass C: contiguous runs out to the regions
-        const uint32_t total = s_start[NPART - 1] + s_hist[NPART - 1];
-        if (!s_ovf) {
-            for (uint32_t e = tid; e < total; e += 256) {
-                const uint32_t o = s_ord[e], local = o & 0xFFFFu;
-                const uint64_t idx = s_gbase[o >> 16] + e;
-                p_words[idx] = s_w[local]; p_pos[idx] = tile_pos + local;
-            }
-        } else {                                                   // some region is full: per-record bound check
-            for (uint32_t e = tid; e < total; e += 256) {
-                const uint32_t o = s_ord[e], local = o & 0xFFFFu, part = o >> 16;
-                const uint32_t at = s_cur[part] + (e - s_start[part]);
-                const uint64_t w = s_w[local];
-                const uint32_t pos = tile_pos + local;
-                if (at < cap_cp) { const uint64_t idx = s_gbase[part] + e; p_words[idx] = w; p_pos[idx] = pos; }
-                else {
-                    const uint64_t rc = revcomp_word(w);
-                    if (bloom_maybe(db, w)) nh += resolve_inline(db, w, pos * NSTR, hits, hitmap);
-                    if (NSTR == 2 && bloom_maybe(db, rc)) nh += resolve_inline(db, rc, pos * NSTR + 1u, hits, hitmap);
-                }
-            }
-        }
-        __syncthreads();
-        if (tid < NPART) s_cur[tid] += s_hist[tid];
-    }
-    __syncthreads();
-    if (tid < NPART) p_fill[blockIdx.x * NPART + tid] = s_cur[tid] < cap_cp ? s_cur[tid] : cap_cp;
-    for (int o = 16; o; o >>= 1) { nv += __shfl_xor_sync(0xFFFFFFFFu, nv, o); nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); }
-    if (lane == 0) {
-        const uint32_t cs = (blockIdx.x * 8 + (tid >> 5)) & (COUNTER_SLOTS - 1);
-        if (nv) atomicAdd(counters + cs, (unsigned long long)nv);
-        if (nh) atomicAdd(counters + COUNTER_SLOTS + cs, (unsigned long long)nh);
-    }
-}
-
-// Probe pass (cooperative launch): the whole grid sweeps partition 0, then 1, ... with a grid barrier in
-// between, so exactly one ~34 MB slice of the filter is live in L2 at a time; the records are read with
-// streaming loads (evict-first) so that they do not push that slice out.  Inside a partition the warps
-// draw work items (1024 records of one region) from a counter, so nobody waits at the barrier for a
-// warp that happened to own fuller regions.  Every lane carries two records per step: one 16-byte
-// record load, two filter loads in flight.
-#define P_SUB 1024u             // records of a region one work item covers
-template <int NSTR>
-__global__ void __launch_bounds__(256, 4)
-probe_kernel(DevDB db, const uint64_t *__restrict__ p_words, const uint32_t *__restrict__ p_pos,
-             const uint32_t *__restrict__ p_fill, uint32_t cap_cp, uint32_t n_ctas, uint32_t *__restrict__ p_ctr,
-             uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count, uint64_t q_cap,
-             uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t subs = (cap_cp + P_SUB - 1) / P_SUB;            // work items per region
-    const uint32_t n_items = n_ctas * subs;
-    WarpQueue wq;
-    wq_init(wq);
-    uint32_t nh = 0;
-    for (uint32_t part = 0; part < NPART; ++part) {
-        for (;;) {
-            uint32_t item = 0;
-            if (lane == 0) item = atomicAdd(p_ctr + part, 1u);
-            item = __shfl_sync(0xFFFFFFFFu, item, 0);
-            if (item >= n_items) break;
-            const uint32_t c = item / subs, sub = item - c * subs;
-            const uint32_t fill = __ldg(p_fill + c * NPART + part);
-            const uint64_t base = ((uint64_t)c * NPART + part) * cap_cp;   // even: cap_cp is even
-            const uint32_t j1 = min(fill, (sub + 1) * P_SUB);
-            // the records of step i+1 are requested before step i is probed (two DRAM round trips overlap)
-            ulonglong2 nxt = make_ulonglong2(0, 0);
-            if (sub * P_SUB + 2u * lane < j1) nxt = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + sub * P_SUB + 2u * lane));
-            for (uint32_t j0 = sub * P_SUB; j0 < j1; j0 += 64) {
-                const uint32_t j = j0 + 2u * lane;
-                uint64_t w[2] = {nxt.x, nxt.y}, rc[2], hc[2];
-                uint4 v[2];
-                bool live[2] = {j < j1, j + 1u < j1};
-                if (j + 64u < j1) nxt = __ldcs(reinterpret_cast<const ulonglong2 *>(p_words + base + j + 64u));   // j + 1 < cap_cp always: aligned 16-byte loads
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    rc[u] = revcomp_word(w[u]);
-                    hc[u] = bloom_block_hash(w[u], rc[u]);
-                    v[u] = make_uint4(0, 0, 0, 0);
-                    if (live[u]) v[u] = __ldg(db.bloom + __umul64hi(hc[u], db.bloom_blocks));
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    // the position is only needed by survivors (~2.5 %)
-                    const bool passF = live[u] && bloom_test(v[u], bloom_masks(hc[u], w[u]));
-                    const bool passR = NSTR == 2 && live[u] && bloom_test(v[u], bloom_masks(hc[u], rc[u]));
-                    const uint32_t bF = __ballot_sync(0xFFFFFFFFu, passF);
-                    const uint32_t bR = NSTR == 2 ? __ballot_sync(0xFFFFFFFFu, passR) : 0u;
-                    const uint32_t cF = __popc(bF), cnt = cF + __popc(bR);
-                    if (!cnt) continue;
-                    wq_reserve(wq, cnt, lane, q_slots, q_count, q_cap);
-                    const uint32_t lt = (1u << lane) - 1u;
-                    uint32_t pos = 0;
-                    if (passF || passR) pos = __ldcs(p_pos + base + j + u);
-                    if (wq.have) {
-                        const uint64_t at = wq.base + wq.used;
-                        if (passF) { const uint64_t i = at + __popc(bF & lt); q_words[i] = w[u]; q_slots[i] = pos * NSTR; }
-                        if (passR) { const uint64_t i = at + cF + __popc(bR & lt); q_words[i] = rc[u]; q_slots[i] = pos * NSTR + 1u; }
-                    } else {
-                        if (passF) nh += resolve_inline(db, w[u], pos * NSTR, hits, hitmap);
-                        if (passR) nh += resolve_inline(db, rc[u], pos * NSTR + 1u, hits, hitmap);
-                    }
-                    wq.used += cnt;
-                }
-            }
-        }
-        grid.sync();
-    }
-    wq_retire(wq, lane, q_slots);
-    for (int o = 16; o; o >>= 1) nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o);
-    if (lane == 0 && nh) atomicAdd(counters + COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)nh);
-}
-
+// Phase B: one survivor per thread, ONE random 32-byte table access each (no chain to wait for)
 __global__ void __launch_bounds__(256, 6)
 queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32_t *__restrict__ q_slots,
                     const unsigned long long *__restrict__ q_count, uint64_t q_cap,
                     uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
-    const uint64_t n = *q_count < q_cap ? *q_count : q_cap;
+    const uint64_t n = *q_count < q_cap ? *q_count : q_cap;       // both multiples of Q_CHUNK: every entry below n was written
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     uint32_t nh = 0, nsect = 0;
-    // one survivor per thread (two per thread in lock-step measured slower: the pair waits for its longer chain)
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t slot = q_slots[i];
         if (slot == Q_INVALID) continue;                           // padding of a retired chunk
-        uint64_t ww[1] = {q_words[i]};
-        uint32_t rr[1], sc;
-        fast_lookup<1>(db, ww, rr, &sc);
+        uint32_t sc;
+        const uint32_t r = kt_lookup(db, q_words[i], &sc);
         nsect += sc;
-        if (rr[0] != HIT_MISS) { hits[slot] = rr[0]; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
+        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
     }
     for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); nsect += __shfl_xor_sync(0xFFFFFFFFu, nsect, o); }
     if ((threadIdx.x & 31u) == 0) {
@@ -939,16 +694,13 @@ queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32
 }
 
 // stage-level: words[] -> ix[] (utb_lookup_words)
-template <bool FAST>
+template <bool TABLE>
 __global__ void lookup_words_kernel(DevDB db, const uint64_t *__restrict__ words, uint64_t n, uint32_t *__restrict__ ix) {
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    if (FAST) {
-        if (db.bloom && !bloom_maybe(db, words[i])) { ix[i] = HIT_MISS; return; }
-        uint64_t ww[1] = {words[i]};
-        uint32_t rr[1];
-        fast_lookup<1>(db, ww, rr);
-        ix[i] = rr[0];
+    if (TABLE) {
+        if (db.sieve && !sv_maybe(db, words[i])) { ix[i] = HIT_MISS; return; }
+        ix[i] = kt_lookup(db, words[i]);
         return;
     }
     Probe q[1];
@@ -956,6 +708,7 @@ __global__ void lookup_words_kernel(DevDB db, const uint64_t *__restrict__ words
     probe_run<1>(db, q);
     ix[i] = probe_end(db, q[0]);
 }
+
 
 // stage-level: expose every window of the packed stream (utb_pack_sequence)
 __global__ void expand_windows_kernel(const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_pos,
@@ -1183,13 +936,14 @@ __device__ void vote_warp_read(const DevDB &db, const VoteIn &in, uint32_t r, ut
 }
 // Persistent over `list` (reads deferred by vote_thread_kernel), or over all reads when list is null.
 __global__ void __launch_bounds__(VW_WARPS * 32)
-vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_count,
+vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ dims, const uint32_t *__restrict__ list, const uint32_t *__restrict__ list_count,
                  utb_result *__restrict__ results, uint32_t *__restrict__ gen_list, uint32_t *__restrict__ gen_count,
                  unsigned long long *__restrict__ counters) {
     __shared__ uint32_t s_key[VW_WARPS][VW_SLOTS], s_cnt[VW_WARPS][VW_SLOTS];
     __shared__ uint32_t s_rk[VW_WARPS][VW_SLOTS], s_lab[VW_WARPS][VW_SLOTS], s_tc[VW_WARPS][VW_SLOTS];
     const uint32_t wib = threadIdx.x >> 5;
     const VoteWarpSmem sm = {s_key[wib], s_cnt[wib], s_rk[wib], s_lab[wib], s_tc[wib]};
+    if (dims) n_reads = dims[0];
     const uint32_t total = list ? *list_count : n_reads;
     for (uint32_t i = blockIdx.x * VW_WARPS + wib; i < total; i += gridDim.x * VW_WARPS) {
         vote_warp_read(db, in, list ? list[i] : i, results, gen_list, gen_count, counters, sm);
@@ -1253,14 +1007,18 @@ __device__ __forceinline__ void walk_thread(const DevDB &db, const uint32_t *T_l
 #undef TC
 }
 __global__ void __launch_bounds__(VT_THREADS)
-vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict__ results,
+vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ dims, utb_result *__restrict__ results,
                    uint32_t *__restrict__ list, uint32_t *__restrict__ list_count, unsigned long long *__restrict__ counters) {
+    if (dims) n_reads = dims[0];
     __shared__ uint32_t s_lab[VT_K * VT_THREADS], s_cnt[VT_K * VT_THREADS];
     __shared__ uint32_t s_good;
-    const uint32_t tid = threadIdx.x, r = blockIdx.x * VT_THREADS + tid;
+    const uint32_t tid = threadIdx.x;
+    uint32_t good = 0;
     if (tid == 0) s_good = 0;
     __syncthreads();
-    if (r < n_reads) {
+    for (uint64_t base = (uint64_t)blockIdx.x * VT_THREADS; base < n_reads; base += (uint64_t)gridDim.x * VT_THREADS) {
+        const uint32_t r = (uint32_t)base + tid;                   // the shared rows are private to a thread: no barrier between rounds
+        if (r >= n_reads) break;
         uint64_t start, count;
         vote_range(in, r, start, count);
         const uint32_t nwords = (uint32_t)((count + 31) >> 5);
@@ -1294,7 +1052,7 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict
         if (defer) list[atomicAdd(list_count, 1u)] = r;
         else if (n == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
         else {
-            atomicAdd(&s_good, 1u);                                 // good finds (itree.c:1029)
+            ++good;                                                 // good finds (itree.c:1029)
             if (uix == 1) {                                         // itree.c:1031-1032, 1039-1040
                 out->kind = UTB_STAR; out->label = lab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0;
             } else {
@@ -1317,6 +1075,8 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, utb_result *__restrict
             }
         }
     }
+    for (int o = 16; o; o >>= 1) good += __shfl_xor_sync(0xFFFFFFFFu, good, o);
+    if ((tid & 31u) == 0 && good) atomicAdd(&s_good, good);
     __syncthreads();
     if (tid == 0 && s_good) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)s_good);
 }
@@ -1429,30 +1189,35 @@ __device__ __forceinline__ uint32_t tax_len_of(const DevDB &db, const utb_result
 }
 __global__ void __launch_bounds__(256)
 fmt_len_kernel(DevDB db, const utb_result *__restrict__ res, const uint32_t *__restrict__ name_len, uint32_t n_reads,
-               uint32_t *__restrict__ line_len) {
-    uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const utb_result v = res[r];
-    uint32_t n = 0;
-    if (v.kind != UTB_NONE) {
-        n = __ldg(name_len + r) + 1u + tax_len_of(db, v) + 1u + dec_digits(v.found) + 1u + dec_digits(v.uix) + 1u;
-        n += v.kind == UTB_STAR ? 1u : dec_digits(v.sl) + 1u + dec_digits(v.ol);
-        n += 1u;
+               const uint32_t *__restrict__ dims, uint32_t *__restrict__ line_len) {
+    if (dims) n_reads = dims[0];
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        const utb_result v = res[r];
+        uint32_t n = 0;
+        if (v.kind != UTB_NONE) {
+            n = __ldg(name_len + r) + 1u + tax_len_of(db, v) + 1u + dec_digits(v.found) + 1u + dec_digits(v.uix) + 1u;
+            n += v.kind == UTB_STAR ? 1u : dec_digits(v.sl) + 1u + dec_digits(v.ol);
+            n += 1u;
+        }
+        line_len[r] = n;
     }
-    line_len[r] = n;
 }
 // exclusive scan of u32 (n up to 2^31): block sums, scan of the sums by one block, local scan + base
 #define SCAN_TILE 2048u
 __global__ void __launch_bounds__(256)
-scan_sums_kernel(const uint32_t *__restrict__ in, uint32_t n, uint32_t *__restrict__ sums) {
+scan_sums_kernel(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__restrict__ n_dev, uint32_t n_tiles, uint32_t *__restrict__ sums) {
+    if (n_dev) n = *n_dev;
     __shared__ uint32_t sh[8];
-    const uint32_t base = blockIdx.x * SCAN_TILE;
-    uint32_t acc = 0;
-    for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) acc += in[base + i];
-    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += sh[w]; sums[blockIdx.x] = t; }
+    for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {   // n_tiles covers the host's upper bound of n: tiles past n sum to 0
+        const uint32_t base = t * SCAN_TILE;
+        uint32_t acc = 0;
+        for (uint32_t i = threadIdx.x; i < SCAN_TILE; i += 256) if (base + i < n) acc += in[base + i];
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) { uint32_t x = 0; for (int w = 0; w < 8; ++w) x += sh[w]; sums[t] = x; }
+        __syncthreads();
+    }
 }
 __global__ void __launch_bounds__(1024)
 scan_top_kernel(uint32_t *__restrict__ sums, uint32_t nb, uint32_t *__restrict__ total) {
@@ -1475,25 +1240,29 @@ scan_top_kernel(uint32_t *__restrict__ sums, uint32_t nb, uint32_t *__restrict__
     if (threadIdx.x == 0) *total = carry;
 }
 __global__ void __launch_bounds__(256)
-scan_apply_kernel(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__restrict__ sums, uint32_t *__restrict__ out) {
+scan_apply_kernel(const uint32_t *__restrict__ in, uint32_t n, const uint32_t *__restrict__ n_dev, uint32_t n_tiles,
+                  const uint32_t *__restrict__ sums, uint32_t *__restrict__ out) {
+    if (n_dev) n = *n_dev;
     __shared__ uint32_t sh[8];
     __shared__ uint32_t run;
-    const uint32_t base = blockIdx.x * SCAN_TILE;
-    if (threadIdx.x == 0) run = sums[blockIdx.x];
-    __syncthreads();
-    for (uint32_t c = 0; c < SCAN_TILE; c += 256) {
-        const uint32_t i = base + c + threadIdx.x;
-        const uint32_t v = i < n ? in[i] : 0;
-        uint32_t x = v;
-        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31) >= (uint32_t)o) x += t; }
-        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+    for (uint32_t t = blockIdx.x; t < n_tiles && t * SCAN_TILE < n; t += gridDim.x) {
+        const uint32_t base = t * SCAN_TILE;
+        if (threadIdx.x == 0) run = sums[t];
         __syncthreads();
-        uint32_t wbase = run;
-        for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += sh[w];
-        if (i < n) out[i] = wbase + x - v;
-        __syncthreads();
-        if (threadIdx.x == 255) run = wbase + x;
-        __syncthreads();
+        for (uint32_t c = 0; c < SCAN_TILE; c += 256) {
+            const uint32_t i = base + c + threadIdx.x;
+            const uint32_t v = i < n ? in[i] : 0;
+            uint32_t x = v;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o); if ((threadIdx.x & 31) >= (uint32_t)o) x += y; }
+            if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+            __syncthreads();
+            uint32_t wbase = run;
+            for (uint32_t w = 0; w < (threadIdx.x >> 5); ++w) wbase += sh[w];
+            if (i < n) out[i] = wbase + x - v;
+            __syncthreads();
+            if (threadIdx.x == 255) run = wbase + x;
+            __syncthreads();
+        }
     }
 }
 __device__ __forceinline__ uint32_t put_dec(char *p, uint32_t v) {
@@ -1517,7 +1286,7 @@ slots_kernel(const uint32_t *__restrict__ seq_len, uint32_t n, uint32_t *__restr
 #define FR_BPT 64u              // bytes per thread
 #define FR_BLOCK (256u * FR_BPT)
 #define FR_ERR_NONE 0xFFFFFFFFu
-enum { FRE_NOHEADER = 1, FRE_SEQ_GT = 2, FRE_TOOLONG = 4 };   // codes as in pipeline.c (FE_*)
+enum { FRE_NOHEADER = 1, FRE_SEQ_GT = 2, FRE_TOOLONG = 4, FRE_CHUNK = 7 };   // 1, 2, 4: codes as in pipeline.c (FE_*); 7: the chunk as a whole
 // bit j of the result: byte j of the 64 bytes at p is '\n' (bytes at or beyond n_bytes never match);
 // *nul (optional): whether one of those bytes is 0
 __device__ __forceinline__ uint64_t nl_mask64(const uint8_t *__restrict__ raw, uint64_t at, uint64_t n_bytes, bool *nul = nullptr) {
@@ -1556,7 +1325,8 @@ nl_count_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, uint32_t *__r
 // blk_off: exclusive scan of blk_cnt.  nl[i] = position of newline i, for i < limit.
 __global__ void __launch_bounds__(256)
 nl_index_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, const uint32_t *__restrict__ blk_off,
-                uint32_t limit, uint32_t *__restrict__ nl) {
+                uint32_t limit, const uint32_t *__restrict__ dims, uint32_t *__restrict__ nl) {
+    if (dims) limit = 2u * dims[0];
     __shared__ uint32_t sh[8];
     const uint64_t at = ((uint64_t)blockIdx.x * 256u + threadIdx.x) * FR_BPT;
     uint64_t m = nl_mask64(raw, at, n_bytes);
@@ -1577,58 +1347,74 @@ nl_index_kernel(const uint8_t *__restrict__ raw, uint64_t n_bytes, const uint32_
 // re-frames from this batch on with its own exact reader, which reproduces the reference's message
 // and partial output.
 __global__ void __launch_bounds__(256)
-frame_parse_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ nl, uint32_t n_reads,
+frame_parse_kernel(const uint8_t *__restrict__ raw, const uint32_t *__restrict__ nl, uint32_t n_reads, const uint32_t *__restrict__ dims,
                    uint64_t *__restrict__ seq_off, uint32_t *__restrict__ seq_len,
                    uint32_t *__restrict__ name_off, uint32_t *__restrict__ name_len,
                    uint32_t *__restrict__ slots, uint32_t *__restrict__ err) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_reads) return;
-    const uint32_t hs = r ? nl[2 * r - 1] + 1u : 0u, hn = nl[2 * r], ss = hn + 1u, sn = nl[2 * r + 1];
-    uint32_t code = 0;
-    if (ss - hs >= UTB_LINELEN || sn + 1u - ss >= UTB_LINELEN) code = FRE_TOOLONG;
-    else if (raw[hs] != '>') code = FRE_NOHEADER;                  // itree.c:880
-    else if (raw[ss] == '>') code = FRE_SEQ_GT;                    // itree.c:886
-    if (code) atomicMin(err, (r << 3) | code);
-    uint32_t length = sn - ss;
-    if (length && raw[ss + length - 1] == '\r') --length;          // itree.c:890
-    uint32_t e = hs + 1u;                                          // name: up to the first ' ' or the newline (itree.c:881)
-    while (e < hn && raw[e] != ' ') ++e;
-    seq_off[r] = ss; seq_len[r] = length;
-    name_off[r] = hs + 1u; name_len[r] = e - hs - 1u;
-    slots[r] = (length + 1u + 31u) / 32u;                          // utb_read_slots
+    if (dims) n_reads = dims[0];
+    for (uint64_t r64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r64 < n_reads; r64 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)r64;
+        const uint32_t hs = r ? nl[2 * r - 1] + 1u : 0u, hn = nl[2 * r], ss = hn + 1u, sn = nl[2 * r + 1];
+        uint32_t code = 0;
+        if (ss - hs >= UTB_LINELEN || sn + 1u - ss >= UTB_LINELEN) code = FRE_TOOLONG;
+        else if (raw[hs] != '>') code = FRE_NOHEADER;              // itree.c:880
+        else if (raw[ss] == '>') code = FRE_SEQ_GT;                // itree.c:886
+        if (code) atomicMin(err, (r << 3) | code);
+        uint32_t length = sn - ss;
+        if (length && raw[ss + length - 1] == '\r') --length;      // itree.c:890
+        uint32_t e = hs + 1u;                                      // name: up to the first ' ' or the newline (itree.c:881)
+        while (e < hn && raw[e] != ' ') ++e;
+        seq_off[r] = ss; seq_len[r] = length;
+        name_off[r] = hs + 1u; name_len[r] = e - hs - 1u;
+        slots[r] = (length + 1u + 31u) / 32u;                      // utb_read_slots
+    }
+}
+// Chunk-level verdict of the device-side framing.  The reader cuts a chunk right before a line that begins with
+// '>' (in a well-formed file exactly the header lines do, itree.c:880, 886), so a chunk holds whole records iff
+// its newline count is even; with that, no NUL byte (strlen() semantics, itree.c:887) and every record well formed
+// (frame_parse_kernel), the next chunk starts on a header line again -- by induction the framing equals the
+// reference's strictly pairwise fgets (itree.c:869-871).  Anything else is reported as record 0 / FRE_CHUNK and
+// the host re-reads from this chunk on with its exact reader.
+__global__ void frame_setup_kernel(const uint32_t *__restrict__ info, uint32_t max_reads, uint32_t *__restrict__ dims, uint32_t *__restrict__ err) {
+    const uint32_t n_lines = info[0], nul = info[1];
+    const bool bad = nul || (n_lines & 1u) || !n_lines || (n_lines >> 1) > max_reads;
+    dims[0] = bad ? 0u : n_lines >> 1;
+    if (bad) atomicMin(err, (uint32_t)FRE_CHUNK);
 }
 
 #define FW_WARPS 8
 __global__ void __launch_bounds__(FW_WARPS * 32)
 fmt_write_kernel(DevDB db, const utb_result *__restrict__ res, const uint8_t *__restrict__ raw,
                  const uint32_t *__restrict__ name_off, const uint32_t *__restrict__ name_len,
-                 const uint32_t *__restrict__ line_off, uint32_t n_reads, char *__restrict__ text) {
+                 const uint32_t *__restrict__ line_off, uint32_t n_reads, const uint32_t *__restrict__ dims, char *__restrict__ text) {
+    if (dims) n_reads = dims[0];
     __shared__ char s_tail[FW_WARPS][48];
     const uint32_t lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
-    const uint32_t r = blockIdx.x * FW_WARPS + wib;
-    if (r >= n_reads) return;
-    const utb_result v = res[r];
-    if (v.kind == UTB_NONE) return;
-    char *out = text + line_off[r];
-    const uint32_t nl = __ldg(name_len + r), tl = tax_len_of(db, v);
-    const uint8_t *nm = raw + __ldg(name_off + r);
-    const char *lab = db.blob + __ldg(db.off + v.label);
-    uint32_t tn = 0;
-    if (lane == 0) {                                               // "\t<found>\t<uix>\t*\n" or "...\t<sl>;<ol>\n"
-        char *t = s_tail[wib];
-        t[tn++] = '\t'; tn += put_dec(t + tn, v.found);
-        t[tn++] = '\t'; tn += put_dec(t + tn, v.uix);
-        t[tn++] = '\t';
-        if (v.kind == UTB_STAR) t[tn++] = '*';
-        else { tn += put_dec(t + tn, v.sl); t[tn++] = ';'; tn += put_dec(t + tn, v.ol); }
-        t[tn++] = '\n';
+    for (uint64_t r = (uint64_t)blockIdx.x * FW_WARPS + wib; r < n_reads; r += (uint64_t)gridDim.x * FW_WARPS) {
+        const utb_result v = res[r];
+        if (v.kind == UTB_NONE) continue;
+        char *out = text + line_off[r];
+        const uint32_t nl = __ldg(name_len + r), tl = tax_len_of(db, v);
+        const uint8_t *nm = raw + __ldg(name_off + r);
+        const char *lab = db.blob + __ldg(db.off + v.label);
+        uint32_t tn = 0;
+        __syncwarp();                                              // the previous round's readers of s_tail are done
+        if (lane == 0) {                                           // "\t<found>\t<uix>\t*\n" or "...\t<sl>;<ol>\n"
+            char *t = s_tail[wib];
+            t[tn++] = '\t'; tn += put_dec(t + tn, v.found);
+            t[tn++] = '\t'; tn += put_dec(t + tn, v.uix);
+            t[tn++] = '\t';
+            if (v.kind == UTB_STAR) t[tn++] = '*';
+            else { tn += put_dec(t + tn, v.sl); t[tn++] = ';'; tn += put_dec(t + tn, v.ol); }
+            t[tn++] = '\n';
+        }
+        tn = __shfl_sync(0xFFFFFFFFu, tn, 0);
+        __syncwarp();
+        for (uint32_t i = lane; i < nl; i += 32) out[i] = (char)nm[i];
+        if (lane == 0) out[nl] = '\t';
+        for (uint32_t i = lane; i < tl; i += 32) out[nl + 1 + i] = lab[i];
+        for (uint32_t i = lane; i < tn; i += 32) out[nl + 1 + tl + i] = s_tail[wib][i];
     }
-    tn = __shfl_sync(0xFFFFFFFFu, tn, 0);
-    __syncwarp();
-    for (uint32_t i = lane; i < nl; i += 32) out[i] = (char)nm[i];
-    if (lane == 0) out[nl] = '\t';
-    for (uint32_t i = lane; i < tl; i += 32) out[nl + 1 + i] = lab[i];
-    for (uint32_t i = lane; i < tn; i += 32) out[nl + 1 + tl + i] = s_tail[wib][i];
 }
 
 // ---------------------------------------------------------------------------
@@ -1683,28 +1469,53 @@ static int check_device(int device) {
     return UTB_OK;
 }
 
-// host (pageable / mmap'ed) -> device through two pinned bounce buffers so the
-// page-cache copy of chunk i+1 overlaps the PCIe copy of chunk i
-static int upload_streamed(void *dst, const void *src, size_t n, cudaStream_t st) {
-    const size_t CH = (size_t)64 << 20;
-    void *pin[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2];
-    CK(cudaMallocHost(&pin[0], CH));
-    CK(cudaMallocHost(&pin[1], CH));
-    CK(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    int k = 0;
-    for (size_t o = 0; o < n; o += CH, k ^= 1) {
-        size_t c = n - o < CH ? n - o : CH;
-        CK(cudaEventSynchronize(ev[k]));
-        memcpy(pin[k], (const char *)src + o, c);
-        CK(cudaMemcpyAsync((char *)dst + o, pin[k], c, cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(ev[k], st));
+// host (pageable / mmap'ed) -> device: UP_THREADS workers, each with its own pinned bounce buffer and
+// stream, take the chunks round-robin, so the page-cache copies run in parallel and overlap the PCIe
+// copies (one thread and one memcpy moved ~3 GB/s: 2.4 s for an 8 GB tree)
+#include <pthread.h>
+#define UP_CHUNK ((size_t)32 << 20)
+#define UP_THREADS 6
+struct up_job { int device; char *dst; const char *src; size_t n; int t, nt; int rc; char err[256]; };
+static void *up_worker(void *a_) {
+    up_job *j = (up_job *)a_;
+    void *pin = nullptr; cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaSetDevice(j->device);
+    if (e == cudaSuccess) e = cudaMallocHost(&pin, UP_CHUNK);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    for (size_t o = (size_t)j->t * UP_CHUNK; e == cudaSuccess && o < j->n; o += (size_t)j->nt * UP_CHUNK) {
+        const size_t c = j->n - o < UP_CHUNK ? j->n - o : UP_CHUNK;
+        e = cudaEventSynchronize(ev);                              // the previous copy out of this buffer is done
+        if (e != cudaSuccess) break;
+        memcpy(pin, j->src + o, c);
+        e = cudaMemcpyAsync(j->dst + o, pin, c, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaEventRecord(ev, st);
     }
-    CK(cudaStreamSynchronize(st));
-    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
-    cudaFreeHost(pin[0]); cudaFreeHost(pin[1]);
-    return UTB_OK;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { j->rc = UTB_ERR_CUDA; snprintf(j->err, sizeof j->err, "CUDA error %s during upload (%s)", cudaGetErrorName(e), cudaGetErrorString(e)); }
+    if (ev) cudaEventDestroy(ev);
+    if (st) cudaStreamDestroy(st);
+    if (pin) cudaFreeHost(pin);
+    return nullptr;
+}
+static int upload_streamed(int device, void *dst, const void *src, size_t n) {
+    int nt = (int)((n + UP_CHUNK - 1) / UP_CHUNK);
+    if (nt > UP_THREADS) nt = UP_THREADS;
+    if (nt < 1) return UTB_OK;
+    up_job job[UP_THREADS];
+    pthread_t th[UP_THREADS];
+    int started = 0, rc = UTB_OK;
+    for (int t = 0; t < nt; ++t) {
+        job[t].device = device; job[t].dst = (char *)dst; job[t].src = (const char *)src; job[t].n = n; job[t].t = t; job[t].nt = nt; job[t].rc = UTB_OK;
+        if (t == nt - 1 || pthread_create(&th[t], nullptr, up_worker, &job[t])) { up_worker(&job[t]); if (t != nt - 1) job[t].t = -1; }   // last share (or a failed spawn) runs here
+        else ++started;
+    }
+    for (int t = 0; t < nt; ++t) {
+        if (t != nt - 1 && job[t].t >= 0) pthread_join(th[t], nullptr);
+        if (job[t].rc && !rc) { rc = job[t].rc; utb_set_error("%s", job[t].err); }
+    }
+    (void)started;
+    return rc;
 }
 
 static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db);
@@ -1722,30 +1533,30 @@ extern "C" int utb_db_upload(const utb_ctr *ctr, int device, utb_db **out) {
     *out = db;
     return UTB_OK;
 }
+// errors inside db_upload_impl / utb_db_clone: everything allocated so far hangs off `db`, which the caller frees
+static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs);
 static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db) {
     int rc;
-    cudaStream_t st;
-    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-    size_t nb_binix = (size_t)UTB_NUMBINS * ctr->binix_bytes;
-    size_t nb_recs = (size_t)(ctr->num_nodes * ctr->sz);
-    size_t nl = ctr->max_ix;
+    const size_t nb_binix = (size_t)UTB_NUMBINS * ctr->binix_bytes;
+    const size_t nb_recs = (size_t)(ctr->num_nodes * ctr->sz);
+    const size_t nl = ctr->max_ix;
+    if (cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || db->sm_count < 1) { cudaGetLastError(); db->sm_count = 148; }
     CK(cudaMalloc(&db->binix, nb_binix + 64));
     CK(cudaMalloc(&db->recs, nb_recs + 64));                       // +slack: itree.c:766
     CK(cudaMalloc(&db->blob, ctr->blob_len + 64));
     CK(cudaMalloc(&db->off, (nl + 1) * 4));
     CK(cudaMalloc(&db->rank, (nl + 1) * 4));
     CK(cudaMalloc(&db->by_rank, (nl + 1) * 4));
-    CK(cudaMemsetAsync((char *)db->binix + nb_binix, 0, 64, st));
-    CK(cudaMemsetAsync((char *)db->recs + nb_recs, 0, 64, st));
-    CK(cudaMemsetAsync(db->blob, 0, ctr->blob_len + 64, st));
-    rc = upload_streamed(db->binix, ctr->binix_raw, nb_binix, st); if (rc) return rc;
-    rc = upload_streamed(db->recs, ctr->recs, nb_recs, st); if (rc) return rc;
-    CK(cudaMemcpyAsync(db->blob, ctr->blob, ctr->blob_len, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(db->off, ctr->off, (nl + 1) * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(db->rank, ctr->rank, nl * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(db->by_rank, ctr->by_rank, nl * 4, cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaStreamDestroy(st));
+    CK(cudaMemset((char *)db->binix + nb_binix, 0, 64));
+    CK(cudaMemset((char *)db->recs + nb_recs, 0, 64));
+    CK(cudaMemset(db->blob, 0, ctr->blob_len + 64));
+    rc = upload_streamed(device, db->binix, ctr->binix_raw, nb_binix); if (rc) return rc;
+    rc = upload_streamed(device, db->recs, ctr->recs, nb_recs); if (rc) return rc;
+    CK(cudaMemcpy(db->blob, ctr->blob, ctr->blob_len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db->off, ctr->off, (nl + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db->rank, ctr->rank, nl * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db->by_rank, ctr->by_rank, nl * 4, cudaMemcpyHostToDevice));
+    db->nb_binix = nb_binix; db->nb_recs = nb_recs; db->nb_blob = ctr->blob_len + 64; db->nb_lab = (nl + 1) * 4;
     db->d.binix32 = ctr->binix_bytes == 4 ? (const uint32_t *)db->binix : nullptr;
     db->d.binix64 = ctr->binix_bytes == 8 ? (const uint64_t *)db->binix : nullptr;
     db->d.recs = (const uint8_t *)db->recs;
@@ -1755,110 +1566,187 @@ static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db) {
     db->d.off = (const uint32_t *)db->off;
     db->d.rank = (const uint32_t *)db->rank;
     db->d.by_rank = (const uint32_t *)db->by_rank;
-    db->hbm_bytes = nb_binix + nb_recs + ctr->blob_len + 3 * (nl + 1) * 4;
     for (size_t i = 0; i < nl; ++i) { size_t l = ctr->off[i + 1] - ctr->off[i]; if (l > db->max_label) db->max_label = l; }
-    // Is the CTR regular (what utree-compress emits: every bucket strictly
-    // sorted, at most the first-bin quirk)?  Then the interpolation search is
-    // exact; otherwise keep the reference's probe sequence.
+    return db_build_tables(db, nb_binix, nb_recs);
+}
+template <typename F> static void launch_per_bin(uint64_t n_records, F f) {
+    // lanes per prefix bin: about half the mean bucket (1 .. 32)
+    const uint64_t mean = n_records >> 24;
+    int g = 1;
+    while (g < 32 && (uint64_t)g * 2 <= mean) g <<= 1;
+    f(g, (unsigned)(((uint64_t)(UTB_NUMBINS - 1) * g + 255) / 256));
+}
+static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
+    const size_t fixed = db->nb_blob + 3 * db->nb_lab;
+    db->hbm_bytes = nb_binix + nb_recs + fixed;
+    // Is the CTR regular (what utree-compress emits: every bucket strictly sorted, at most the first-bin
+    // quirk)?  Then the record words are distinct and a hash table answers exactly what xtSuffixBS
+    // answers; otherwise keep the reference's probe sequence on the on-disk image.
     {
         db->d.quirk_bin = 0xFFFFFFFFu;
         unsigned long long *d_out, h_out[4] = {0, 0, ~0ull, ~0ull};
         CK(cudaMalloc(&d_out, 32));
-        CK(cudaMemcpy(d_out, h_out, 32, cudaMemcpyHostToDevice));
-        verify_kernel<<<(UTB_NUMBINS - 1 + 255) / 256, 256>>>(db->d, d_out);
-        CK(cudaGetLastError());
-        CK(cudaMemcpy(h_out, d_out, 32, cudaMemcpyDeviceToHost));
+        cudaError_t e = cudaMemcpy(d_out, h_out, 32, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) { verify_kernel<<<(UTB_NUMBINS - 1 + 255) / 256, 256>>>(db->d, d_out); e = cudaGetLastError(); }
+        if (e == cudaSuccess) e = cudaMemcpy(h_out, d_out, 32, cudaMemcpyDeviceToHost);
         cudaFree(d_out);
+        CK(e);
         db->regular = h_out[0] == 0 && (h_out[1] == 0 || (h_out[1] == 1 && h_out[2] == h_out[3]));
         if (db->regular && h_out[1] == 1) db->d.quirk_bin = (uint32_t)h_out[2];
         const char *lk = getenv("UTB_LOOKUP");                      // "exact" forces the reference probe sequence
-        db->use_interp = db->regular && !(lk && !strcmp(lk, "exact"));
+        db->use_table = db->regular && !(lk && !strcmp(lk, "exact"));
     }
-    if (db->use_interp) {
-        // one-time re-layout (slack after the last record: a window load may overrun into it)
-        const size_t n = (size_t)ctr->num_nodes;
-        size_t lay_bytes;
-        if (ctr->ix_bytes == 2) {                                  // key/aux interleaved per 128-byte line
-            const size_t blocks = (n + 15) / 16 + 2;
-            lay_bytes = blocks * 128;
-            CK(cudaMalloc(&db->keys, lay_bytes));
-            CK(cudaMemset(db->keys, 0xFF, lay_bytes));
-            relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, (uint32_t *)db->keys, nullptr, nullptr);
-        } else {
-            lay_bytes = (n + 32) * 12;
-            CK(cudaMalloc(&db->keys, (n + 32) * 4));
-            CK(cudaMalloc(&db->aux, (n + 32) * 8));
-            CK(cudaMemset((char *)db->keys + n * 4, 0xFF, 32 * 4));
-            relayout_kernel<<<(unsigned)((n + 255) / 256), 256>>>(db->d, nullptr, (uint32_t *)db->keys, (uint64_t *)db->aux);
+    if (db->use_table) {
+        const uint64_t n = db->d.num_nodes;
+        // sector hash table at load <= 0.5 (4 entries per sector); grown if a record cannot be placed within KT_MAXD sectors
+        uint64_t sectors = n / 2 + 1;
+        if (sectors < KT_MIN_SECTORS) sectors = KT_MIN_SECTORS;
+        uint32_t *d_ovf;
+        CK(cudaMalloc(&d_ovf, 4));
+        for (int attempt = 0;; ++attempt) {
+            cudaError_t e = cudaMalloc(&db->ktab, sectors * 32);
+            if (e == cudaSuccess && db->d.ix_bytes == 4) e = cudaMalloc(&db->kvals, sectors * 16);
+            if (e == cudaSuccess) e = cudaMemset(db->ktab, 0, sectors * 32);
+            if (e == cudaSuccess) e = cudaMemset(d_ovf, 0, 4);
+            if (e != cudaSuccess) { cudaFree(d_ovf); CK(e); }
+            DevDB dd = db->d;
+            unsigned long long *kt = (unsigned long long *)db->ktab; uint32_t *kv = (uint32_t *)db->kvals;
+            launch_per_bin(n, [&](int g, unsigned blocks) {
+                switch (g) {
+                case 1: ktab_build_kernel<1><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                case 2: ktab_build_kernel<2><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                case 4: ktab_build_kernel<4><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                case 8: ktab_build_kernel<8><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                case 16: ktab_build_kernel<16><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                default: ktab_build_kernel<32><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                }
+            });
+            uint32_t ovf = 0;
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpy(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { cudaFree(d_ovf); CK(e); }
+            if (!ovf) break;
+            cudaFree(db->ktab); cudaFree(db->kvals); db->ktab = db->kvals = nullptr;
+            if (attempt == 3) { cudaFree(d_ovf); utb_set_error("cannot build the lookup table (%u records unplaced)", ovf); return UTB_ERR_LIMIT; }
+            sectors += sectors / 2;
         }
-        CK(cudaGetLastError());
-        CK(cudaDeviceSynchronize());
-        db->d.kv = ctr->ix_bytes == 2 ? (const uint32_t *)db->keys : nullptr;
-        db->d.keys = ctr->ix_bytes == 2 ? nullptr : (const uint32_t *)db->keys;
-        db->d.aux64 = ctr->ix_bytes == 2 ? nullptr : (const uint64_t *)db->aux;
-        CK(cudaFree(db->recs));                                    // the byte-packed blob is no longer needed
-        db->recs = nullptr; db->d.recs = nullptr;
-        db->hbm_bytes = nb_binix + lay_bytes + ctr->blob_len + 3 * (nl + 1) * 4;
-        const char *bm = getenv("UTB_BLOOM");                      // 0 off, 1 always, default auto
-        db->bloom_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
-        if (db->bloom_mode) {
-            // 16 bits per record: 8 records per 128-bit block -> ~0.1 % false positives
-            uint64_t blocks = n / 8 + 1024;
-            CK(cudaMalloc(&db->bloom, blocks * 16));
-            CK(cudaMemset(db->bloom, 0, blocks * 16));
-            db->d.bloom_blocks = blocks;
-            bloom_build_kernel<<<(UTB_NUMBINS - 1 + 255) / 256, 256>>>(db->d, (uint32_t *)db->bloom);
+        cudaFree(d_ovf);
+        db->d.ktab = (const uint64_t *)db->ktab; db->d.kvals = (const uint32_t *)db->kvals; db->d.kt_sectors = sectors;
+        db->nb_ktab = sectors * 32; db->nb_kvals = db->kvals ? sectors * 16 : 0;
+        const char *bm = getenv("UTB_SIEVE");                      // 0 off, 1 always, default auto
+        db->sieve_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
+        if (db->sieve_mode) {
+            // SV_RPL records per 128-byte line = ~43 bits per record: ~0.04 % false positives
+            const uint64_t lines = n / SV_RPL + 1024;
+            if (lines >= ((uint64_t)1 << 32)) { utb_set_error("tree too large for the sieve"); return UTB_ERR_LIMIT; }
+            CK(cudaMalloc(&db->sieve, lines * 128));
+            CK(cudaMemset(db->sieve, 0, lines * 128));
+            db->d.sv_lines = lines;
+            DevDB dd = db->d;
+            uint32_t *sv = (uint32_t *)db->sieve;
+            launch_per_bin(n, [&](int g, unsigned blocks) {
+                switch (g) {
+                case 1: sieve_build_kernel<1><<<blocks, 256>>>(dd, sv); break;
+                case 2: sieve_build_kernel<2><<<blocks, 256>>>(dd, sv); break;
+                case 4: sieve_build_kernel<4><<<blocks, 256>>>(dd, sv); break;
+                case 8: sieve_build_kernel<8><<<blocks, 256>>>(dd, sv); break;
+                case 16: sieve_build_kernel<16><<<blocks, 256>>>(dd, sv); break;
+                default: sieve_build_kernel<32><<<blocks, 256>>>(dd, sv); break;
+                }
+            });
             CK(cudaGetLastError());
             CK(cudaDeviceSynchronize());
-            db->d.bloom = (const uint4 *)db->bloom;
-            db->hbm_bytes += blocks * 16;
+            db->d.sieve = (const uint2 *)db->sieve;
+            db->nb_sieve = lines * 128;
+        }
+        CK(cudaDeviceSynchronize());
+        CK(cudaFree(db->recs)); CK(cudaFree(db->binix));           // the on-disk image is no longer needed
+        db->recs = db->binix = nullptr; db->d.recs = nullptr; db->d.binix32 = nullptr; db->d.binix64 = nullptr;
+        db->nb_recs = db->nb_binix = 0;
+        db->hbm_bytes = db->nb_ktab + db->nb_kvals + db->nb_sieve + fixed;
+    } else {
+        // Reference probe sequence: the hot prefix table pinned in L2 -- reserve persisting lines for the
+        // index so the record traffic does not evict it (applied per stream in utb_batch_create).
+        cudaDeviceProp p;
+        CK(cudaGetDeviceProperties(&p, db->device));
+        const char *env = getenv("UTB_L2_PERSIST");
+        if ((!env || atoi(env) != 0) && p.persistingL2CacheMaxSize > 0 && p.accessPolicyMaxWindowSize > 0) {
+            size_t want = nb_binix < (size_t)p.persistingL2CacheMaxSize ? nb_binix : (size_t)p.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                db->l2_window = 1;
+                db->l2_window_bytes = nb_binix < (size_t)p.accessPolicyMaxWindowSize ? nb_binix : (size_t)p.accessPolicyMaxWindowSize;
+                // a window larger than the set-aside would thrash it: persist only the fraction that fits
+                db->l2_hit_ratio = want >= db->l2_window_bytes ? 1.0f : (float)((double)want / (double)db->l2_window_bytes);
+            } else cudaGetLastError();
         }
     }
-    // Hot prefix table pinned in L2: reserve persisting lines for the index so
-    // the streaming record traffic does not evict it (applied per stream in
-    // utb_batch_create).
-    cudaDeviceProp p;
-    CK(cudaGetDeviceProperties(&p, device));
-    const char *env = getenv("UTB_L2_PERSIST");
-    if ((!env || atoi(env) != 0) && p.persistingL2CacheMaxSize > 0 && p.accessPolicyMaxWindowSize > 0) {
-        size_t want = nb_binix < (size_t)p.persistingL2CacheMaxSize ? nb_binix : (size_t)p.persistingL2CacheMaxSize;
-        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
-            db->l2_window = 1;
-            db->l2_window_bytes = nb_binix < (size_t)p.accessPolicyMaxWindowSize ? nb_binix : (size_t)p.accessPolicyMaxWindowSize;
-            // a window larger than the set-aside would thrash it: persist only the fraction that fits
-            db->l2_hit_ratio = want >= db->l2_window_bytes ? 1.0f : (float)((double)want / (double)db->l2_window_bytes);
-            const char *hr = getenv("UTB_L2_HITRATIO");
-            if (hr) db->l2_hit_ratio = (float)atof(hr);
-        } else cudaGetLastError();
+    if (getenv("UTB_STATS"))
+        fprintf(stderr, "utree-b200: device %d: %s, %.2f GB resident (table %.2f GB, sieve %.2f GB)\n", db->device,
+                db->use_table ? "sector hash table" : "reference probe sequence", db->hbm_bytes / 1e9,
+                (db->nb_ktab + db->nb_kvals) / 1e9, db->nb_sieve / 1e9);
+    return UTB_OK;
+}
+
+// A second GPU gets the finished tables from the first one over NVLink (peer copy) instead of a
+// second PCIe upload and rebuild.
+extern "C" int utb_db_clone(const utb_db *src, int device, utb_db **out) {
+    if (!src || !out) { utb_set_error("utb_db_clone: null argument"); return UTB_ERR_ARG; }
+    *out = nullptr;
+    int rc = check_device(device);
+    if (rc) return rc;
+    CK(cudaSetDevice(device));
+    utb_db *db = (utb_db *)calloc(1, sizeof(utb_db));
+    if (!db) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    *db = *src;
+    db->device = device;
+    db->binix = db->recs = db->blob = db->off = db->rank = db->by_rank = db->ktab = db->kvals = db->sieve = nullptr;
+    if (cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || db->sm_count < 1) { cudaGetLastError(); db->sm_count = 148; }
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(src->device, 0);
+        if (e != cudaSuccess) cudaGetLastError();                   // already enabled, or staged through the host by the runtime
+    } else cudaGetLastError();
+    struct { void **dst; void *from; size_t n; } parts[] = {
+        {&db->binix, src->binix, src->nb_binix ? src->nb_binix + 64 : 0}, {&db->recs, src->recs, src->nb_recs ? src->nb_recs + 64 : 0},
+        {&db->blob, src->blob, src->nb_blob}, {&db->off, src->off, src->nb_lab}, {&db->rank, src->rank, src->nb_lab},
+        {&db->by_rank, src->by_rank, src->nb_lab}, {&db->ktab, src->ktab, src->nb_ktab}, {&db->kvals, src->kvals, src->nb_kvals},
+        {&db->sieve, src->sieve, src->nb_sieve}};
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < sizeof parts / sizeof parts[0] && e == cudaSuccess; ++i) {
+        if (!parts[i].n || !parts[i].from) continue;
+        e = cudaMalloc(parts[i].dst, parts[i].n);
+        if (e == cudaSuccess) e = cudaMemcpyPeer(*parts[i].dst, device, parts[i].from, src->device, parts[i].n);
     }
-    const char *fg = getenv("UTB_L2_FETCH");                        // DRAM->L2 fetch granularity hint: 32 / 64 / 128
-    if (fg && atoi(fg) > 0 && cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)) != cudaSuccess) cudaGetLastError();
-    if (getenv("UTB_STATS")) {
-        size_t fgv = 0, pl = 0;
-        cudaDeviceGetLimit(&fgv, cudaLimitMaxL2FetchGranularity);
-        cudaDeviceGetLimit(&pl, cudaLimitPersistingL2CacheSize);
-        fprintf(stderr, "utree-b200: device %d %s: L2 %d MiB, persisting max %d MiB (set %zu MiB), window max %d MiB, "
-                "fetch granularity %zu B, binix window %zu MiB hitRatio %.2f\n", device, p.name, p.l2CacheSize >> 20,
-                p.persistingL2CacheMaxSize >> 20, pl >> 20, p.accessPolicyMaxWindowSize >> 20, fgv,
-                db->l2_window_bytes >> 20, db->l2_hit_ratio);
+    if (e != cudaSuccess) {
+        utb_set_error("CUDA error %s cloning the tree to device %d (%s)", cudaGetErrorName(e), device, cudaGetErrorString(e));
+        utb_db_free(db);
+        return UTB_ERR_CUDA;
     }
+    db->d.binix32 = src->d.binix32 ? (const uint32_t *)db->binix : nullptr;
+    db->d.binix64 = src->d.binix64 ? (const uint64_t *)db->binix : nullptr;
+    db->d.recs = (const uint8_t *)db->recs;
+    db->d.blob = (const char *)db->blob; db->d.off = (const uint32_t *)db->off;
+    db->d.rank = (const uint32_t *)db->rank; db->d.by_rank = (const uint32_t *)db->by_rank;
+    db->d.ktab = (const uint64_t *)db->ktab; db->d.kvals = (const uint32_t *)db->kvals; db->d.sieve = (const uint2 *)db->sieve;
+    if (db->l2_window && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, db->l2_window_bytes) != cudaSuccess) { cudaGetLastError(); db->l2_window = 0; }
+    *out = db;
     return UTB_OK;
 }
 
 extern "C" void utb_db_free(utb_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob); cudaFree(db->keys); cudaFree(db->aux); cudaFree(db->bloom);
+    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob); cudaFree(db->ktab); cudaFree(db->kvals); cudaFree(db->sieve);
     cudaFree(db->off); cudaFree(db->rank); cudaFree(db->by_rank);
     free(db);
 }
 extern "C" uint64_t utb_db_hbm_bytes(const utb_db *db) { return db ? db->hbm_bytes : 0; }
-extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_interp : 0; }
+extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_table : 0; }
+extern "C" int utb_db_device(const utb_db *db) { return db ? db->device : -1; }
 
 // ---------------------------------------------------------------------------
 // C ABI: batches
 // ---------------------------------------------------------------------------
-#define VB_BLOCKS 148
 
 struct utb_batch {
     utb_db *db;
@@ -1872,7 +1760,7 @@ struct utb_batch {
     uint32_t *h_name_off, *h_name_len; char *h_text; uint32_t *h_text_len; size_t text_cap;   // device-side formatting
     // device
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
-    uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits;
+    uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits; uint64_t *d_pkr;
     utb_result *d_results; uint32_t *d_gen_list; uint32_t *d_gen_count; uint32_t *d_warp_list; uint32_t *d_warp_count;
     uint32_t *d_name_off, *d_name_len, *d_line_len, *d_line_off, *d_scan_sums, *d_text_len; char *d_text;
     int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
@@ -1880,13 +1768,14 @@ struct utb_batch {
     uint32_t *d_hist, *d_tlab, *d_tcnt;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
-    uint64_t *d_pwords; uint32_t *d_ppos; uint32_t *d_pfill; uint32_t *d_pctr; uint64_t p_total, part_min_pos;   // partitioned filter pass
     // last submit
-    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_bloom; int used_partition;
+    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_sieve;
     uint64_t launches;
     // device-side framing
-    uint32_t *d_nl, *d_blk, *d_frame_err, *d_ngroups, *h_frame_err; const uint32_t *ngroups_dev; int framed_on_device;
-    uint32_t *d_frame_info, *h_frame_info; cudaEvent_t count_ready; size_t raw_bytes;   // [0] newlines of the chunk, [1] NUL seen
+    uint32_t *d_nl, *d_blk, *d_frame_err, *h_frame_err; int framed_on_device;
+    uint32_t *d_frame_info;                                        // [0] newlines of the chunk, [1] NUL seen
+    uint32_t *d_dims, *h_dims; const uint32_t *dims_dev;           // [0] records, [1] position groups of the batch as the device derived them
+    size_t in_bytes;                                               // raw bytes of the last submit
 };
 
 extern "C" uint64_t utb_read_slots(uint32_t len) { return ((uint64_t)len + 1 + 31) / 32; }
@@ -1908,13 +1797,12 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_text_len); cudaFree(b->d_text);
     if (b->text_len_ready) cudaEventDestroy(b->text_len_ready);
     cudaFree(b->d_raw); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_grp_off);
-    cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results);
+    cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results); cudaFree(b->d_pkr);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_warp_list); cudaFree(b->d_warp_count); cudaFree(b->d_counters);
     cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
-    cudaFree(b->d_pwords); cudaFree(b->d_ppos); cudaFree(b->d_pfill); cudaFree(b->d_pctr);
-    cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFree(b->d_ngroups); cudaFreeHost(b->h_frame_err);
-    cudaFree(b->d_frame_info); cudaFreeHost(b->h_frame_info); if (b->count_ready) cudaEventDestroy(b->count_ready);
+    cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFreeHost(b->h_frame_err);
+    cudaFree(b->d_frame_info); cudaFree(b->d_dims); cudaFreeHost(b->h_dims);
     if (b->done) cudaEventDestroy(b->done);
     for (int i = 0; i < 7; ++i) if (b->ev[i]) cudaEventDestroy(b->ev[i]);
     if (b->st) cudaStreamDestroy(b->st);
@@ -1955,6 +1843,8 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_line_off, (max_reads + 1) * 4));
     BK(cudaMalloc(&b->d_scan_sums, (max_reads / SCAN_TILE + 2) * 4));
     BK(cudaMalloc(&b->d_text_len, 4));
+    BK(cudaMalloc(&b->d_dims, 8));
+    BK(cudaMallocHost(&b->h_dims, 8));
     BK(cudaMalloc(&b->d_raw, max_bytes + 128));
     BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
     BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
@@ -1968,30 +1858,22 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_warp_list, max_reads * 4));
     BK(cudaMalloc(&b->d_warp_count, 4));
     BK(cudaMalloc(&b->d_counters, 4 * COUNTER_SLOTS * 8));
-    BK(cudaMalloc(&b->d_hist, (size_t)VB_BLOCKS * nl * 4));
-    BK(cudaMalloc(&b->d_tlab, (size_t)VB_BLOCKS * nl * 4));
-    BK(cudaMalloc(&b->d_tcnt, (size_t)VB_BLOCKS * nl * 4));
-    BK(cudaMemset(b->d_hist, 0, (size_t)VB_BLOCKS * nl * 4));
+    BK(cudaMalloc(&b->d_hist, (size_t)db->sm_count * nl * 4));
+    BK(cudaMalloc(&b->d_tlab, (size_t)db->sm_count * nl * 4));
+    BK(cudaMalloc(&b->d_tcnt, (size_t)db->sm_count * nl * 4));
+    BK(cudaMemset(b->d_hist, 0, (size_t)db->sm_count * nl * 4));
     BK(cudaMemset(b->d_raw, 0, max_bytes + 128));
-    if (db->bloom) {                                               // queue for a quarter of the lookup slots; overflow resolves inline
+    if (db->sieve) {                                               // queue for a quarter of the lookup slots; overflow resolves inline
         b->q_cap = npos * 2 / 4 + 4096;
+        const char *qc = getenv("UTB_QCAP");                       // tests: a tiny queue forces the overflow path
+        if (qc && atoll(qc) > 0) b->q_cap = (uint64_t)atoll(qc);
+        b->q_cap = (b->q_cap + Q_CHUNK - 1) / Q_CHUNK * Q_CHUNK;    // whole chunks: the consumer reads [0, min(count, cap)) and every entry of it is written
         BK(cudaMalloc(&b->d_qwords, b->q_cap * 8));
         BK(cudaMalloc(&b->d_qslots, b->q_cap * 4));
+        BK(cudaMemset(b->d_qslots, 0xFF, b->q_cap * 4));            // Q_INVALID
         BK(cudaMalloc(&b->d_qcount, 8));
         BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
-        // Partitioned filter pass: pays once a batch holds enough positions for the probes of a partition to
-        // reuse its filter lines (and to amortise 64 grid barriers); UTB_PARTITION=1 forces it, =0 disables it.
-        const char *pe = getenv("UTB_PARTITION");
-        b->part_min_pos = pe ? (atoi(pe) ? 0 : ~0ull) : PART_MIN_POS;
-        const char *pm = getenv("UTB_PARTITION_MIN_MPOS");         // threshold in Mi positions (tuning)
-        if (pm && atoi(pm) > 0) b->part_min_pos = (uint64_t)atoi(pm) << 20;
-        if (npos >= b->part_min_pos) {                              // one region per (CTA, partition), 25 % head-room
-            b->p_total = (uint64_t)((double)npos * 1.25) + (uint64_t)P_CTAS * NPART * 68;
-            BK(cudaMalloc(&b->d_pwords, b->p_total * 8));
-            BK(cudaMalloc(&b->d_ppos, b->p_total * 4));
-            BK(cudaMalloc(&b->d_pfill, (size_t)P_CTAS * NPART * 4));
-            BK(cudaMalloc(&b->d_pctr, NPART * 4));
-        }
+        BK(cudaMalloc(&b->d_pkr, (b->max_groups + 2) * 8));
     }
     if (db->l2_window) {
         cudaStreamAttrValue a;
@@ -2008,6 +1890,12 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     return UTB_OK;
 }
 
+// grid of a grid-stride kernel: enough CTAs for n items of `per` each, at most `waves` CTAs per SM
+static unsigned gs_grid(const utb_batch *b, uint64_t n, uint32_t per, unsigned waves) {
+    const uint64_t need = (n + per - 1) / per, cap = (uint64_t)b->db->sm_count * waves;
+    return (unsigned)(need < cap ? (need ? need : 1) : cap);
+}
+
 // launches the device stages on b->st; if timed, records ev[0..4] around them
 static int launch_stages(utb_batch *b, bool timed) {
     const DevDB &d = b->db->d;
@@ -2018,65 +1906,37 @@ static int launch_stages(utb_batch *b, bool timed) {
     CK(cudaMemsetAsync(b->d_counters, 0, 4 * COUNTER_SLOTS * 8, b->st));
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
-        pack_kernel<<<(n_groups + 1 + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
-                                                                   n_reads, n_groups, b->ngroups_dev, b->d_pk, b->d_bad);
+        pack_kernel<<<gs_grid(b, (uint64_t)n_groups + 1, 256, 32), 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
+                                                                   n_reads, n_groups, b->dims_dev, b->d_pk, b->d_bad, b->d_pkr);
         b->launches++;
     }
     if (timed) CK(cudaEventRecord(b->ev[1], b->st));
     if (n_pos) {
         const unsigned nb = (unsigned)(((uint64_t)n_pos * nstr + 255) / 256);
-        // pre-filter on while misses dominate (it only adds a fetch to lookups that hit)
-        const bool bloom = b->db->bloom && (b->db->bloom_mode == 1 || (b->db->bloom_mode == 2 && b->db->ema_hit_rate < 0.40));
-        b->used_bloom = bloom;
-        b->used_partition = 0;
-        if (b->db->use_interp && bloom) {
+        // sieve on while misses dominate (it only adds a fetch to lookups that hit)
+        const bool sieve = b->db->sieve && (b->db->sieve_mode == 1 || (b->db->sieve_mode == 2 && b->db->ema_hit_rate < 0.40));
+        const unsigned sms = (unsigned)b->db->sm_count;
+        b->used_sieve = sieve;
+        if (b->db->use_table && sieve) {
             CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
-            // hits are sparse (only filter survivors that really match): the survivor kernel flags them in a
+            // hits are sparse (only sieve survivors that really match): the survivor kernel flags them in a
             // 1-bit-per-slot map, the vote reads the map and gathers only flagged slots
             CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st));
             if (timed) CK(cudaEventRecord(b->ev[4], b->st));
-            const unsigned wb = (n_pos + 255u * FILT_ILP) / (256u * FILT_ILP);   // CTAs that cover every position once
-            const unsigned pb = wb < 148u * FILT_MINB ? wb : 148u * FILT_MINB;  // persistent: FILT_MINB CTAs per SM
-            if (b->d_pwords && (uint64_t)n_pos >= b->part_min_pos) {
-                const unsigned tiles = (unsigned)(((uint64_t)n_pos + P_TILE - 1) / P_TILE);
-                const unsigned gb = tiles < P_CTAS ? tiles : P_CTAS;
-                uint32_t cap_cp = ((uint32_t)((double)n_pos / ((double)gb * NPART) * 1.25) + 66u) & ~1u;   // even; <= p_total / (gb * NPART)
-                // measured on B200 (10 M reads): atomic ranks 11.5 ms, match ranks 16.2 ms -> atomics by default
-                const char *pa = getenv("UTB_PART_ATOMS");                  // tests: 0 selects the match-ranked variant
-                const int part_atoms = !(pa && atoi(pa) == 0);
-#define LAUNCH_PART(NS, M, SM) do { \
-                    CK(cudaFuncSetAttribute(partition_kernel<NS, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM)); \
-                    partition_kernel<NS, M><<<gb, 256, SM, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_counters, b->d_pwords, b->d_ppos, b->d_pfill, cap_cp, b->d_hits, b->d_hitmap); } while (0)
-                if (nstr == 2) { if (part_atoms) LAUNCH_PART(2, false, P_SMEM); else LAUNCH_PART(2, true, P_SMEM_MATCH); }
-                else { if (part_atoms) LAUNCH_PART(1, false, P_SMEM); else LAUNCH_PART(1, true, P_SMEM_MATCH); }
-#undef LAUNCH_PART
-                if (timed) CK(cudaEventRecord(b->ev[6], b->st));
-                b->used_partition = 1;
-                CK(cudaMemsetAsync(b->d_pctr, 0, NPART * 4, b->st));
-                // cooperative launch: the grid barrier between partitions needs every CTA resident
-                const void *pk_fn = nstr == 2 ? (const void *)probe_kernel<2> : (const void *)probe_kernel<1>;
-                int per_sm = 0;
-                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pk_fn, 256, 0));
-                if (per_sm > 4) per_sm = 4;
-                int sms = 148;                                      // B200; a co-resident grid must not assume more than the device has
-                if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->db->device) != cudaSuccess || sms < 1) { cudaGetLastError(); sms = 148; }
-                unsigned pgrid = (unsigned)sms * (unsigned)(per_sm > 0 ? per_sm : 1), n_ctas = gb;
-                DevDB dd = d;
-                void *args[] = {&dd, &b->d_pwords, &b->d_ppos, &b->d_pfill, &cap_cp, &n_ctas, &b->d_pctr, &b->d_qwords, &b->d_qslots,
-                                &b->d_qcount, &b->q_cap, &b->d_hits, &b->d_hitmap, &b->d_counters};
-                CK(cudaLaunchCooperativeKernel(pk_fn, dim3(pgrid), dim3(256), args, 0, b->st));
-                b->launches++;
-            } else if (nstr == 2) filter_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else filter_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            // persistent: SV_MINB CTAs per SM, every warp a contiguous range of steps (small batches: one tile per warp)
+            const unsigned wb = (n_groups + 8u * SV_U - 1) / (8u * SV_U);
+            const unsigned pb = wb < sms * SV_MINB ? (wb ? wb : 1u) : sms * SV_MINB;
+            if (nstr == 2) sieve_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            else sieve_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
-            queue_lookup_kernel<<<148 * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
+            queue_lookup_kernel<<<sms * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
             b->launches++;
-        } else if (b->db->use_interp) {
-            if (nstr == 2) lookup_kernel<2, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
-            else lookup_kernel<1, true, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
+        } else if (b->db->use_table) {
+            if (nstr == 2) lookup_kernel<2, true><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters);
+            else lookup_kernel<1, true><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters);
         } else {
-            if (nstr == 2) lookup_kernel<2, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
-            else lookup_kernel<1, false, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->ngroups_dev, b->d_hits, b->d_counters);
+            if (nstr == 2) lookup_kernel<2, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters);
+            else lookup_kernel<1, false><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters);
         }
         b->launches++;
     }
@@ -2084,20 +1944,20 @@ static int launch_stages(utb_batch *b, bool timed) {
     if (n_reads) {
         VoteIn in;
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
-        in.hitmap = b->used_bloom ? b->d_hitmap : nullptr;
+        in.hitmap = b->used_sieve ? b->d_hitmap : nullptr;
         if (in.hitmap) {
             // thread per read for the common case; label-rich or long reads fall through to the warp kernel
             // (and from there to the block kernel) by way of device-side lists
             CK(cudaMemsetAsync(b->d_warp_count, 0, 4, b->st));
-            vote_thread_kernel<<<(n_reads + VT_THREADS - 1) / VT_THREADS, VT_THREADS, 0, b->st>>>(
-                d, in, n_reads, b->d_results, b->d_warp_list, b->d_warp_count, b->d_counters);
-            vote_warp_kernel<<<148 * 6, VW_WARPS * 32, 0, b->st>>>(
-                d, in, n_reads, b->d_warp_list, b->d_warp_count, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
+            vote_thread_kernel<<<gs_grid(b, n_reads, VT_THREADS, 32), VT_THREADS, 0, b->st>>>(
+                d, in, n_reads, b->dims_dev, b->d_results, b->d_warp_list, b->d_warp_count, b->d_counters);
+            vote_warp_kernel<<<(unsigned)b->db->sm_count * 6, VW_WARPS * 32, 0, b->st>>>(
+                d, in, n_reads, b->dims_dev, b->d_warp_list, b->d_warp_count, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
             b->launches++;
         } else
-            vote_warp_kernel<<<(n_reads + VW_WARPS - 1) / VW_WARPS, VW_WARPS * 32, 0, b->st>>>(
-                d, in, n_reads, nullptr, nullptr, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
-        vote_block_kernel<<<VB_BLOCKS, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
+            vote_warp_kernel<<<gs_grid(b, n_reads, VW_WARPS, 32), VW_WARPS * 32, 0, b->st>>>(
+                d, in, n_reads, b->dims_dev, nullptr, nullptr, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
+        vote_block_kernel<<<(unsigned)b->db->sm_count, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
                                                                b->d_hist, b->d_tlab, b->d_tcnt, b->d_counters);
         b->launches += 2;
     }
@@ -2118,7 +1978,7 @@ static int ensure_text_buffers(utb_batch *b) {
 }
 
 static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
-static int finish_submit(utb_batch *b);
+static int finish_submit(utb_batch *b, size_t n_bytes);
 extern "C" int utb_batch_submit(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
     return submit_impl(b, nullptr, n_bytes, n_reads, do_rc, 0, 0);
 }
@@ -2127,7 +1987,8 @@ extern "C" int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_read
 }
 // Pipeline-internal variant: `src` (pinned host memory, or NULL for the batch's own staging) holds the raw
 // bytes; total_groups != 0 means the caller already summed utb_read_slots() over the reads, so the
-// per-read offsets are scanned on the device instead of in a serial host loop.
+// per-read offsets are scanned on the device instead of in a serial host loop.  want_text: 0 result
+// records, 1 text through the batch's pinned staging, 2 text left on the device for utb_batch_text_to().
 extern "C" int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc,
                                    int want_text, uint64_t total_groups) {
     return submit_impl(b, src, n_bytes, n_reads, do_rc, want_text, total_groups);
@@ -2137,6 +1998,15 @@ extern "C" int utb_host_ptr_is_pinned(const void *p) {
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return 0; }
     return a.type == cudaMemoryTypeHost;
 }
+// page-locked host memory visible to every device (the searcher's output arena)
+extern "C" int utb_pinned_alloc(size_t n, void **out) {
+    if (!out || !n) { utb_set_error("utb_pinned_alloc: bad argument"); return UTB_ERR_ARG; }
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, n, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); utb_set_error("cannot page-lock %zu bytes (%s)", n, cudaGetErrorString(e)); return UTB_ERR_NOMEM; }
+    return UTB_OK;
+}
+extern "C" void utb_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 extern "C" uint32_t *utb_batch_name_off(utb_batch *b) { return b->h_name_off; }
 extern "C" uint32_t *utb_batch_name_len(utb_batch *b) { return b->h_name_len; }
 
@@ -2156,7 +2026,7 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
     if (g > b->max_groups) { utb_set_error("utb_batch_submit: %llu position groups exceed capacity %llu", (unsigned long long)g, (unsigned long long)b->max_groups); return UTB_ERR_LIMIT; }
     if (!total_groups) b->h_grp_off[n_reads] = (uint32_t)g;
     b->n_reads = n_reads; b->n_groups = (uint32_t)g; b->do_rc = do_rc ? 1 : 0;
-    b->want_text = want_text; b->ngroups_dev = nullptr; b->framed_on_device = 0;
+    b->want_text = want_text; b->dims_dev = nullptr; b->framed_on_device = 0;
     if (want_text) {
         int rt = ensure_text_buffers(b);
         if (rt) return rt;
@@ -2171,133 +2041,117 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
         CK(cudaMemcpyAsync(b->d_seq_len, b->h_seq_len, n_reads * 4, cudaMemcpyHostToDevice, b->st));
         if (!total_groups) CK(cudaMemcpyAsync(b->d_grp_off, b->h_grp_off, (n_reads + 1) * 4, cudaMemcpyHostToDevice, b->st));
         else {                                                     // grp_off = exclusive scan of the per-read slot counts
-            const uint32_t n = (uint32_t)n_reads, nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+            const uint32_t n = (uint32_t)n_reads, nt = (n + SCAN_TILE - 1) / SCAN_TILE;
             slots_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->d_seq_len, n, b->d_line_len);
-            scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
-            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_text_len);
-            scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_grp_off);
+            scan_sums_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, nullptr, nt, b->d_scan_sums);
+            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nt, b->d_text_len);
+            scan_apply_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, nullptr, nt, b->d_scan_sums, b->d_grp_off);
             b->launches += 4;
         }
     }
-    return finish_submit(b);
+    return finish_submit(b, n_bytes);
 }
 
 // device stages + (text | result records) + counters back to the host, all on the batch's stream
-static int finish_submit(utb_batch *b) {
-    const size_t n_reads = b->n_reads;
+static int finish_submit(utb_batch *b, size_t n_bytes) {
+    const size_t n_reads = b->n_reads;                             // device-side framing: an upper bound (the device holds the count)
     const int want_text = b->want_text;
     int rc = launch_stages(b, true);
     if (rc) return rc;
     if (want_text) {
         // lines built on the device: lengths -> exclusive scan -> one warp per read writes its line
-        const uint32_t n = (uint32_t)n_reads, nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+        const uint32_t n = (uint32_t)n_reads, nt = (n + SCAN_TILE - 1) / SCAN_TILE;
         CK(cudaMemsetAsync(b->d_text_len, 0, 4, b->st));
         if (n) {
-            fmt_len_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->db->d, b->d_results, b->d_name_len, n, b->d_line_len);
-            scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
-            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_text_len);
-            scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_line_off);
-            fmt_write_kernel<<<(n + FW_WARPS - 1) / FW_WARPS, FW_WARPS * 32, 0, b->st>>>(
-                b->db->d, b->d_results, b->d_raw, b->d_name_off, b->d_name_len, b->d_line_off, n, b->d_text);
+            fmt_len_kernel<<<gs_grid(b, n, 256, 16), 256, 0, b->st>>>(b->db->d, b->d_results, b->d_name_len, n, b->dims_dev, b->d_line_len);
+            scan_sums_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, b->dims_dev, nt, b->d_scan_sums);
+            scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nt, b->d_text_len);
+            scan_apply_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, b->dims_dev, nt, b->d_scan_sums, b->d_line_off);
+            fmt_write_kernel<<<gs_grid(b, n, FW_WARPS, 32), FW_WARPS * 32, 0, b->st>>>(
+                b->db->d, b->d_results, b->d_raw, b->d_name_off, b->d_name_len, b->d_line_off, n, b->dims_dev, b->d_text);
             b->launches += 5;
             CK(cudaGetLastError());
         }
         CK(cudaMemcpyAsync(b->h_text_len, b->d_text_len, 4, cudaMemcpyDeviceToHost, b->st));
-        // the text length is only known on the device: copy an estimate now (no extra round trip in the
-        // common case), wait_text tops it up if it was short
-        size_t est = (size_t)(b->db->text_per_read * 1.15 * (double)n_reads) + 4096;
-        if (b->db->text_per_read <= 0) est = 0;
-        if (est > b->text_cap) est = b->text_cap;
-        b->text_prefetched = est;
-        if (est) CK(cudaMemcpyAsync(b->h_text, b->d_text, est, cudaMemcpyDeviceToHost, b->st));
+        b->text_prefetched = 0;
+        if (want_text == 1) {
+            // the text length is only known on the device: copy an estimate now (no extra round trip in the
+            // common case), wait_text tops it up if it was short
+            size_t est = (size_t)(b->db->text_per_byte * 1.15 * (double)n_bytes) + 4096;
+            if (b->db->text_per_byte <= 0) est = 0;
+            if (est > b->text_cap) est = b->text_cap;
+            b->text_prefetched = est;
+            if (est) CK(cudaMemcpyAsync(b->h_text, b->d_text, est, cudaMemcpyDeviceToHost, b->st));
+        }
     } else if (n_reads) CK(cudaMemcpyAsync(b->h_results, b->d_results, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost, b->st));
+    if (b->dims_dev) CK(cudaMemcpyAsync(b->h_dims, b->d_dims, 8, cudaMemcpyDeviceToHost, b->st));
     CK(cudaMemcpyAsync(b->h_counters, b->d_counters, 4 * COUNTER_SLOTS * 8, cudaMemcpyDeviceToHost, b->st));
     CK(cudaEventRecord(b->done, b->st));
-    b->in_flight = 1;
+    b->in_flight = 1; b->in_bytes = n_bytes;
     return UTB_OK;
 }
 
-// Raw submit (pipeline-internal), in two steps so that the host need not look at the bytes at all:
-//   utb_batch_raw_begin  copies the chunk to the device and counts its newlines there (and notes a NUL byte);
-//   utb_batch_raw_count  blocks until that count is on the host (only this batch's copy and one small kernel
-//                        are waited for; the other stream slots keep the GPU busy meanwhile);
-//   utb_batch_raw_finish the caller has derived from the count that the first n_bytes hold exactly n_reads
-//                        complete records = 2 * n_reads lines, each ended by '\n', and no NUL byte: the records
-//                        are framed on the device, searched, and the output text is built there.
-// utb_batch_submit_raw = begin + finish for a caller that counted the newlines itself.
-// utb_batch_frame_error() tells after the wait whether a record was malformed.
-extern "C" int utb_batch_raw_begin(utb_batch *b, const char *src, size_t n_bytes) {
-    if (!b || !n_bytes) { utb_set_error("utb_batch_raw_begin: bad argument"); return UTB_ERR_ARG; }
-    if (n_bytes > b->max_bytes) { utb_set_error("utb_batch_raw_begin: batch over capacity"); return UTB_ERR_LIMIT; }
+// Chunk submit (pipeline-internal): the host has not looked at the bytes beyond cutting the chunk right before
+// a line that starts with '>' (or at the end of the input); the chunk is copied to the device, which counts its
+// newlines, derives and verifies the record count (frame_setup_kernel), frames every record (frame_parse_kernel),
+// searches, and builds the output text.  Nothing is waited for here.  n_reads (host value, 0 = unknown): when
+// the caller knows the record count it is only used as the upper bound the grids are sized for.
+// utb_batch_frame_error() tells after the wait whether the chunk or one of its records was malformed,
+// utb_batch_reads() how many records it held.
+extern "C" int utb_batch_submit_chunk(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text) {
+    if (!b || !n_bytes || want_text < 1 || want_text > 2) { utb_set_error("utb_batch_submit_chunk: bad argument"); return UTB_ERR_ARG; }
+    if (n_bytes > b->max_bytes || n_reads > b->max_reads || n_bytes >= 0xFFFFFFFFull) { utb_set_error("utb_batch_submit_chunk: batch over capacity"); return UTB_ERR_LIMIT; }
     CK(cudaSetDevice(b->db->device));
     if (!b->d_nl) {
-        CK(cudaMalloc(&b->d_nl, (2 * b->max_reads + 2) * 4));
-        CK(cudaMalloc(&b->d_blk, (b->max_bytes / FR_BLOCK + 2) * 4));
-        CK(cudaMalloc(&b->d_frame_err, 4));
-        CK(cudaMalloc(&b->d_ngroups, 4));
-        CK(cudaMalloc(&b->d_frame_info, 8));
-        CK(cudaMallocHost(&b->h_frame_err, 4));
-        CK(cudaMallocHost(&b->h_frame_info, 8));
-        CK(cudaEventCreateWithFlags(&b->count_ready, cudaEventDisableTiming));
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        cudaError_t e = cudaMalloc(&p[0], (2 * b->max_reads + 2) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&p[1], (b->max_bytes / FR_BLOCK + 2) * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&p[2], 4);
+        if (e == cudaSuccess) e = cudaMalloc(&p[3], 8);
+        if (e == cudaSuccess) e = cudaMallocHost(&p[4], 4);
+        if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) cudaFree(p[i]); cudaFreeHost(p[4]); CK(e); }
+        b->d_nl = (uint32_t *)p[0]; b->d_blk = (uint32_t *)p[1]; b->d_frame_err = (uint32_t *)p[2]; b->d_frame_info = (uint32_t *)p[3];
+        b->h_frame_err = (uint32_t *)p[4];
     }
     int rt = ensure_text_buffers(b);
     if (rt) return rt;
-    b->raw_bytes = n_bytes;
+    // upper bounds the launches are sized for: every read owns ceil((len+1)/32) <= len/32 + 1 groups
+    const size_t n_ub = n_reads ? n_reads : b->max_reads;
+    uint64_t g_ub = n_bytes / 32 + n_ub + 1;
+    if (g_ub > b->max_groups) g_ub = b->max_groups;
+    b->n_reads = n_ub; b->n_groups = (uint32_t)g_ub; b->do_rc = do_rc ? 1 : 0;
+    b->want_text = want_text; b->dims_dev = b->d_dims; b->framed_on_device = 1;
+    *b->h_frame_err = FR_ERR_NONE;
     CK(cudaMemcpyAsync(b->d_raw, src ? src : b->h_bytes, n_bytes, cudaMemcpyHostToDevice, b->st));
     CK(cudaMemsetAsync(b->d_frame_err, 0xFF, 4, b->st));
     CK(cudaMemsetAsync(b->d_frame_info, 0, 8, b->st));
-    const uint32_t fb = (uint32_t)((n_bytes + FR_BLOCK - 1) / FR_BLOCK);
+    const uint32_t fb = (uint32_t)((n_bytes + FR_BLOCK - 1) / FR_BLOCK), n = (uint32_t)n_ub, nt = (n + SCAN_TILE - 1) / SCAN_TILE;
     nl_count_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, b->d_frame_info + 1);
     scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_blk, fb, b->d_frame_info);       // block counts -> exclusive offsets, total newlines
-    b->launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(b->h_frame_info, b->d_frame_info, 8, cudaMemcpyDeviceToHost, b->st));
-    CK(cudaEventRecord(b->count_ready, b->st));
-    return UTB_OK;
-}
-extern "C" int utb_batch_raw_count(utb_batch *b, size_t *n_newlines, int *has_nul) {
-    if (!b || !b->count_ready || !n_newlines || !has_nul) { utb_set_error("utb_batch_raw_count: bad argument"); return UTB_ERR_ARG; }
-    CK(cudaSetDevice(b->db->device));
-    CK(cudaEventSynchronize(b->count_ready));
-    *n_newlines = b->h_frame_info[0]; *has_nul = b->h_frame_info[1] != 0;
-    return UTB_OK;
-}
-extern "C" int utb_batch_raw_finish(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc) {
-    if (!b || !n_reads || !n_bytes || n_bytes > b->raw_bytes) { utb_set_error("utb_batch_raw_finish: bad argument"); return UTB_ERR_ARG; }
-    if (n_reads > b->max_reads) { utb_set_error("utb_batch_raw_finish: batch over capacity"); return UTB_ERR_LIMIT; }
-    CK(cudaSetDevice(b->db->device));
-    // every read owns ceil((len+1)/32) <= len/32 + 1 groups and its two lines hold at least 2 more bytes than its bases
-    uint64_t g_ub = (n_bytes - 2 * n_reads) / 32 + n_reads + 1;
-    if (n_bytes < 2 * n_reads || g_ub > b->max_groups) g_ub = b->max_groups;
-    b->n_reads = n_reads; b->n_groups = (uint32_t)g_ub; b->do_rc = do_rc ? 1 : 0;
-    b->want_text = 1; b->ngroups_dev = b->d_ngroups; b->framed_on_device = 1;
-    *b->h_frame_err = FR_ERR_NONE;
-    // the block offsets were scanned over the whole chunk; newlines at or beyond n_bytes have index >= 2 * n_reads
-    const uint32_t n = (uint32_t)n_reads, fb = (uint32_t)((b->raw_bytes + FR_BLOCK - 1) / FR_BLOCK), nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    nl_index_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, 2 * n, b->d_nl);
-    frame_parse_kernel<<<(n + 255) / 256, 256, 0, b->st>>>(b->d_raw, b->d_nl, n, b->d_seq_off, b->d_seq_len, b->d_name_off, b->d_name_len,
-                                                          b->d_line_len, b->d_frame_err);
-    // grp_off = exclusive scan of the per-read group counts; the total stays on the device
-    scan_sums_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums);
-    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nb, b->d_ngroups);
-    scan_apply_kernel<<<nb, 256, 0, b->st>>>(b->d_line_len, n, b->d_scan_sums, b->d_grp_off);
-    b->launches += 5;
+    frame_setup_kernel<<<1, 1, 0, b->st>>>(b->d_frame_info, (uint32_t)n_ub, b->d_dims, b->d_frame_err);
+    nl_index_kernel<<<fb, 256, 0, b->st>>>(b->d_raw, n_bytes, b->d_blk, 0, b->d_dims, b->d_nl);
+    frame_parse_kernel<<<gs_grid(b, n, 256, 16), 256, 0, b->st>>>(b->d_raw, b->d_nl, n, b->d_dims, b->d_seq_off, b->d_seq_len, b->d_name_off,
+                                                                  b->d_name_len, b->d_line_len, b->d_frame_err);
+    // grp_off = exclusive scan of the per-read group counts; the total (dims[1]) stays on the device
+    scan_sums_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, b->d_dims, nt, b->d_scan_sums);
+    scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nt, b->d_dims + 1);
+    scan_apply_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_line_len, n, b->d_dims, nt, b->d_scan_sums, b->d_grp_off);
+    b->launches += 8;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(b->h_frame_err, b->d_frame_err, 4, cudaMemcpyDeviceToHost, b->st));
-    return finish_submit(b);
+    return finish_submit(b, n_bytes);
 }
-extern "C" int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc) {
-    int rc = utb_batch_raw_begin(b, src, n_bytes);
-    return rc ? rc : utb_batch_raw_finish(b, n_bytes, n_reads, do_rc);
-}
-// After the wait of a raw submit: 0 if every record was well formed, else 1 with the index of the first
-// malformed record of the batch and its FE_* code (1 no header '>', 2 sequence begins '>', 4 line too long).
+// After the wait of a chunk submit: 0 if the chunk and every record of it were well formed, else 1 with the index
+// of the first malformed record and its code (1 no header '>', 2 sequence begins '>', 4 line too long, 7 the
+// chunk itself: odd line count, NUL byte, more records than the batch holds).
 extern "C" int utb_batch_frame_error(const utb_batch *b, size_t *record, int *code) {
     if (!b || !b->framed_on_device || !b->h_frame_err || *b->h_frame_err == FR_ERR_NONE) return 0;
     if (record) *record = *b->h_frame_err >> 3;
     if (code) *code = (int)(*b->h_frame_err & 7u);
     return 1;
 }
+// records of the last batch (after the wait)
+extern "C" size_t utb_batch_reads(const utb_batch *b) { return b ? b->n_reads : 0; }
 
 extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
     if (!b) { utb_set_error("utb_batch_wait: null batch"); return UTB_ERR_ARG; }
@@ -2311,6 +2165,7 @@ extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
             b->db->ema_hit_rate = b->db->ema_hit_rate < 0 ? r : 0.5 * b->db->ema_hit_rate + 0.5 * r;
         }
     }
+    if (b->in_flight && b->dims_dev) b->n_reads = b->h_dims[0];     // device-side framing: the record count arrives with the results
     b->in_flight = 0;
     if (results) *results = b->h_results;
     return UTB_OK;
@@ -2319,7 +2174,7 @@ extern "C" int utb_batch_wait(utb_batch *b, const utb_result **results) {
 // After utb_batch_submit_text: blocks until the batch is done and its output text is in pinned host memory.
 extern "C" int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len, uint64_t *good_finds) {
     if (!b || !text || !len) { utb_set_error("utb_batch_wait_text: null argument"); return UTB_ERR_ARG; }
-    if (!b->want_text) { utb_set_error("utb_batch_wait_text: batch was not submitted with utb_batch_submit_text"); return UTB_ERR_ARG; }
+    if (b->want_text != 1) { utb_set_error("utb_batch_wait_text: batch was not submitted for text through the staging buffer"); return UTB_ERR_ARG; }
     int rc = utb_batch_wait(b, nullptr);
     if (rc) return rc;
     const size_t n = *b->h_text_len;
@@ -2329,12 +2184,37 @@ extern "C" int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len,
                            cudaMemcpyDeviceToHost, b->st));
         CK(cudaStreamSynchronize(b->st));
     }
-    if (b->n_reads >= 64) {
-        double r = (double)n / (double)b->n_reads;
-        b->db->text_per_read = b->db->text_per_read <= 0 ? r : 0.5 * b->db->text_per_read + 0.5 * r;
+    if (b->in_bytes >= 4096) {
+        double r = (double)n / (double)b->in_bytes;
+        b->db->text_per_byte = b->db->text_per_byte <= 0 ? r : 0.5 * b->db->text_per_byte + 0.5 * r;
     }
     *text = b->h_text; *len = n;
     if (good_finds) { uint64_t g = 0; for (int i = 0; i < COUNTER_SLOTS; ++i) g += b->h_counters[2 * COUNTER_SLOTS + i]; *good_finds = g; }
+    return UTB_OK;
+}
+// want_text == 2: blocks until the batch is done; its text (*len bytes) is still on the device.
+extern "C" int utb_batch_wait_len(utb_batch *b, size_t *len, uint64_t *good_finds) {
+    if (!b || !len) { utb_set_error("utb_batch_wait_len: null argument"); return UTB_ERR_ARG; }
+    if (b->want_text != 2) { utb_set_error("utb_batch_wait_len: batch was not submitted with the text left on the device"); return UTB_ERR_ARG; }
+    int rc = utb_batch_wait(b, nullptr);
+    if (rc) return rc;
+    *len = *b->h_text_len;
+    if (*len > b->text_cap) { utb_set_error("device text overflow"); return UTB_ERR_LIMIT; }
+    if (good_finds) { uint64_t g = 0; for (int i = 0; i < COUNTER_SLOTS; ++i) g += b->h_counters[2 * COUNTER_SLOTS + i]; *good_finds = g; }
+    return UTB_OK;
+}
+// ... and is copied from there straight to its place in the caller's page-locked output (no staging, no host
+// memcpy); asynchronous on the batch's stream, i.e. ordered before the slot's next batch.  utb_batch_sync waits.
+extern "C" int utb_batch_text_to(utb_batch *b, char *dst, size_t len) {
+    if (!b || (!dst && len) || len > b->text_cap) { utb_set_error("utb_batch_text_to: bad argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    if (len) CK(cudaMemcpyAsync(dst, b->d_text, len, cudaMemcpyDeviceToHost, b->st));
+    return UTB_OK;
+}
+extern "C" int utb_batch_sync(utb_batch *b) {
+    if (!b) return UTB_OK;
+    CK(cudaSetDevice(b->db->device));
+    CK(cudaStreamSynchronize(b->st));
     return UTB_OK;
 }
 
@@ -2359,21 +2239,14 @@ extern "C" uint64_t utb_batch_launches(const utb_batch *b) { return b ? b->launc
 // Two-phase detail of the LAST run (valid after wait): ms[0] filter kernel, ms[1] queue kernel (0/0 when the
 // single lookup kernel ran); sectors[0] = lookups answered by the filter (one sector per position, both
 // strands), sectors[1] = sectors the exact path touched for the survivors.
-// ms[0] partition_kernel, ms[1] probe_kernel of the LAST run; both 0 when the direct filter kernel ran.
-extern "C" int utb_batch_partition_detail(utb_batch *b, float ms[2]) {
-    if (!b || !ms) { utb_set_error("utb_batch_partition_detail: null argument"); return UTB_ERR_ARG; }
-    CK(cudaSetDevice(b->db->device));
-    ms[0] = ms[1] = 0;
-    if (!b->used_bloom || !b->used_partition) return UTB_OK;
-    CK(cudaEventElapsedTime(&ms[0], b->ev[4], b->ev[6]));
-    CK(cudaEventElapsedTime(&ms[1], b->ev[6], b->ev[5]));
-    return UTB_OK;
-}
 extern "C" int utb_batch_lookup_detail(utb_batch *b, float ms[2], uint64_t sectors[2]) {
     if (!b || !ms || !sectors) { utb_set_error("utb_batch_lookup_detail: null argument"); return UTB_ERR_ARG; }
     CK(cudaSetDevice(b->db->device));
     ms[0] = ms[1] = 0; sectors[0] = sectors[1] = 0;
-    if (!b->used_bloom) return UTB_OK;
+    if (!b->used_sieve) {                                         // single lookup kernel: only the table sectors are known
+        for (int i = 0; i < COUNTER_SLOTS; ++i) sectors[1] += b->h_counters[3 * COUNTER_SLOTS + i];
+        return UTB_OK;
+    }
     CK(cudaEventElapsedTime(&ms[0], b->ev[4], b->ev[5]));   // the kernel alone (the hits fill before it is part of the stage)
     CK(cudaEventElapsedTime(&ms[1], b->ev[5], b->ev[2]));
     for (int i = 0; i < COUNTER_SLOTS; ++i) { sectors[0] += b->h_counters[i]; sectors[1] += b->h_counters[3 * COUNTER_SLOTS + i]; }
@@ -2412,7 +2285,7 @@ extern "C" int utb_lookup_words(utb_db *db, const uint64_t *words, size_t n, uin
     CK(cudaMalloc(&dw, n * 8));
     CK(cudaMalloc(&di, n * 4));
     CK(cudaMemcpy(dw, words, n * 8, cudaMemcpyHostToDevice));
-    if (db->use_interp) lookup_words_kernel<true><<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
+    if (db->use_table) lookup_words_kernel<true><<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
     else lookup_words_kernel<false><<<(unsigned)((n + 255) / 256), 256>>>(db->d, dw, n, di);
     CK(cudaGetLastError());
     CK(cudaMemcpy(ix, di, n * 4, cudaMemcpyDeviceToHost));
@@ -2437,7 +2310,7 @@ extern "C" int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len, uint
     CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_len, &len, 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_grp, grp, 8, cudaMemcpyHostToDevice));
-    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad);
+    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad, nullptr);
     expand_windows_kernel<<<(n_pos + 255) / 256, 256>>>(d_pk, d_bad, n_pos, d_f, d_r, d_v);
     CK(cudaGetLastError());
     CK(cudaMemcpy(fwd, d_f, (size_t)len * 8, cudaMemcpyDeviceToHost));
@@ -2457,13 +2330,13 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     CK(cudaMalloc(&d_hits, (nh + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
     CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
-    CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
+    CK(cudaMalloc(&d_hist, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)db->sm_count * nl * 4));
+    CK(cudaMemset(d_hist, 0, (size_t)db->sm_count * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = nullptr;
-    vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, nullptr, d_res, d_gl, d_gc, d_cnt);
-    vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
+    vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, nullptr, nullptr, d_res, d_gl, d_gc, d_cnt);
+    vote_block_kernel<<<(unsigned)db->sm_count, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
     CK(cudaGetLastError());
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
     cudaFree(d_hits); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_cnt);
@@ -2498,16 +2371,16 @@ extern "C" int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
     CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_wl, n_reads * 4)); CK(cudaMalloc(&d_wc, 4));
     CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
-    CK(cudaMalloc(&d_hist, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)VB_BLOCKS * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)VB_BLOCKS * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
+    CK(cudaMalloc(&d_hist, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)db->sm_count * nl * 4));
+    CK(cudaMemset(d_hist, 0, (size_t)db->sm_count * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     CK(cudaMemcpy(d_hits, ph, (tot + 32) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_map, pm, (tot / 32 + 2) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, poff, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     free(poff); free(ph); free(pm);
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = d_map;
-    vote_thread_kernel<<<(unsigned)((n_reads + VT_THREADS - 1) / VT_THREADS), VT_THREADS>>>(db->d, in, (uint32_t)n_reads, d_res, d_wl, d_wc, d_cnt);
-    vote_warp_kernel<<<148 * 6, VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, d_wl, d_wc, d_res, d_gl, d_gc, d_cnt);
-    vote_block_kernel<<<VB_BLOCKS, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
+    vote_thread_kernel<<<(unsigned)((n_reads + VT_THREADS - 1) / VT_THREADS), VT_THREADS>>>(db->d, in, (uint32_t)n_reads, nullptr, d_res, d_wl, d_wc, d_cnt);
+    vote_warp_kernel<<<(unsigned)db->sm_count * 6, VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, d_wl, d_wc, d_res, d_gl, d_gc, d_cnt);
+    vote_block_kernel<<<(unsigned)db->sm_count, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
     CK(cudaGetLastError());
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
     cudaFree(d_hits); cudaFree(d_map); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_wl); cudaFree(d_wc);

@@ -33,18 +33,20 @@
 #include <unistd.h>
 
 int utb_batch_last_ms(utb_batch *b, float ms[4]);
-int utb_batch_submit_text(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
 int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
 int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
-int utb_batch_submit_raw(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc);
+int utb_batch_submit_chunk(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text);
 int utb_batch_frame_error(const utb_batch *b, size_t *record, int *code);
-int utb_batch_raw_begin(utb_batch *b, const char *src, size_t n_bytes);
-int utb_batch_raw_count(utb_batch *b, size_t *n_newlines, int *has_nul);
-int utb_batch_raw_finish(utb_batch *b, size_t n_bytes, size_t n_reads, int do_rc);
+size_t utb_batch_reads(const utb_batch *b);
+int utb_batch_wait_len(utb_batch *b, size_t *len, uint64_t *good_finds);
+int utb_batch_text_to(utb_batch *b, char *dst, size_t len);
+int utb_batch_sync(utb_batch *b);
+int utb_pinned_alloc(size_t n, void **out);
+void utb_pinned_free(void *p);
 
 #define SLOTS_PER_DEVICE 6                         /* measured on B200: 3 slots 89 ms, 4 slots 78 ms, 6 slots 71 ms per 10 M reads */
-#define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* large enough for the device's partitioned lookup pass on the full-size batches */
+#define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* ~2.3 ms of PCIe per batch: launch and sync costs are a few percent of that */
 #define RAMP_BYTES ((size_t)32 << 20)              /* first / last batches: small, so the pipeline fills and drains fast */
 #define MAX_TEAM 64
 
@@ -126,8 +128,9 @@ struct utb_searcher {
     size_t max_label;              /* longest label incl. NUL */
     int verbose;                   /* CLI: progress lines on stdout */
     int device_format;             /* output lines built on the GPU (default) or by the host formatter team */
-    int device_frame;              /* records framed on the GPU (default with device_format): the host only needs the newline count */
-    int host_count;                /* ... and counts them itself (UTB_HOST_COUNT=1) instead of waiting for the device's count */
+    int device_frame;              /* records framed on the GPU (default with device_format): the host only cuts chunks at a "\n>" */
+    char *arena; size_t arena_cap; /* page-locked output of utb_search_mem: the devices copy their text straight into it; valid until
+                                    * the next search on this searcher or its destruction */
 };
 
 static double now_s(void) {
@@ -151,8 +154,6 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->device_format = !(e && atoi(e) != 0);
     e = getenv("UTB_HOST_FRAME");
     s->device_frame = s->device_format && !(e && atoi(e) != 0);
-    e = getenv("UTB_HOST_COUNT");
-    s->host_count = e && atoi(e) != 0;
     for (uint32_t i = 0; i < ctr->max_ix; ++i) {
         size_t l = ctr->off[i + 1] - ctr->off[i];
         if (l > s->max_label) s->max_label = l;
@@ -166,10 +167,16 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     s->ramp_bytes = e && atoi(e) > 0 ? (size_t)atoi(e) << 20 : RAMP_BYTES;
     s->slots = (slot_t *)calloc((size_t)s->n_slots, sizeof(slot_t));
     if (!s->devices || !s->dbs || !s->slots) { utb_searcher_destroy(s); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    /* one upload + table build (PCIe); a repeated device shares that handle, every further GPU gets the
+     * finished tables by peer copy over NVLink */
     for (int d = 0; d < n_devices; ++d) {
         s->devices[d] = devices[d];
-        int rc = utb_db_upload(ctr, devices[d], &s->dbs[d]);
-        if (rc) { utb_searcher_destroy(s); return rc; }
+        int rc = UTB_OK, shared = -1;
+        for (int e = 0; e < d; ++e) if (devices[e] == devices[d]) { shared = e; break; }
+        if (shared >= 0) s->dbs[d] = s->dbs[shared];
+        else if (d == 0) rc = utb_db_upload(ctr, devices[d], &s->dbs[d]);
+        else rc = utb_db_clone(s->dbs[0], devices[d], &s->dbs[d]);
+        if (rc) { s->n_devices = d; utb_searcher_destroy(s); return rc; }
     }
     for (int i = 0; i < s->n_slots; ++i) {
         slot_t *sl = &s->slots[i];
@@ -186,7 +193,12 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
 void utb_searcher_destroy(utb_searcher *s) {
     if (!s) return;
     if (s->slots) for (int i = 0; i < s->n_slots; ++i) utb_batch_destroy(s->slots[i].b);
-    if (s->dbs) for (int d = 0; d < s->n_devices; ++d) utb_db_free(s->dbs[d]);
+    if (s->dbs) for (int d = 0; d < s->n_devices; ++d) {
+        int shared = 0;
+        for (int e = 0; e < d; ++e) if (s->dbs[e] == s->dbs[d]) shared = 1;
+        if (!shared) utb_db_free(s->dbs[d]);
+    }
+    utb_pinned_free(s->arena);
     free(s->slots); free(s->dbs); free(s->devices); free(s);
 }
 
@@ -236,58 +248,35 @@ static ssize_t src_fill(source_t *s, team_t *team, char *dst, size_t cap) {
 }
 
 /* ---- output sink -------------------------------------------------------------------- */
-/* memory sink: an anonymous mapping grown with mremap (no data copies); the
- * caller's pointer sits 64 bytes into the mapping, utb_free() unmaps it. */
-#define SINK_MAGIC 0x55544253494e4b31ull
-typedef struct { uint64_t magic, map_len; } sink_hdr;
+/* memory sink: the searcher's page-locked arena.  The text of a batch goes from the device straight to its
+ * final place in it (utb_batch_text_to): no staging buffer, no host memcpy.  The arena is kept for the next
+ * search of this searcher (page-locking ~1 GB costs far more than a search). */
 typedef struct {
-    int fd;                 /* file sink (pwrite at off), or */
-    char *map; size_t cap;  /* memory sink */
+    int fd;                 /* >= 0: file sink (pwrite at off); < 0: memory sink */
+    utb_searcher *s;
     size_t off;             /* bytes emitted so far */
-    size_t hint;            /* expected output size (first mapping) */
+    size_t hint;            /* expected output size (first allocation) */
     int failed;
 } sink_t;
 
-/* The mapping of the last output handed back through utb_free() is kept for the next search of the
- * process: its pages are already faulted in, which is worth more than the copy itself (a fresh
- * anonymous mapping costs one zero-fill per page on first touch). */
-#define SINK_CACHE_MAX ((size_t)8 << 30)
-static pthread_mutex_t g_sink_mu = PTHREAD_MUTEX_INITIALIZER;
-static char *g_sink_map;
-static size_t g_sink_cap;
-
 static int sink_reserve(sink_t *k, size_t upto) {
     if (k->fd >= 0) return 0;
-    size_t need = upto + 64;
-    if (need <= k->cap) return 0;
-    if (!k->map) {
-        pthread_mutex_lock(&g_sink_mu);
-        if (g_sink_map) { k->map = g_sink_map; k->cap = g_sink_cap; g_sink_map = NULL; g_sink_cap = 0; }
-        pthread_mutex_unlock(&g_sink_mu);
-        if (need <= k->cap) return 0;
+    utb_searcher *s = k->s;
+    if (upto <= s->arena_cap) return 0;
+    size_t nc = s->arena_cap ? s->arena_cap + s->arena_cap / 2 : (k->hint > ((size_t)1 << 24) ? k->hint : (size_t)1 << 24);
+    if (nc < upto) nc = upto + upto / 4;
+    void *m = NULL;
+    if (utb_pinned_alloc(nc, &m)) { k->failed = 1; return -1; }
+    if (s->arena) {
+        for (int i = 0; i < s->n_slots; ++i) utb_batch_sync(s->slots[i].b);   /* copies still in flight into the old arena */
+        memcpy(m, s->arena, k->off);
+        utb_pinned_free(s->arena);
     }
-    size_t nc = k->cap ? k->cap : (k->hint > ((size_t)1 << 24) ? k->hint : (size_t)1 << 24);
-    while (nc < need) nc <<= 1;
-    void *m = k->map ? mremap(k->map, k->cap, nc, MREMAP_MAYMOVE)
-                     : mmap(NULL, nc, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
-    if (m == MAP_FAILED) { k->failed = 1; return -1; }
-    k->map = (char *)m; k->cap = nc;
-#ifdef MADV_HUGEPAGE
-    madvise(k->map, nc, MADV_HUGEPAGE);                            /* 512x fewer first-touch faults */
-#endif
-    ((sink_hdr *)k->map)->magic = SINK_MAGIC;
-    ((sink_hdr *)k->map)->map_len = nc;
+    s->arena = (char *)m; s->arena_cap = nc;
     return 0;
 }
-void utb_free(void *p) {
-    if (!p) return;
-    sink_hdr *h = (sink_hdr *)((char *)p - 64);
-    if (h->magic != SINK_MAGIC) return;
-    pthread_mutex_lock(&g_sink_mu);
-    if (!g_sink_map && h->map_len <= SINK_CACHE_MAX) { g_sink_map = (char *)h; g_sink_cap = h->map_len; h = NULL; }
-    pthread_mutex_unlock(&g_sink_mu);
-    if (h) munmap(h, h->map_len);
-}
+/* Kept for callers of the round-1 ABI: the output of utb_search_mem belongs to the searcher (see above). */
+void utb_free(void *p) { (void)p; }
 
 /* ---- shared run state ------------------------------------------------------------------ */
 typedef struct {
@@ -300,6 +289,7 @@ typedef struct {
     uint64_t consumed;      /* batches the formatter is done with */
     int discard;            /* a device-framed batch held a malformed record: output from restart_seq on is dropped, */
     uint64_t restart_seq;   /* the reader rewinds to that batch and frames the rest on the host (exact error path)    */
+    uint64_t reads_done;    /* records of the batches consumed so far (device-framed batches report their count on completion) */
     int done_reading;
     int error;              /* sticky UTB_ERR_* from the device side */
     char errmsg[512];
@@ -371,7 +361,7 @@ static void emit_part(void *c_, int part, int nparts) {
     (void)nparts;
     size_t n = f->len[part];
     if (!n) return;
-    if (f->sink->fd < 0) { memcpy(f->sink->map + 64 + f->off[part], f->buf[part], n); return; }
+    if (f->sink->fd < 0) { memcpy(f->sink->s->arena + f->off[part], f->buf[part], n); return; }
     const char *p = f->buf[part];
     off_t o = (off_t)f->off[part];
     while (n) {
@@ -386,7 +376,7 @@ static void copy_part(void *c_, int part, int nparts) {
     copy_ctx *c = (copy_ctx *)c_;
     size_t a = c->len * (size_t)part / (size_t)nparts, b = c->len * (size_t)(part + 1) / (size_t)nparts;
     if (a == b) return;
-    if (c->sink->fd < 0) { memcpy(c->sink->map + 64 + c->off + a, c->text + a, b - a); return; }
+    if (c->sink->fd < 0) { memcpy(c->sink->s->arena + c->off + a, c->text + a, b - a); return; }
     const char *p = c->text + a; size_t n = b - a; off_t o = (off_t)(c->off + a);
     while (n) {
         ssize_t k = pwrite(c->sink->fd, p, n, o);
@@ -401,6 +391,7 @@ static void *formatter_main(void *arg) {
     fmt_ctx F;
     memset(&F, 0, sizeof F);
     F.c = s->ctr; F.max_label = s->max_label; F.sink = R->sink;
+    const int direct = s->device_format && R->sink->fd < 0;       /* device text -> its final place in the arena */
     for (uint64_t seq = 0;; ++seq) {
         pthread_mutex_lock(&R->mu);
         while (R->submitted <= seq && !R->done_reading) pthread_cond_wait(&R->cv, &R->mu);
@@ -411,10 +402,13 @@ static void *formatter_main(void *arg) {
         const utb_result *res = NULL;
         const char *text = NULL; size_t text_len = 0; uint64_t good = 0;
         double tw = now_s();
-        int rc = s->device_format ? utb_batch_wait_text(sl->b, &text, &text_len, &good) : utb_batch_wait(sl->b, &res);
+        int rc = direct ? utb_batch_wait_len(sl->b, &text_len, &good)
+                        : s->device_format ? utb_batch_wait_text(sl->b, &text, &text_len, &good) : utb_batch_wait(sl->b, &res);
         R->st.fm_wait_gpu += now_s() - tw;
         if (seq < 64) R->tl_gpu_done[seq] = now_s() - R->t0;
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
+        sl->n_reads = utb_batch_reads(sl->b);                      /* device-framed: the count came back with the results */
+        sl->first_read = R->reads_done;
         pthread_mutex_lock(&R->mu);
         if (!rc && !R->discard && utb_batch_frame_error(sl->b, NULL, NULL)) { R->discard = 1; R->restart_seq = seq; }
         const int discard = R->discard;
@@ -423,14 +417,19 @@ static void *formatter_main(void *arg) {
         if (!rc && s->device_format) {
             double tf = now_s();
             if (text_len && !sink_reserve(R->sink, R->sink->off + text_len)) {
-                copy_ctx cc = {R->sink, text, text_len, R->sink->off};
-                team_run(&R->fmt_team, copy_part, &cc);
+                if (direct) {
+                    int r2 = utb_batch_text_to(sl->b, s->arena + R->sink->off, text_len);
+                    if (r2 && !R->error) { R->error = r2; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
+                } else {
+                    copy_ctx cc = {R->sink, text, text_len, R->sink->off};
+                    team_run(&R->fmt_team, copy_part, &cc);
+                }
                 R->sink->off += text_len;
                 R->st.out_bytes += text_len;
             }
             R->st.good_finds += good;
             R->st.fm_emit += now_s() - tf;
-            R->st.d2h_bytes += text_len + 4 * 1024 * 8 + 4;
+            R->st.d2h_bytes += text_len + 4 * 1024 * 8 + 16;
         } else if (!rc) {
             F.sl = sl; F.res = res; F.bytes = sl->host_bytes;
             double tf = now_s();
@@ -455,6 +454,7 @@ static void *formatter_main(void *arg) {
             utb_batch_last_ms(sl->b, ms);
             R->st.lookups += lk; R->st.hits += ht;
             R->st.seconds_device += 1e-3 * (double)ms[3];
+            R->reads_done += sl->n_reads;
             if (s->verbose) {   /* itree.c:878 */
                 uint64_t a = sl->first_read, b = sl->first_read + sl->n_reads;
                 for (uint64_t m = (a >> 20) + 1; (m << 20) <= b; ++m)
@@ -838,7 +838,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
      * lies: no staging memcpy, no carry (batches are just consecutive ranges of it) */
     const int zero_copy = src->fd < 0 && src->mem_len && utb_host_ptr_is_pinned(src->mem) &&
                           utb_host_ptr_is_pinned(src->mem + src->mem_len - 1);
-    int rc = UTB_OK, fmt_err = 0;
+    int rc = UTB_OK, fmt_err = 0, chunked = 0;                    /* chunked: device-framed batches may still be in flight */
     char fmt_msg[256] = "";
     uint64_t seq = 0, n_reads_total = 0, consumed = 0;
     /* device-side framing needs an input that can be rewound if a malformed record turns up */
@@ -857,10 +857,11 @@ read_loop:
              * which reproduces the reference's partial output, message and exit code exactly. */
             while (R.consumed < R.submitted) pthread_cond_wait(&R.cv, &R.mu);
             const slot_t *ks = &s->slots[R.restart_seq % (uint64_t)s->n_slots];
-            consumed = ks->src_off; n_reads_total = ks->first_read;
+            consumed = ks->src_off; n_reads_total = R.reads_done;   /* the batches before it were counted, none from it on */
             if (src->fd >= 0) { src->file_off = (off_t)consumed; src->eof = src->file_off >= src->file_size; }
             else { src->mem_pos = (size_t)consumed; src->eof = src->mem_pos >= src->mem_len; }
-            carry_len = 0; device_frame = 0; R.discard = 0;
+            carry_len = 0; device_frame = 0; chunked = 0; R.discard = 0;
+            fmt_err = 0; fmt_msg[0] = 0;                           /* an error met further down the input is met again, in order */
             pthread_mutex_unlock(&R.mu);
             continue;
         }
@@ -896,38 +897,35 @@ read_loop:
         if (!fill) break;                                          /* clean EOF */
 
         sl->src_off = consumed;
+        const int want_text = !s->device_format ? 0 : sink->fd < 0 ? 2 : 1;   /* 2: the device text goes straight into the output arena */
         if (device_frame && fill >= 2 && fill < 0xFFFFFFFFull) {
-            /* fast path: all the framing needs from here is the newline count of the chunk.  By default the
-             * device counts too -- the chunk goes to the GPU right away and this thread only waits for two
-             * numbers; UTB_HOST_COUNT=1 counts on the host threads instead (utb_count_newlines). */
-            size_t n_lines = 0; int nul = 0;
-            if (!s->host_count) {
-                int r1 = utb_batch_raw_begin(sl->b, zero_copy ? buf : NULL, fill);
-                if (!r1) r1 = utb_batch_raw_count(sl->b, &n_lines, &nul);
-                if (r1) { rc = r1; break; }
-            } else {
-                nlc_ctx C;
-                C.buf = buf; C.fill = fill;
-                team_run(&rd_team, nlc_part, &C);
-                for (int p = 0; p < rd_team.n; ++p) { n_lines += C.cnt[p]; nul |= C.has_nul[p]; }
+            /* Fast path: the host does not look at the bytes.  In a well-formed file exactly the header lines
+             * begin with '>' (itree.c:880, 886), so the chunk is cut right before the last line that does (at the
+             * end of the input: after the final newline) and goes to the GPU as it is; the device counts the
+             * lines, checks that they pair up and that every record is well formed, and frames them.  Nothing is
+             * waited for: if the check fails the formatter drops the batches from that one on and this loop
+             * rewinds to it with the exact host reader.  Left to the host reader from the start: a last line
+             * without '\n', a chunk without a second header. */
+            size_t used = 0;
+            if (src->eof) { if (buf[fill - 1] == '\n') used = fill; }
+            else for (size_t hi = fill - 1; hi > 0;) {             /* newline at index < fill - 1 followed by '>' */
+                const char *q = (const char *)memrchr(buf, '\n', hi);
+                if (!q) break;
+                const size_t i = (size_t)(q - buf);
+                if (buf[i + 1] == '>') { used = i + 1; break; }
+                hi = i;
             }
-            const size_t n_rec = n_lines / 2;
-            /* left to the host reader: NUL bytes, a last line without '\n' or a dangling header at EOF, more
-             * records than the batch arrays hold, a record larger than the buffer */
-            if (!nul && n_rec >= 1 && n_rec <= utb_batch_max_reads(sl->b) && !(src->eof && (buf[fill - 1] != '\n' || (n_lines & 1)))) {
-                const char *last = (const char *)memrchr(buf, '\n', fill);
-                if (n_lines & 1) last = (const char *)memrchr(buf, '\n', (size_t)(last - buf));
-                const size_t used = (size_t)(last - buf) + 1;
-                sl->n_reads = n_rec; sl->host_bytes = buf; sl->n_bytes = used; sl->first_read = n_reads_total;
-                n_reads_total += n_rec; consumed += used;
+            if (used >= 2) {
+                sl->n_reads = 0; sl->host_bytes = buf; sl->n_bytes = used;
+                consumed += used;
                 if (zero_copy) { src->mem_pos += used; if (src->mem_pos < src->mem_len) src->eof = 0; }
                 else if (used < fill) { carry_len = fill - used; memcpy(carry, buf + used, carry_len); }
                 rd_t[2] += now_s() - tp; tp = now_s();
-                if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = n_rec; }
-                int r2 = s->host_count ? utb_batch_submit_raw(sl->b, zero_copy ? buf : NULL, used, n_rec, do_rc)
-                                       : utb_batch_raw_finish(sl->b, used, n_rec, do_rc);
+                if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = 0; }
+                int r2 = utb_batch_submit_chunk(sl->b, zero_copy ? buf : NULL, used, 0, do_rc, want_text);
                 if (r2) { rc = r2; break; }
-                R.st.h2d_bytes += (s->host_count ? used : fill) + 4;
+                R.st.h2d_bytes += used;
+                chunked = 1;
                 if (seq < 64) R.tl_submit[seq] = now_s() - t0;
                 pthread_mutex_lock(&R.mu);
                 sl->state = 1;
@@ -938,6 +936,17 @@ read_loop:
                 if (src->eof && !carry_len) break;
                 continue;
             }
+        }
+        if (chunked) {
+            /* the host reader numbers its records (error messages carry the line count): the batches in
+             * flight report theirs on completion, so let them finish first */
+            pthread_mutex_lock(&R.mu);
+            while (R.consumed < R.submitted) pthread_cond_wait(&R.cv, &R.mu);
+            const int again = R.discard;
+            n_reads_total = R.reads_done;
+            pthread_mutex_unlock(&R.mu);
+            chunked = 0;
+            if (again) continue;                                   /* the top of the loop rewinds; this chunk is read again */
         }
         frame_ctx F;
         memset(&F, 0, sizeof F);
@@ -988,7 +997,7 @@ read_loop:
         if (seq < 64) { R.tl_framed[seq] = now_s() - t0; R.tl_reads[seq] = n; }
         if (n) {
             /* every sequence lies inside the first n_bytes of the buffer */
-            int r2 = utb_batch_submit_ex(sl->b, zero_copy ? buf : NULL, fmt_err ? fill : used, n, do_rc, s->device_format,
+            int r2 = utb_batch_submit_ex(sl->b, zero_copy ? buf : NULL, fmt_err ? fill : used, n, do_rc, want_text,
                                          groups_known && !cut ? groups : 0);
             if (r2) { rc = r2; break; }
             R.st.h2d_bytes += (fmt_err ? fill : used) + n * (s->device_format ? 24 : 16) + 4;
@@ -1003,13 +1012,15 @@ read_loop:
         if (fmt_err) break;
         if (src->eof && !carry_len) break;
     }
-    if (!rc && !fmt_err && device_frame) {
-        /* the input is exhausted, but a device-framed batch still in flight may hold a malformed record */
+    if (!rc && chunked) {
+        /* the reader is done (input exhausted, or a format error of its own), but a device-framed batch still in
+         * flight may hold an EARLIER malformed record: that one decides the output, the message and the line number */
         pthread_mutex_lock(&R.mu);
         while (R.consumed < R.submitted) pthread_cond_wait(&R.cv, &R.mu);
         const int again = R.discard;
         pthread_mutex_unlock(&R.mu);
-        if (again) goto read_loop;                                 /* the top of the loop rewinds */
+        chunked = 0;
+        if (again) goto read_loop;                                 /* the top of the loop rewinds and forgets the later error */
     }
     free(idx);
     pthread_mutex_lock(&R.mu);
@@ -1024,7 +1035,11 @@ read_loop:
     pthread_cond_destroy(&R.cv);
     if (!rc && R.error) { rc = R.error; utb_set_error("%s", R.errmsg); }
     if (!rc && sink->failed) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
-    R.st.reads = n_reads_total;
+    for (int i = 0; i < s->n_slots; ++i) {                        /* text copies into the output arena still in flight */
+        int r3 = utb_batch_sync(s->slots[i].b);
+        if (r3 && !rc) rc = r3;
+    }
+    R.st.reads = R.reads_done;
     R.st.batches = seq;
     for (int i = 0; i < s->n_slots; ++i) R.st.kernel_launches += utb_batch_launches(s->slots[i].b);
     R.st.kernel_launches -= launches0;
@@ -1057,7 +1072,7 @@ int utb_search_file(utb_searcher *s, const char *fasta_path, const char *out_pat
     source_t src; memset(&src, 0, sizeof src); src.fd = fd;
     struct stat st;
     if (!fstat(fd, &st) && S_ISREG(st.st_mode)) { src.seekable = 1; src.file_size = st.st_size; if (!st.st_size) src.eof = 1; }
-    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = fo;
+    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = fo; sink.s = s;
     int rc = run_search(s, &src, &sink, do_rc, stats, ref_exit);
     if (close(fo) && !rc) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
     close(fd);
@@ -1068,10 +1083,10 @@ int utb_search_mem(utb_searcher *s, const char *fasta, size_t n, int do_rc,
                    char **out, size_t *out_len, utb_stats *stats, int *ref_exit) {
     if (!s || (!fasta && n) || !out || !out_len) { utb_set_error("utb_search_mem: null argument"); return UTB_ERR_ARG; }
     source_t src; memset(&src, 0, sizeof src); src.fd = -1; src.mem = fasta; src.mem_len = n; src.eof = n == 0;
-    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = -1;
-    sink.hint = n / 2 + n / 8;                                     /* typical output: ~half the FASTA */
+    sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = -1; sink.s = s;
+    sink.hint = n / 2 + n / 4 + ((size_t)1 << 20);                 /* typical output: about half the FASTA */
     int rc = run_search(s, &src, &sink, do_rc, stats, ref_exit);
-    *out = sink.map ? sink.map + 64 : NULL; *out_len = sink.off;
+    *out = sink.off ? s->arena : NULL; *out_len = sink.off;
     return rc;
 }
 
