@@ -65,12 +65,17 @@ def test_pack_matches_oracle_words(gpu):
         assert np.array_equal(np.concatenate([fwd[valid == 1], rc[valid == 1][::-1]]), owords_rc), name
 
 
+@pytest.mark.parametrize("env", [{}, {"UTB_VOTE_SPLIT_SLOTS": "256"}, {"UTB_VOTE_SORT_MAX": "3"},
+                                 {"UTB_VOTE_SPLIT_SLOTS": "256", "UTB_VOTE_SORT_MAX": "3"}])
 @pytest.mark.parametrize("sparse", [False, True])
 @pytest.mark.parametrize("dbname", ["toyA", "toyB_u32"])
-def test_vote_matches_oracle(gpu, dbname, sparse):
+def test_vote_matches_oracle(gpu, dbname, sparse, env):
     """Vote on real hit lists, on permuted hit lists and on synthetic multisets; dense
-    (warp/block kernels) and through the pipeline's sparse hit map (thread kernel first)."""
+    (warp/block kernels) and through the pipeline's sparse hit map (thread kernel first).  With a tiny
+    split threshold every read the warp kernel defers is split across the grid and merged; with a tiny
+    sort limit the touched-label list gives way to the sweep over all labels in rank order."""
     ctr, db, orc = gpu[dbname]
+    os.environ.update(env)
     rng = np.random.default_rng(9)
     lists = []
     reads = read_fasta(gold("toyA_reads.fa"))[:300] + read_fasta(gold("long_reads.fa")) if dbname == "toyA" \
@@ -90,7 +95,11 @@ def test_vote_matches_oracle(gpu, dbname, sparse):
     off = np.zeros(len(lists) + 1, dtype=np.uint64)
     off[1:] = np.cumsum([l.size for l in lists])
     # sprinkle misses between the hits: they must be ignored
-    res = db.vote_hits(np.concatenate(lists), off, sparse=sparse)
+    try:
+        res = db.vote_hits(np.concatenate(lists), off, sparse=sparse)
+    finally:
+        for k in env:
+            del os.environ[k]
     for i, h in enumerate(lists):
         v = orc.vote(h)
         r = res[i]
@@ -345,6 +354,25 @@ def test_every_lookup_variant_gives_the_reference_output(ctrs, tmp_path, env, db
     try:
         code, ref_exit, text, st = s.search_mem(open(gold(reads), "rb").read(), do_rc=bool(rc))
         assert code == 0 and text == open(gold(out), "rb").read()
+    finally:
+        s.destroy(); ctr.close()
+
+
+def test_long_queries_split_across_ctas_and_merged(ctrs, tmp_path):
+    """64 kb queries with the split threshold lowered to 8192 lookup slots: every one of them is voted by
+    the whole grid (per-read histogram, touched-label list, one merge + walk): identical bytes."""
+    from utree_b200 import capi
+    os.environ["UTB_VOTE_SPLIT_SLOTS"] = "8192"
+    try:
+        ctr = capi.Ctr(ctrs["toyA"])
+        s = capi.Searcher(ctr, devices=(0,), host_threads=3)
+    finally:
+        del os.environ["UTB_VOTE_SPLIT_SLOTS"]
+    try:
+        data = open(gold("long_reads.fa"), "rb").read() + open(gold("toyA_reads.fa"), "rb").read()
+        want = open(gold("long_rc.out"), "rb").read() + open(gold("toyA_rc.out"), "rb").read()
+        code, ref_exit, text, st = s.search_mem(data * 3, do_rc=True)
+        assert code == 0 and text == want * 3
     finally:
         s.destroy(); ctr.close()
 

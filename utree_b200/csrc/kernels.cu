@@ -72,7 +72,7 @@ struct DevDB {
     uint64_t kt_sectors;
     // membership pre-filter over all record words: blocked Bloom, line chosen by the word's minimizer
     const uint2 *sieve;        // sv_lines x 16 blocks of 8 bytes
-    uint64_t sv_lines;
+    uint32_t sv_lines;         // < 2^28
 };
 
 struct utb_db {
@@ -115,6 +115,7 @@ __device__ __forceinline__ uint64_t revcomp_word(uint64_t w) {
     uint64_t x = __brevll(~w);
     return ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
 }
+#define PK_GUARD 8u               // all-bad groups behind the last read: the sieve kernel walks whole tiles without bounds checks
 // pkr (optional): the reverse complement of every packed group, so that the reverse-complement window of a
 // position is a funnel shift of two pkr words exactly as the forward window is one of two pk words
 __global__ void __launch_bounds__(256)
@@ -123,9 +124,9 @@ pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_of
             uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ dims,
             uint64_t *__restrict__ pk, uint32_t *__restrict__ bad, uint64_t *__restrict__ pkr) {
     if (dims) { n_reads = dims[0]; n_groups = dims[1]; }          // device-side framing: the host only knows upper bounds
-    for (uint64_t g64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g64 <= n_groups; g64 += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t g64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g64 < (uint64_t)n_groups + PK_GUARD; g64 += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t g = (uint32_t)g64;
-        if (g == n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; break; }   // guard group
+        if (g >= n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; continue; }   // guard groups: all positions bad
         // read owning group g: largest r with grp_off[r] <= g
         uint32_t lo = 0, hi = n_reads;                     // invariant: grp_off[lo] <= g < grp_off[hi]
         while (hi - lo > 1) {
@@ -390,9 +391,9 @@ __device__ __forceinline__ uint32_t sv_mhash(uint32_t m, uint32_t r) {   // orde
     a *= 0x9E3779B1u; a ^= a >> 15; a *= 0x85EBCA77u;
     return a;
 }
-__device__ __forceinline__ uint64_t sv_line(uint32_t mv, uint64_t n_lines) {   // n_lines < 2^32
+__device__ __forceinline__ uint32_t sv_line(uint32_t mv, uint32_t n_lines) {   // n_lines < 2^28: a block index fits 32 bits
     uint32_t t = mv * 0xB5297A4Du; t ^= t >> 16; t *= 0x68E31DA5u;           // the minimum of 17 hashes is small: spread it again
-    return ((uint64_t)t * n_lines) >> 32;
+    return __umulhi(t, n_lines);
 }
 // xh / rh: upper halves (first 16 bases) of the word and of its reverse complement -- symmetric in the two
 __device__ __forceinline__ uint32_t sv_block(uint32_t xh, uint32_t rh) { return ((xh ^ rh) * 0x9E3779B1u) >> 28; }
@@ -417,7 +418,7 @@ __device__ __forceinline__ uint32_t sv_minimizer(uint64_t x, uint64_t rc) {
     }
     return mv;
 }
-__device__ __forceinline__ uint64_t sv_index(const DevDB &db, uint32_t mv, uint32_t blk) { return sv_line(mv, db.sv_lines) * 16u + blk; }
+__device__ __forceinline__ uint32_t sv_index(const DevDB &db, uint32_t mv, uint32_t blk) { return (sv_line(mv, db.sv_lines) << 4) | blk; }
 __device__ __forceinline__ bool sv_maybe(const DevDB &db, uint64_t word) {
     const uint64_t rc = revcomp_word(word);
     const uint2 v = __ldg(db.sieve + sv_index(db, sv_minimizer(word, rc), sv_block((uint32_t)(word >> 32), (uint32_t)(rc >> 32))));
@@ -438,7 +439,7 @@ sieve_build_kernel(DevDB db, uint32_t *__restrict__ sieve) {
     for (uint64_t i = a + gl; i < b; i += G) {
         const uint64_t word = (p << 40) | load_suffix(db.recs, i * db.sz);
         const uint64_t rc = revcomp_word(word);
-        uint32_t *blk = sieve + 2u * sv_index(db, sv_minimizer(word, rc), sv_block((uint32_t)(word >> 32), (uint32_t)(rc >> 32)));
+        uint32_t *blk = sieve + 2ull * sv_index(db, sv_minimizer(word, rc), sv_block((uint32_t)(word >> 32), (uint32_t)(rc >> 32)));
         const uint2 m = sv_masks((uint32_t)(word >> 32), (uint32_t)word);
         atomicOr(blk + 0, m.x); atomicOr(blk + 1, m.y);
     }
@@ -556,13 +557,10 @@ __device__ __forceinline__ uint32_t emit_survivors(const DevDB &db, WarpQueue &w
 // the 17 hashes at positions p .. p+16, taken across lanes with shuffles (doubling: 2, 4, 8, 16, 17),
 // where positions beyond lane 31 belong to the next step -- which is computed one tile ahead and
 // carried over, so nothing is computed twice.
-#ifndef SV_U
-#define SV_U 4                    // steps per tile = filter loads in flight per lane
-#endif
-#ifndef SV_MINB
-#define SV_MINB 3                 // CTAs per SM the register budget is sized for
-#endif
-struct SvStep { uint32_t wh, wl, rh, rl, h, blk; bool valid; };   // window, its reverse complement (halves), 16-mer hash, block in the line
+// template parameters of sieve_kernel: SV_U steps per tile (= filter loads in flight per lane), SV_MINB CTAs per SM
+// the register budget is sized for; the pair in use is picked at run time (sv_variant: measured on B200, UTB_SV_VARIANT)
+#define SV_DEAD 0xFFFFFFFFu       // SvStep.blk of a position without a valid window
+struct SvStep { uint32_t wh, wl, rh, rl, h, blk; };              // window, its reverse complement (halves), 16-mer hash, block in the line
 struct SvWords { uint64_t hi, lo, rhi, rlo; uint32_t bh, bl; };   // groups s and s + 1 of pk / pkr / bad
 __device__ __forceinline__ void sv_step(const SvWords &g, bool upper, uint32_t r2, uint32_t lane, SvStep &s) {
     // forward window: the 128 bits hi:lo shifted left by 2 * lane, upper 64 bits
@@ -573,22 +571,22 @@ __device__ __forceinline__ void sv_step(const SvWords &g, bool upper, uint32_t r
     const uint32_t a0 = (uint32_t)(g.rlo >> 32), a1 = (uint32_t)g.rlo, a2 = (uint32_t)(g.rhi >> 32), a3 = (uint32_t)g.rhi;
     const uint32_t z0 = upper ? a2 : a3, z1 = upper ? a1 : a2, z2 = upper ? a0 : a1;
     s.rl = __funnelshift_r(z0, z1, r2); s.rh = __funnelshift_r(z1, z2, r2);
-    s.valid = __funnelshift_r(g.bh, g.bl, lane) == 0u;             // no bad base in the 32 positions from here
     s.h = sv_mhash(s.wh, s.rl);
-    s.blk = sv_block(s.wh, s.rh);
+    s.blk = __funnelshift_r(g.bh, g.bl, lane) == 0u ? sv_block(s.wh, s.rh) : SV_DEAD;   // a bad base in the 32 positions from here: no window
 }
-// value of the (virtual) array x[0..SV_U] at index 32 * u + lane + D
-template <int D>
-__device__ __forceinline__ void sv_shift_min(uint32_t (&x)[SV_U + 1], uint32_t lane) {
+// x[u][lane] -> value of the (virtual) array x at index 32 * u + lane + D; the last array only serves lanes that stay inside it
+template <int D, int SV_U>
+__device__ __forceinline__ void sv_shifted(const uint32_t (&x)[SV_U + 1], uint32_t (&y)[SV_U + 1], uint32_t lane) {
     uint32_t rot[SV_U + 1];
 #pragma unroll
     for (int u = 0; u <= SV_U; ++u) rot[u] = __shfl_sync(0xFFFFFFFFu, x[u], (lane + D) & 31u);
     const bool same = lane + D < 32u;
 #pragma unroll
-    for (int u = 0; u < SV_U; ++u) { const uint32_t y = same ? rot[u] : rot[u + 1]; x[u] = y < x[u] ? y : x[u]; }
-    x[SV_U] = rot[SV_U] < x[SV_U] ? rot[SV_U] : x[SV_U];          // only its low lanes are ever used (no step beyond it is needed)
+    for (int u = 0; u < SV_U; ++u) y[u] = same ? rot[u] : rot[u + 1];
+    y[SV_U] = rot[SV_U];
 }
-template <int NSTR>
+__device__ __forceinline__ void sv_prefetch(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+template <int NSTR, int SV_U, int SV_MINB>
 __global__ void __launch_bounds__(256, SV_MINB)
 sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint64_t *__restrict__ pkr, uint32_t n_pos,
              const uint32_t *__restrict__ n_groups_dev,
@@ -599,62 +597,63 @@ sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restri
     const uint32_t lane = threadIdx.x & 31u;
     const bool upper = lane >= 16u;
     const uint32_t r2 = 2u * (lane & 15u);
-    const uint32_t n_steps = n_pos >> 5;                           // n_pos is a multiple of 32; group n_steps is the guard group
+    const uint32_t n_steps = n_pos >> 5;                           // n_pos is a multiple of 32; PK_GUARD all-bad groups follow group n_steps - 1
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5), wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     uint32_t per = (n_steps + n_warps - 1) / n_warps;
     per = (per + SV_U - 1) / SV_U * SV_U;
     const uint64_t s0 = (uint64_t)wid * per;
     const uint32_t s1 = s0 + per < n_steps ? (uint32_t)(s0 + per) : n_steps;
+    const uint2 *__restrict__ sieve = db.sieve;
+    const uint32_t n_lines = db.sv_lines;
     WarpQueue wq;
     wq_init(wq);
     uint32_t nv = 0, nh = 0;
     if (s0 < s1) {
         SvStep st[SV_U + 1];
-        // groups s and s + 1 feed step s; the pair is carried from step to step (two 8-byte and one 4-byte load per step)
+        // groups s and s + 1 feed step s; the pair is carried from step to step (two 8-byte and one 4-byte load per step).
+        // A tile may run past s1 only at the very end of the batch, into the guard groups: no bounds checks in the loop.
         SvWords g;
         g.hi = __ldg(pk + s0); g.rhi = __ldg(pkr + s0); g.bh = __ldg(bad + s0);
         g.lo = __ldg(pk + s0 + 1); g.rlo = __ldg(pkr + s0 + 1); g.bl = __ldg(bad + s0 + 1);
         sv_step(g, upper, r2, lane, st[0]);
         for (uint32_t s = (uint32_t)s0; s < s1; s += SV_U) {
+            {   // the three streams are read front to back: ask for the lines two ahead (a line of pk / pkr feeds 16 steps)
+                const uint32_t pf = s + 32u < n_steps ? s + 32u : n_steps;
+                sv_prefetch(pk + pf); sv_prefetch(pkr + pf); sv_prefetch(bad + pf);
+            }
 #pragma unroll
             for (int u = 1; u <= SV_U; ++u) {
                 g.hi = g.lo; g.rhi = g.rlo; g.bh = g.bl;
-                const uint32_t gi = s + u + 1;                     // groups up to n_steps + 1 exist (guard + slack)
-                if (gi <= n_steps + 1) { g.lo = __ldg(pk + gi); g.rlo = __ldg(pkr + gi); g.bl = __ldg(bad + gi); }
-                else { g.lo = 0; g.rlo = 0; g.bl = 0xFFFFFFFFu; }
-                if (s + u <= n_steps) sv_step(g, upper, r2, lane, st[u]);
-                else { st[u].wh = st[u].wl = st[u].rh = st[u].rl = 0; st[u].h = 0xFFFFFFFFu; st[u].blk = 0; st[u].valid = false; }
+                g.lo = __ldg(pk + s + u + 1); g.rlo = __ldg(pkr + s + u + 1); g.bl = __ldg(bad + s + u + 1);
+                sv_step(g, upper, r2, lane, st[u]);
             }
-            uint32_t x[SV_U + 1], h16[SV_U + 1];
+            // minimizer = min of the 17 hashes at q .. q+16: windows of 3, then 9 (3 + 3 + 3), then 17 (9 + 9, one shared)
+            uint32_t x[SV_U + 1], y1[SV_U + 1], y2[SV_U + 1];
 #pragma unroll
-            for (int u = 0; u <= SV_U; ++u) { x[u] = st[u].h; h16[u] = st[u].h; }
-            sv_shift_min<1>(x, lane);                              // min over [q, q+1]
-            sv_shift_min<2>(x, lane);                              // [q, q+3]
-            sv_shift_min<4>(x, lane);                              // [q, q+7]
-            sv_shift_min<8>(x, lane);                              // [q, q+15]
-            {                                                      // [q, q+16]
-                uint32_t rot[SV_U + 1];
+            for (int u = 0; u <= SV_U; ++u) x[u] = st[u].h;
+            sv_shifted<1, SV_U>(x, y1, lane); sv_shifted<2, SV_U>(x, y2, lane);
 #pragma unroll
-                for (int u = 0; u <= SV_U; ++u) rot[u] = __shfl_sync(0xFFFFFFFFu, h16[u], (lane + 16u) & 31u);
+            for (int u = 0; u <= SV_U; ++u) x[u] = __vimin3_u32(x[u], y1[u], y2[u]);     // [q, q+2]
+            sv_shifted<3, SV_U>(x, y1, lane); sv_shifted<6, SV_U>(x, y2, lane);
 #pragma unroll
-                for (int u = 0; u < SV_U; ++u) { const uint32_t y = lane < 16u ? rot[u] : rot[u + 1]; x[u] = y < x[u] ? y : x[u]; }
-            }
+            for (int u = 0; u <= SV_U; ++u) x[u] = __vimin3_u32(x[u], y1[u], y2[u]);     // [q, q+8]
+            sv_shifted<8, SV_U>(x, y1, lane);
+#pragma unroll
+            for (int u = 0; u < SV_U; ++u) x[u] = x[u] < y1[u] ? x[u] : y1[u];           // [q, q+16]
             uint2 v[SV_U];
-            bool live[SV_U];
 #pragma unroll
             for (int u = 0; u < SV_U; ++u) {
-                live[u] = st[u].valid && s + u < s1;
                 v[u] = make_uint2(0, 0);
-                if (live[u]) v[u] = __ldg(db.sieve + sv_index(db, x[u], st[u].blk));
+                if (st[u].blk != SV_DEAD) v[u] = __ldg(sieve + ((sv_line(x[u], n_lines) << 4) | st[u].blk));
             }
 #pragma unroll
             for (int u = 0; u < SV_U; ++u) {
-                if (__any_sync(0xFFFFFFFFu, live[u])) {            // the padding group behind every read holds no window at all
-                    const bool passF = live[u] && sv_test(v[u], st[u].wh, st[u].wl);
-                    const bool passR = NSTR == 2 && live[u] && sv_test(v[u], st[u].rh, st[u].rl);
-                    nh += emit_survivors<NSTR>(db, wq, lane, passF, passR, ((uint64_t)st[u].wh << 32) | st[u].wl, ((uint64_t)st[u].rh << 32) | st[u].rl,
+                const bool live = st[u].blk != SV_DEAD;
+                if (__any_sync(0xFFFFFFFFu, live)) {               // the padding group behind every read holds no window at all
+                    const bool tF = sv_test(v[u], st[u].wh, st[u].wl), tR = NSTR == 2 && sv_test(v[u], st[u].rh, st[u].rl);
+                    nh += emit_survivors<NSTR>(db, wq, lane, live & tF, live & tR, ((uint64_t)st[u].wh << 32) | st[u].wl, ((uint64_t)st[u].rh << 32) | st[u].rl,
                                                (s + u) * 32u + lane, q_words, q_slots, q_count, q_cap, hits, hitmap);
-                    nv += live[u] ? NSTR : 0;                      // hits[] is only valid where hitmap is set: nothing to store for misses
+                    nv += live ? NSTR : 0;                         // hits[] is only valid where hitmap is set: nothing to store for misses
                 }
             }
             st[0] = st[SV_U];
@@ -1081,91 +1080,195 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__rest
     if (tid == 0 && s_good) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), (unsigned long long)s_good);
 }
 
-// Block per read for long queries / label-rich reads: global-memory histogram
-// over label ids (block-private scratch, kept zeroed), compaction in rank
-// order, then the same walk.  Persistent over the queue filled by
-// vote_warp_kernel.
+// ---- long queries and label-rich reads ---------------------------------------------------
+// Reads the warp kernel defers (more than VW_MAXHITS lookup slots or more than VW_SLOTS distinct
+// labels) are voted from a dense per-label histogram in global memory; the labels a read touches
+// are appended to a list the moment their count leaves zero, so what follows costs O(touched
+// labels), not O(max_ix): the list is sorted by label rank in shared memory (itree.c:1041), the
+// counts are gathered and the scratch is left clean, then the same walk runs.
+//   vote_block_kernel   one CTA per read, CTA-private scratch; reads with more than `split_slots`
+//                       lookup slots (north_star: "long and whole-genome queries split across
+//                       blocks and merged") are handed on to
+//   vote_big_count_kernel  the hit map of every such read is cut into chunks of VBIG_CHUNK_WORDS
+//                       words which the whole grid accumulates into that read's histogram, and
+//   vote_big_finish_kernel one CTA per read merges: sort, gather, walk.
 #define VB_THREADS 256
+#define VB_PER_SM 2
+#define VB_SORT_MAX 2048u           // touched labels sorted in shared memory; beyond: sweep over all labels in rank order
+#define VBIG_CHUNK_WORDS 2048u      // hit-map words (65,536 lookup slots) a CTA accumulates at a time
+#define VBIG_POOL_MAX 256u          // split reads a batch can hold scratch for
+struct VoteLong {
+    uint32_t *hist, *tlab, *tcnt;                       // [CTAs of vote_block_kernel][max_ix]
+    uint32_t *big_hist, *big_tlab, *big_tcnt;           // [pool][max_ix]
+    uint32_t *big_list;                                 // [pool] read index
+    uint32_t *big_state;                                // [0] split reads of the batch, then per read: touched labels, hits
+    uint32_t pool;
+    uint32_t sort_max;                                  // <= VB_SORT_MAX (tests lower it to reach the sweep)
+    unsigned long long split_slots;
+};
+// Adds the labels of the hit-map words [w0, w1) of one read (dense mode: of the slots they cover) to hist;
+// labels met for the first time are appended to tlab through *nt.  Block-wide call; returns this thread's hits.
+__device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn &in, uint64_t start, uint64_t count, uint64_t w0, uint64_t w1,
+                                                  uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    uint32_t n_local = 0;
+    if (in.hitmap) {
+        const uint32_t *hm = in.hitmap + (start >> 5);             // start is a multiple of 32
+        for (uint64_t wi = w0 + tid; wi < w1; wi += VB_THREADS) {
+            uint32_t m = __ldg(hm + wi);
+            while (m) {
+                const uint32_t bit = __ffs(m) - 1; m &= m - 1;
+                const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
+                if (h < db.max_ix) {
+                    if (atomicAdd(&hist[h], 1u) == 0u) tlab[atomicAdd(nt, 1u)] = h;
+                    ++n_local;
+                }
+            }
+        }
+    } else {
+        const uint64_t lo = w0 * 32u, hi = w1 * 32u < count ? w1 * 32u : count;
+        for (uint64_t base = lo; base < hi; base += VB_THREADS) {
+            const uint64_t i = base + tid;
+            const uint32_t h = i < hi ? __ldg(in.hits + start + i) : HIT_NOWIN;
+            const bool ok = h < db.max_ix;
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
+            if (ok && (uint32_t)(__ffs(peers) - 1) == lane && atomicAdd(&hist[h], (uint32_t)__popc(peers)) == 0u) tlab[atomicAdd(nt, 1u)] = h;
+            n_local += ok;
+        }
+    }
+    return n_local;
+}
+struct VlSmem { unsigned long long key[VB_SORT_MAX]; uint32_t warp[VB_THREADS / 32]; uint32_t base; };
+// hist holds the label counts of one read, tlab[0 .. nt) the labels touched (any order), n the hits.  Block-wide.
+__device__ void vl_finish(const DevDB &db, uint32_t *hist, uint32_t *tlab, uint32_t *tcnt, uint32_t nt, uint32_t n, uint32_t sort_max,
+                          utb_result *out, unsigned long long *__restrict__ counters, VlSmem &sm) {
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    if (n == 0) {                                                  // block-uniform
+        if (tid == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        return;
+    }
+    __threadfence();
+    __syncthreads();
+    uint32_t uix;
+    if (nt <= sort_max) {
+        // sort the touched labels by rank (strcmp order, itree.c:1041): bitonic network over rank << 32 | label
+        uint32_t np2 = 2;
+        while (np2 < nt) np2 <<= 1;
+        for (uint32_t i = tid; i < np2; i += VB_THREADS) {
+            unsigned long long k = ~0ull;
+            if (i < nt) { const uint32_t lab = __ldcg(tlab + i); k = ((unsigned long long)__ldg(db.rank + lab) << 32) | lab; }
+            sm.key[i] = k;
+        }
+        __syncthreads();
+        for (uint32_t k2 = 2; k2 <= np2; k2 <<= 1)
+            for (uint32_t j = k2 >> 1; j; j >>= 1) {
+                for (uint32_t i = tid; i < np2; i += VB_THREADS) {
+                    const uint32_t l = i ^ j;
+                    if (l > i) {
+                        const unsigned long long a = sm.key[i], c = sm.key[l];
+                        const bool up = (i & k2) == 0;
+                        if ((a > c) == up) { sm.key[i] = c; sm.key[l] = a; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (uint32_t i = tid; i < nt; i += VB_THREADS) {
+            const uint32_t lab = (uint32_t)sm.key[i];
+            tlab[i] = lab; tcnt[i] = __ldcg(hist + lab);          // L2 view: the counts were made by atomics
+            hist[lab] = 0;                                         // leave the scratch clean
+        }
+        uix = nt;
+    } else {
+        // very many labels: compaction of the whole label space in rank order (itree.c:1036-1041 produce exactly this list)
+        if (tid == 0) sm.base = 0;
+        __syncthreads();
+        for (uint32_t r0 = 0; r0 < db.max_ix; r0 += VB_THREADS) {
+            const uint32_t rr = r0 + tid;
+            const uint32_t lab = rr < db.max_ix ? __ldg(db.by_rank + rr) : 0;
+            const uint32_t c = rr < db.max_ix ? __ldcg(hist + lab) : 0;
+            const uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
+            if (lane == 0) sm.warp[wid] = __popc(bal);
+            __syncthreads();
+            uint32_t wbase = sm.base;
+            for (uint32_t w = 0; w < wid; ++w) wbase += sm.warp[w];
+            if (c) {
+                const uint32_t p = wbase + __popc(bal & ((1u << lane) - 1u));
+                tlab[p] = lab; tcnt[p] = c;
+                hist[lab] = 0;
+            }
+            __syncthreads();
+            if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < VB_THREADS / 32; ++w) t += sm.warp[w]; sm.base += t; }
+            __syncthreads();
+        }
+        uix = sm.base;
+    }
+    __threadfence();
+    __syncthreads();
+    if (wid == 0) {
+        if (lane == 0) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), 1ull);   // good finds (itree.c:1029)
+        if (uix == 1) {                                            // itree.c:1031-1032, 1039-1040
+            if (lane == 0) { out->kind = UTB_STAR; out->label = tlab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        } else walk_warp(db, tlab, tcnt, uix, n, out);
+    }
+    __syncthreads();
+}
 __global__ void __launch_bounds__(VB_THREADS)
 vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
                   const uint32_t *__restrict__ gen_list, const uint32_t *__restrict__ gen_count,
-                  uint32_t *__restrict__ hist_all, uint32_t *__restrict__ tlab_all, uint32_t *__restrict__ tcnt_all,
-                  unsigned long long *__restrict__ counters) {
-    __shared__ uint32_t s_warp[VB_THREADS / 32];
-    __shared__ uint32_t s_base, s_n;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
-    uint32_t *hist = hist_all + (size_t)blockIdx.x * db.max_ix;
-    uint32_t *T_lab = tlab_all + (size_t)blockIdx.x * db.max_ix;
-    uint32_t *T_cnt = tcnt_all + (size_t)blockIdx.x * db.max_ix;
+                  VoteLong vl, unsigned long long *__restrict__ counters) {
+    __shared__ VlSmem sm;
+    __shared__ uint32_t s_nt, s_n, s_big;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    uint32_t *hist = vl.hist + (size_t)blockIdx.x * db.max_ix;
+    uint32_t *tlab = vl.tlab + (size_t)blockIdx.x * db.max_ix;
+    uint32_t *tcnt = vl.tcnt + (size_t)blockIdx.x * db.max_ix;
     const uint32_t total = *gen_count;
     for (uint32_t qi = blockIdx.x; qi < total; qi += gridDim.x) {
         const uint32_t r = gen_list[qi];
         uint64_t start, count;
         vote_range(in, r, start, count);
-        // 1. histogram (warp-aggregated global atomics) + foundUniq
-        uint32_t n_local = 0;
-        if (in.hitmap) {
-            const uint32_t *hm = in.hitmap + (start >> 5);
-            const uint64_t nwords = (count + 31) >> 5;
-            for (uint64_t wi = tid; wi < nwords; wi += VB_THREADS) {
-                uint32_t m = __ldg(hm + wi);
-                while (m) {
-                    const uint32_t bit = __ffs(m) - 1; m &= m - 1;
-                    const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
-                    if (h < db.max_ix) { atomicAdd(&hist[h], 1u); ++n_local; }
-                }
+        if (tid == 0) {
+            s_nt = 0; s_n = 0; s_big = 0;
+            if (count > vl.split_slots) {                          // split across the grid (scratch permitting)
+                const uint32_t bi = atomicAdd(vl.big_state, 1u);
+                if (bi < vl.pool) { vl.big_list[bi] = r; s_big = 1; }
             }
-        } else
-        for (uint64_t base = 0; base < count; base += VB_THREADS) {
-            uint64_t i = base + tid;
-            uint32_t h = i < count ? __ldg(in.hits + start + i) : HIT_NOWIN;
-            bool ok = h < db.max_ix;
-            uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-            if (ok && (uint32_t)(__ffs(peers) - 1) == lane) atomicAdd(&hist[h], (uint32_t)__popc(peers));
-            n_local += ok;
         }
+        __syncthreads();
+        if (s_big) { __syncthreads(); continue; }
+        uint32_t n_local = vl_accumulate(db, in, start, count, 0, (count + 31) >> 5, hist, tlab, &s_nt);
         for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
-        if (tid == 0) { s_n = 0; s_base = 0; }
-        __syncthreads();
         if (lane == 0 && n_local) atomicAdd(&s_n, n_local);
-        __threadfence();
         __syncthreads();
-        const uint32_t n = s_n;
-        // 2. compaction in rank order (itree.c:1036-1041 produce exactly this list)
-        for (uint32_t r0 = 0; r0 < db.max_ix; r0 += VB_THREADS) {
-            uint32_t rr = r0 + tid;
-            uint32_t lab = rr < db.max_ix ? __ldg(db.by_rank + rr) : 0;
-            uint32_t c = rr < db.max_ix ? __ldcg(hist + lab) : 0;    // L2 view: the counts were made by atomics
-            uint32_t bal = __ballot_sync(0xFFFFFFFFu, c != 0);
-            if (lane == 0) s_warp[wid] = __popc(bal);
-            __syncthreads();
-            uint32_t wbase = s_base;
-            for (uint32_t w = 0; w < wid; ++w) wbase += s_warp[w];
-            if (c) {
-                uint32_t p = wbase + __popc(bal & ((1u << lane) - 1u));
-                T_lab[p] = lab; T_cnt[p] = c;
-                hist[lab] = 0;                                     // leave the scratch clean
-            }
-            __syncthreads();
-            if (tid == 0) { uint32_t t = 0; for (uint32_t w = 0; w < VB_THREADS / 32; ++w) t += s_warp[w]; s_base += t; }
-            __syncthreads();
-        }
-        __threadfence();
-        __syncthreads();
-        const uint32_t uix = s_base;
-        utb_result *out = results + r;
-        if (wid == 0) {
-            if (n == 0) {
-                if (lane == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
-            } else {
-                if (lane == 0) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), 1ull);
-                if (uix == 1) {
-                    if (lane == 0) { out->kind = UTB_STAR; out->label = T_lab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
-                } else walk_warp(db, T_lab, T_cnt, uix, n, out);
-            }
-        }
+        vl_finish(db, hist, tlab, tcnt, s_nt, s_n, vl.sort_max, results + r, counters, sm);
         __syncthreads();
     }
+}
+__global__ void __launch_bounds__(VB_THREADS)
+vote_big_count_kernel(DevDB db, VoteIn in, VoteLong vl) {
+    const uint32_t n_big = min(*vl.big_state, vl.pool), lane = threadIdx.x & 31u;
+    for (uint32_t bi = 0; bi < n_big; ++bi) {
+        uint64_t start, count;
+        vote_range(in, vl.big_list[bi], start, count);
+        const uint64_t n_words = (count + 31) >> 5, n_chunks = (n_words + VBIG_CHUNK_WORDS - 1) / VBIG_CHUNK_WORDS;
+        uint32_t *hist = vl.big_hist + (size_t)bi * db.max_ix, *tlab = vl.big_tlab + (size_t)bi * db.max_ix;
+        uint32_t n_local = 0;
+        // the chunks of consecutive reads start at different CTAs, so short tails do not pile up on CTA 0
+        for (uint64_t c = (blockIdx.x + gridDim.x - (bi * 61u) % gridDim.x) % gridDim.x; c < n_chunks; c += gridDim.x) {
+            const uint64_t w0 = c * VBIG_CHUNK_WORDS, w1 = w0 + VBIG_CHUNK_WORDS < n_words ? w0 + VBIG_CHUNK_WORDS : n_words;
+            n_local += vl_accumulate(db, in, start, count, w0, w1, hist, tlab, vl.big_state + 1 + 2 * bi);
+        }
+        for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
+        if (lane == 0 && n_local) atomicAdd(vl.big_state + 2 + 2 * bi, n_local);
+    }
+}
+__global__ void __launch_bounds__(VB_THREADS)
+vote_big_finish_kernel(DevDB db, VoteLong vl, utb_result *__restrict__ results, unsigned long long *__restrict__ counters) {
+    __shared__ VlSmem sm;
+    const uint32_t n_big = min(*vl.big_state, vl.pool);
+    for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x)
+        vl_finish(db, vl.big_hist + (size_t)bi * db.max_ix, vl.big_tlab + (size_t)bi * db.max_ix, vl.big_tcnt + (size_t)bi * db.max_ix,
+                  vl.big_state[1 + 2 * bi], vl.big_state[2 + 2 * bi], vl.sort_max, results + vl.big_list[bi], counters, sm);
 }
 
 // ---------------------------------------------------------------------------
@@ -1637,11 +1740,11 @@ static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
         db->sieve_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
         if (db->sieve_mode) {
             // SV_RPL records per 128-byte line = ~43 bits per record: ~0.04 % false positives
-            const uint64_t lines = n / SV_RPL + 1024;
-            if (lines >= ((uint64_t)1 << 32)) { utb_set_error("tree too large for the sieve"); return UTB_ERR_LIMIT; }
+            uint64_t lines = n / SV_RPL + 1024;
+            if (lines >= ((uint64_t)1 << 28)) lines = ((uint64_t)1 << 28) - 1;   // > 6.4 G records: more records per line, more false positives
             CK(cudaMalloc(&db->sieve, lines * 128));
             CK(cudaMemset(db->sieve, 0, lines * 128));
-            db->d.sv_lines = lines;
+            db->d.sv_lines = (uint32_t)lines;
             DevDB dd = db->d;
             uint32_t *sv = (uint32_t *)db->sieve;
             launch_per_bin(n, [&](int g, unsigned blocks) {
@@ -1745,6 +1848,55 @@ extern "C" int utb_db_lookup_mode(const utb_db *db) { return db ? db->use_table 
 extern "C" int utb_db_device(const utb_db *db) { return db ? db->device : -1; }
 
 // ---------------------------------------------------------------------------
+// scratch + launch of the long-read vote (vote_block / vote_big_* kernels)
+// ---------------------------------------------------------------------------
+struct vote_scratch { VoteLong vl; unsigned n_cta; };
+static void vs_free(vote_scratch *vs) {
+    cudaFree(vs->vl.hist); cudaFree(vs->vl.tlab); cudaFree(vs->vl.tcnt);
+    cudaFree(vs->vl.big_hist); cudaFree(vs->vl.big_tlab); cudaFree(vs->vl.big_tcnt); cudaFree(vs->vl.big_list); cudaFree(vs->vl.big_state);
+    memset(vs, 0, sizeof *vs);
+}
+// max_bytes: raw bytes a batch can hold -- a read of more than max_bytes / pool bases cannot occur more than pool times
+static int vs_alloc(const utb_db *db, size_t max_bytes, vote_scratch *vs) {
+    memset(vs, 0, sizeof *vs);
+    const size_t nl = db->d.max_ix ? db->d.max_ix : 1;
+    vs->n_cta = (unsigned)db->sm_count * VB_PER_SM;
+    size_t pool = ((size_t)96 << 20) / (12 * nl);
+    if (pool > VBIG_POOL_MAX) pool = VBIG_POOL_MAX;
+    if (pool < 1) pool = 1;
+    vs->vl.pool = (uint32_t)pool;
+    size_t split_bases = max_bytes / pool + 1;
+    if (split_bases < ((size_t)256 << 10)) split_bases = (size_t)256 << 10;
+    vs->vl.split_slots = 2ull * split_bases;
+    const char *e = getenv("UTB_VOTE_SPLIT_SLOTS");                // tests: a small threshold sends short "long" reads through the split path
+    if (e && atoll(e) > 0) vs->vl.split_slots = (unsigned long long)atoll(e);
+    vs->vl.sort_max = VB_SORT_MAX;
+    e = getenv("UTB_VOTE_SORT_MAX");
+    if (e && atoi(e) >= 0 && (uint32_t)atoi(e) < VB_SORT_MAX) vs->vl.sort_max = (uint32_t)atoi(e);
+    cudaError_t err = cudaMalloc(&vs->vl.hist, (size_t)vs->n_cta * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.tlab, (size_t)vs->n_cta * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.tcnt, (size_t)vs->n_cta * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_hist, pool * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_tlab, pool * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_tcnt, pool * nl * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_list, pool * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_state, (1 + 2 * pool) * 4);
+    if (err == cudaSuccess) err = cudaMemset(vs->vl.hist, 0, (size_t)vs->n_cta * nl * 4);      // the kernels leave the histograms zeroed
+    if (err == cudaSuccess) err = cudaMemset(vs->vl.big_hist, 0, pool * nl * 4);
+    if (err != cudaSuccess) { vs_free(vs); CK(err); }
+    return UTB_OK;
+}
+static int launch_long_vote(const utb_db *db, const VoteIn &in, utb_result *results, const uint32_t *gen_list, const uint32_t *gen_count,
+                            vote_scratch *vs, unsigned long long *counters, cudaStream_t st) {
+    CK(cudaMemsetAsync(vs->vl.big_state, 0, (1 + 2 * (size_t)vs->vl.pool) * 4, st));
+    vote_block_kernel<<<vs->n_cta, VB_THREADS, 0, st>>>(db->d, in, results, gen_list, gen_count, vs->vl, counters);
+    vote_big_count_kernel<<<(unsigned)db->sm_count * 4, VB_THREADS, 0, st>>>(db->d, in, vs->vl);
+    vote_big_finish_kernel<<<vs->vl.pool < (uint32_t)db->sm_count ? vs->vl.pool : (unsigned)db->sm_count, VB_THREADS, 0, st>>>(db->d, vs->vl, results, counters);
+    CK(cudaGetLastError());
+    return UTB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // C ABI: batches
 // ---------------------------------------------------------------------------
 
@@ -1765,7 +1917,7 @@ struct utb_batch {
     uint32_t *d_name_off, *d_name_len, *d_line_len, *d_line_off, *d_scan_sums, *d_text_len; char *d_text;
     int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
-    uint32_t *d_hist, *d_tlab, *d_tcnt;
+    vote_scratch vs;
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
     // last submit
@@ -1799,7 +1951,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_raw); cudaFree(b->d_seq_off); cudaFree(b->d_seq_len); cudaFree(b->d_grp_off);
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results); cudaFree(b->d_pkr);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_warp_list); cudaFree(b->d_warp_count); cudaFree(b->d_counters);
-    cudaFree(b->d_hist); cudaFree(b->d_tlab); cudaFree(b->d_tcnt);
+    vs_free(&b->vs);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFreeHost(b->h_frame_err);
     cudaFree(b->d_frame_info); cudaFree(b->d_dims); cudaFreeHost(b->h_dims);
@@ -1822,7 +1974,6 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     // every read owns ceil((len+1)/32) <= len/32 + 1 groups
     b->max_groups = max_bytes / 32 + max_reads + 1;
     size_t npos = (size_t)b->max_groups * 32;
-    size_t nl = db->d.max_ix ? db->d.max_ix : 1;
 #define BK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { utb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); utb_batch_destroy(b); return UTB_ERR_CUDA; } } while (0)
     BK(cudaStreamCreateWithFlags(&b->st, cudaStreamNonBlocking));
     BK(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
@@ -1849,8 +2000,8 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_seq_off, max_reads * 8));
     BK(cudaMalloc(&b->d_seq_len, max_reads * 4));
     BK(cudaMalloc(&b->d_grp_off, (max_reads + 1) * 4));
-    BK(cudaMalloc(&b->d_pk, (b->max_groups + 2) * 8));
-    BK(cudaMalloc(&b->d_bad, (b->max_groups + 2) * 4));
+    BK(cudaMalloc(&b->d_pk, (b->max_groups + PK_GUARD + 2) * 8));
+    BK(cudaMalloc(&b->d_bad, (b->max_groups + PK_GUARD + 2) * 4));
     BK(cudaMalloc(&b->d_hits, npos * 2 * 4));
     BK(cudaMalloc(&b->d_results, max_reads * sizeof(utb_result)));
     BK(cudaMalloc(&b->d_gen_list, max_reads * 4));
@@ -1858,10 +2009,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
     BK(cudaMalloc(&b->d_warp_list, max_reads * 4));
     BK(cudaMalloc(&b->d_warp_count, 4));
     BK(cudaMalloc(&b->d_counters, 4 * COUNTER_SLOTS * 8));
-    BK(cudaMalloc(&b->d_hist, (size_t)db->sm_count * nl * 4));
-    BK(cudaMalloc(&b->d_tlab, (size_t)db->sm_count * nl * 4));
-    BK(cudaMalloc(&b->d_tcnt, (size_t)db->sm_count * nl * 4));
-    BK(cudaMemset(b->d_hist, 0, (size_t)db->sm_count * nl * 4));
+    if (vs_alloc(db, max_bytes, &b->vs)) { utb_batch_destroy(b); return UTB_ERR_CUDA; }
     BK(cudaMemset(b->d_raw, 0, max_bytes + 128));
     if (db->sieve) {                                               // queue for a quarter of the lookup slots; overflow resolves inline
         b->q_cap = npos * 2 / 4 + 4096;
@@ -1873,7 +2021,7 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         BK(cudaMemset(b->d_qslots, 0xFF, b->q_cap * 4));            // Q_INVALID
         BK(cudaMalloc(&b->d_qcount, 8));
         BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
-        BK(cudaMalloc(&b->d_pkr, (b->max_groups + 2) * 8));
+        BK(cudaMalloc(&b->d_pkr, (b->max_groups + PK_GUARD + 2) * 8));
     }
     if (db->l2_window) {
         cudaStreamAttrValue a;
@@ -1906,7 +2054,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     CK(cudaMemsetAsync(b->d_counters, 0, 4 * COUNTER_SLOTS * 8, b->st));
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
-        pack_kernel<<<gs_grid(b, (uint64_t)n_groups + 1, 256, 32), 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
+        pack_kernel<<<gs_grid(b, (uint64_t)n_groups + PK_GUARD, 256, 32), 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
                                                                    n_reads, n_groups, b->dims_dev, b->d_pk, b->d_bad, b->d_pkr);
         b->launches++;
     }
@@ -1923,11 +2071,20 @@ static int launch_stages(utb_batch *b, bool timed) {
             // 1-bit-per-slot map, the vote reads the map and gathers only flagged slots
             CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st));
             if (timed) CK(cudaEventRecord(b->ev[4], b->st));
-            // persistent: SV_MINB CTAs per SM, every warp a contiguous range of steps (small batches: one tile per warp)
-            const unsigned wb = (n_groups + 8u * SV_U - 1) / (8u * SV_U);
-            const unsigned pb = wb < sms * SV_MINB ? (wb ? wb : 1u) : sms * SV_MINB;
-            if (nstr == 2) sieve_kernel<2><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
-            else sieve_kernel<1><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap);
+            // persistent: MINB CTAs per SM, every warp a contiguous range of steps (small batches: one tile per warp)
+            static const int sv_variant = [] { const char *e = getenv("UTB_SV_VARIANT"); return e ? atoi(e) : 0; }();
+#define SV_LAUNCH(U, MINB) do { \
+                const unsigned wb = (n_groups + 8u * U - 1) / (8u * U); \
+                const unsigned pb = wb < sms * MINB ? (wb ? wb : 1u) : sms * MINB; \
+                if (nstr == 2) sieve_kernel<2, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap); \
+                else sieve_kernel<1, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap); } while (0)
+            switch (sv_variant) {
+            case 1: SV_LAUNCH(4, 4); break;
+            case 2: SV_LAUNCH(2, 5); break;
+            case 3: SV_LAUNCH(2, 6); break;
+            default: SV_LAUNCH(4, 3); break;
+            }
+#undef SV_LAUNCH
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
             queue_lookup_kernel<<<sms * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
             b->launches++;
@@ -1957,9 +2114,9 @@ static int launch_stages(utb_batch *b, bool timed) {
         } else
             vote_warp_kernel<<<gs_grid(b, n_reads, VW_WARPS, 32), VW_WARPS * 32, 0, b->st>>>(
                 d, in, n_reads, b->dims_dev, nullptr, nullptr, b->d_results, b->d_gen_list, b->d_gen_count, b->d_counters);
-        vote_block_kernel<<<(unsigned)b->db->sm_count, VB_THREADS, 0, b->st>>>(d, in, b->d_results, b->d_gen_list, b->d_gen_count,
-                                                               b->d_hist, b->d_tlab, b->d_tcnt, b->d_counters);
-        b->launches += 2;
+        int rv = launch_long_vote(b->db, in, b->d_results, b->d_gen_list, b->d_gen_count, &b->vs, b->d_counters, b->st);
+        if (rv) return rv;
+        b->launches += 4;
     }
     if (timed) CK(cudaEventRecord(b->ev[3], b->st));
     CK(cudaGetLastError());
@@ -2303,14 +2460,14 @@ extern "C" int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len, uint
     uint8_t *d_raw; uint64_t *d_off, *d_pk, *d_f, *d_r; uint32_t *d_len, *d_grp, *d_bad; uint8_t *d_v;
     CK(cudaMalloc(&d_raw, (size_t)len + 128)); CK(cudaMemset(d_raw, 0, (size_t)len + 128));
     CK(cudaMalloc(&d_off, 8)); CK(cudaMalloc(&d_len, 4)); CK(cudaMalloc(&d_grp, 8));
-    CK(cudaMalloc(&d_pk, (size_t)(n_groups + 2) * 8)); CK(cudaMalloc(&d_bad, (size_t)(n_groups + 2) * 4));
+    CK(cudaMalloc(&d_pk, (size_t)(n_groups + PK_GUARD + 2) * 8)); CK(cudaMalloc(&d_bad, (size_t)(n_groups + PK_GUARD + 2) * 4));
     CK(cudaMalloc(&d_f, (size_t)n_pos * 8)); CK(cudaMalloc(&d_r, (size_t)n_pos * 8)); CK(cudaMalloc(&d_v, n_pos));
     uint64_t off = 1; uint32_t grp[2] = {0, n_groups};
     CK(cudaMemcpy(d_raw + 1, seq, len, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_len, &len, 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_grp, grp, 8, cudaMemcpyHostToDevice));
-    pack_kernel<<<(n_groups + 1 + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad, nullptr);
+    pack_kernel<<<(n_groups + PK_GUARD + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad, nullptr);
     expand_windows_kernel<<<(n_pos + 255) / 256, 256>>>(d_pk, d_bad, n_pos, d_f, d_r, d_v);
     CK(cudaGetLastError());
     CK(cudaMemcpy(fwd, d_f, (size_t)len * 8, cudaMemcpyDeviceToHost));
@@ -2325,22 +2482,21 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     if (!db || !off || !results || (!hits && n_reads && off[n_reads])) { utb_set_error("utb_vote_hits: null argument"); return UTB_ERR_ARG; }
     if (!n_reads) return UTB_OK;
     CK(cudaSetDevice(db->device));
-    size_t nh = off[n_reads], nl = db->d.max_ix ? db->d.max_ix : 1;
-    uint32_t *d_hits, *d_gl, *d_gc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
+    size_t nh = off[n_reads];
+    uint32_t *d_hits, *d_gl, *d_gc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt; vote_scratch vs;
     CK(cudaMalloc(&d_hits, (nh + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
     CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
-    CK(cudaMalloc(&d_hist, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)db->sm_count * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)db->sm_count * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
+    { int rv = vs_alloc(db, (size_t)nh / 2 + 1, &vs); if (rv) return rv; }
+    CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     if (nh) CK(cudaMemcpy(d_hits, hits, nh * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = nullptr;
     vote_warp_kernel<<<(unsigned)((n_reads + VW_WARPS - 1) / VW_WARPS), VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, nullptr, nullptr, d_res, d_gl, d_gc, d_cnt);
-    vote_block_kernel<<<(unsigned)db->sm_count, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
-    CK(cudaGetLastError());
+    { int rv = launch_long_vote(db, in, d_res, d_gl, d_gc, &vs, d_cnt, 0); if (rv) return rv; }
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
     cudaFree(d_hits); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_cnt);
-    cudaFree(d_hist); cudaFree(d_tl); cudaFree(d_tc);
+    vs_free(&vs);
     return UTB_OK;
 }
 
@@ -2365,14 +2521,13 @@ extern "C" int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint
             ph[poff[r] + i] = h;
             if (h < HIT_NOWIN) pm[(poff[r] + i) >> 5] |= 1u << ((poff[r] + i) & 31u);
         }
-    const size_t nl = db->d.max_ix ? db->d.max_ix : 1;
-    uint32_t *d_hits, *d_map, *d_gl, *d_gc, *d_wl, *d_wc, *d_hist, *d_tl, *d_tc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt;
+    uint32_t *d_hits, *d_map, *d_gl, *d_gc, *d_wl, *d_wc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt; vote_scratch vs;
     CK(cudaMalloc(&d_hits, (tot + 32) * 4)); CK(cudaMalloc(&d_map, (tot / 32 + 2) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
     CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_wl, n_reads * 4)); CK(cudaMalloc(&d_wc, 4));
     CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
-    CK(cudaMalloc(&d_hist, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tl, (size_t)db->sm_count * nl * 4)); CK(cudaMalloc(&d_tc, (size_t)db->sm_count * nl * 4));
-    CK(cudaMemset(d_hist, 0, (size_t)db->sm_count * nl * 4)); CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
+    { int rv = vs_alloc(db, (size_t)tot / 2 + 1, &vs); if (rv) return rv; }
+    CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
     CK(cudaMemcpy(d_hits, ph, (tot + 32) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_map, pm, (tot / 32 + 2) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, poff, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
@@ -2380,11 +2535,10 @@ extern "C" int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint
     VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = d_map;
     vote_thread_kernel<<<(unsigned)((n_reads + VT_THREADS - 1) / VT_THREADS), VT_THREADS>>>(db->d, in, (uint32_t)n_reads, nullptr, d_res, d_wl, d_wc, d_cnt);
     vote_warp_kernel<<<(unsigned)db->sm_count * 6, VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, d_wl, d_wc, d_res, d_gl, d_gc, d_cnt);
-    vote_block_kernel<<<(unsigned)db->sm_count, VB_THREADS>>>(db->d, in, d_res, d_gl, d_gc, d_hist, d_tl, d_tc, d_cnt);
-    CK(cudaGetLastError());
+    { int rv = launch_long_vote(db, in, d_res, d_gl, d_gc, &vs, d_cnt, 0); if (rv) return rv; }
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
     cudaFree(d_hits); cudaFree(d_map); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_wl); cudaFree(d_wc);
-    cudaFree(d_cnt); cudaFree(d_hist); cudaFree(d_tl); cudaFree(d_tc);
+    cudaFree(d_cnt); vs_free(&vs);
     return UTB_OK;
 }
 
