@@ -128,6 +128,28 @@ def test_cli_usage_and_db_errors(built, tmp_path):
                        "Searching at speed 0.", "Using up to 1 threads.", "Invalid DB file"]
 
 
+@pytest.mark.parametrize("keep", ["records", "index"])
+def test_cli_truncated_tree_prints_the_banner_and_exits_3(built, ctrs, tmp_path, keep):
+    """A CTR cut inside its records / inside its prefix index: XT_read32 prints what it has read so far, then
+    "Error in reading tree." and exits 3 (itree.c:754-768).  Live against oracle/_ref when it is built."""
+    full = open(ctrs["toyA"], "rb").read()
+    n = int.from_bytes(full[24:32], "little")
+    cut = 32 + (2 ** 24 + 1) * 4 + (n // 2) * 7 + 3 if keep == "records" else 32 + 1_000_003
+    bad = str(tmp_path / "cut.ctr")
+    open(bad, "wb").write(full[:cut])
+    args = [bad, os.path.join(GOLD, "toyA_reads.fa"), str(tmp_path / "o.txt"), "1", "RC"]
+    p = subprocess.run([os.path.join(ROOT, "bin", "utree-search_gg")] + args, capture_output=True, text=True)
+    got_index = (cut - 32) // 4 if keep == "index" else 2 ** 24 + 1
+    assert p.returncode == 3
+    assert p.stdout.splitlines()[4:] == ["Using 32-bit counters", f"{got_index} elements read.",
+                                         f"Nodes in input tree: {n} (PACKSIZE=32, CNTTYPE=NA, IXTYPE=uint16_t, SZ=7)",
+                                         "Error in reading tree."]
+    ref = os.path.join(REFDIR, "utree-search_gg")
+    if os.path.exists(ref):
+        q = subprocess.run([ref] + args, capture_output=True, text=True)
+        assert (q.returncode, q.stdout) == (p.returncode, p.stdout)
+
+
 # ---- host logic: framer and formatter (no GPU) --------------------------------
 def _py_frame(data):
     """Reference reader restated in Python (itree.c:866-890); returns (records, error?)."""

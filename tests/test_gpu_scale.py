@@ -52,7 +52,7 @@ def test_l2_scale_and_l4_match_reference(bench_mod, tmp_path, config, n_reads):
     cfg = dict(bench_mod.CONFIGS[config])
     ctr_path, meta = bench_mod.ensure_ctr(config, cfg, 0)
     assert meta["records"] > (900_000_000 if config == "l2s" else 40_000_000)
-    reads = bench_mod.make_reads(cfg, 5_000_000, n_reads, 0)           # a window of the read stream the bench never uses
+    reads, _ = bench_mod.make_reads(cfg, 60_000_000, n_reads, 0)          # a window of the read stream the bench never uses
     fa = str(tmp_path / "r.fa")
     reads.tofile(fa)
     want = _ref_search(ctr_path, fa, str(tmp_path / "ref.out"))
@@ -60,6 +60,50 @@ def test_l2_scale_and_l4_match_reference(bench_mod, tmp_path, config, n_reads):
     assert got == want
     assert want.count(b"\n") > 0.9 * n_reads * (0.5 if config == "l4" else 1) * 0.5
     assert st["lookups"] > 200 * n_reads
+
+
+@need_ref
+def test_l2_scale_two_million_reads_every_batch_size(bench_mod, tmp_path):
+    """2 M reads against the L2-scale tree: full-size 128 MiB batches (the shape the bench's e2e leg runs) and the
+    ramp batches at both ends.  The reference runs with all host threads, so its lines come in any order
+    (SURVEY 0 #3): the two outputs must hold the same lines, ours in input order."""
+    cfg = dict(bench_mod.CONFIGS["l2s"])
+    ctr_path, _ = bench_mod.ensure_ctr("l2s", cfg, 0)
+    n_reads = 2_000_000
+    reads, _ = bench_mod.make_reads(cfg, 70_000_000, n_reads, 0)
+    fa = str(tmp_path / "r.fa")
+    reads.tofile(fa)
+    exe = os.path.join(REF, "utree-search_gg")
+    p = subprocess.run([exe, ctr_path, fa, str(tmp_path / "ref.out"), str(os.cpu_count() or 4), "RC"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert p.returncode == 0, p.stderr[-500:]
+    want = open(str(tmp_path / "ref.out"), "rb").read().split(b"\n")
+    got, st = _ours(ctr_path, reads.tobytes())
+    assert st["batches"] >= 4 and st["reads"] == n_reads
+    lines = got.split(b"\n")
+    assert sorted(lines) == sorted(want)
+    names = [ln.split(b"\t", 1)[0] for ln in lines if ln]
+    assert names == sorted(names) and len(names) > 0.9 * n_reads      # names are r%09u: input order = sorted
+
+
+def test_two_physical_gpus_one_searcher(bench_mod, tmp_path):
+    """ONE searcher over two physical devices (tables uploaded to the first, cloned to the second over NVLink,
+    batches dealt round-robin, ordered merge) gives the bytes of a single-device search."""
+    from utree_b200 import capi
+    if capi.device_count() < 2:
+        pytest.skip("one GPU visible")
+    cfg = dict(bench_mod.CONFIGS["small"])
+    ctr_path, _ = bench_mod.ensure_ctr("small", cfg, 0)
+    reads, _ = bench_mod.make_reads(cfg, 0, 1_500_000, 0)
+    data = reads.tobytes()
+    one, st1 = _ours(ctr_path, data)
+    ctr = capi.Ctr(ctr_path)
+    s = capi.Searcher(ctr, devices=(0, 1), host_threads=8)
+    try:
+        rc, ex, two, st2 = s.search_mem(data, do_rc=True)
+        assert rc == 0 and two == one and st2["reads"] == st1["reads"] and st2["batches"] >= 4
+    finally:
+        s.destroy(); ctr.close()
 
 
 @need_ref

@@ -376,6 +376,69 @@ extern "C" int uts_make_reads(int device, uint64_t seed, uint32_t n_phyla, uint3
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// long reads / whole-genome queries: variable-length records ">r%09u\n" + bases + "\n"
+// ---------------------------------------------------------------------------
+// One thread per output byte: the record of a byte is found by bisection over the record offsets.  A
+// read no longer than a genome is a window of one genome; a longer one (whole-genome queries up to the
+// 16,777,214-base limit) runs on through the following genomes.  Substitutions and strand as in reads_kernel.
+__global__ void __launch_bounds__(256)
+long_reads_kernel(Universe u, uint64_t rseed, uint64_t first, uint32_t n_reads, const uint64_t *__restrict__ off,
+                  const uint32_t *__restrict__ len, uint64_t b0, uint64_t b1, uint32_t sub_permille, char *__restrict__ out) {
+    const char A[4] = {'A', 'C', 'G', 'T'};
+    for (uint64_t i = b0 + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < b1; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_reads;                                // off[lo] <= i < off[hi]
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (off[mid] <= i) lo = mid; else hi = mid; }
+        const uint64_t local = i - off[lo], id = first + lo;
+        const uint32_t L = len[lo];
+        char c;
+        if (local == 0) c = '>';
+        else if (local == 1) c = 'r';
+        else if (local < 11) { uint64_t v = id; for (uint64_t k = 10; k > local; --k) v /= 10; c = (char)('0' + v % 10); }
+        else if (local == 11 || local == 12ull + L) c = '\n';
+        else {
+            const uint64_t j = local - 12, h = mix64(rseed ^ mix64(id));
+            const uint32_t g0 = (uint32_t)(h % u_genomes(u));
+            const uint64_t start = L <= u.genome_len ? (h >> 32) % (u.genome_len - L + 1) : 0;
+            const bool rc = (mix64(h) >> 7) & 1u;
+            const uint64_t src = rc ? L - 1 - j : j, p = start + src;
+            const uint64_t x = mix64(h + 0x1000 + src);
+            uint32_t b = base_of(u, (uint32_t)((g0 + p / u.genome_len) % u_genomes(u)), (uint32_t)(p % u.genome_len));
+            if (x % 1000u < sub_permille) b = (b + 1u + (uint32_t)((x >> 20) % 3u)) & 3u;
+            if (rc) b = 3u - b;
+            c = A[b];
+        }
+        out[i - b0] = c;
+    }
+}
+// Fills host buffer `out` (sum of 12 + len[r] + 1 bytes) with reads [first, first + n_reads) of the given lengths.
+extern "C" int uts_make_long_reads(int device, uint64_t seed, uint32_t n_phyla, uint32_t n_genera, uint32_t n_species,
+                                   uint32_t n_strains, uint32_t genome_len, uint64_t read_seed, uint64_t first,
+                                   uint32_t n_reads, const uint32_t *len, uint32_t sub_permille, char *out) {
+    Universe u{seed, n_phyla, n_genera, n_species, n_strains, genome_len};
+    if (!out || !len || !n_reads || first + n_reads > 999999999ull) { snprintf(g_err, sizeof g_err, "bad argument"); return 1; }
+    SCK(cudaSetDevice(device));
+    std::vector<uint64_t> off(n_reads + 1);
+    off[0] = 0;
+    for (uint32_t r = 0; r < n_reads; ++r) {
+        if (len[r] < 1 || len[r] > 16777214u) { snprintf(g_err, sizeof g_err, "read %u: bad length %u", r, len[r]); return 1; }
+        off[r + 1] = off[r] + 12ull + len[r] + 1ull;
+    }
+    const uint64_t total = off[n_reads], STEP = (uint64_t)256 << 20;
+    uint64_t *d_off; uint32_t *d_len; char *d;
+    SCK(cudaMalloc(&d_off, (n_reads + 1) * 8ull)); SCK(cudaMalloc(&d_len, n_reads * 4ull)); SCK(cudaMalloc(&d, STEP));
+    SCK(cudaMemcpy(d_off, off.data(), (n_reads + 1) * 8ull, cudaMemcpyHostToDevice));
+    SCK(cudaMemcpy(d_len, len, n_reads * 4ull, cudaMemcpyHostToDevice));
+    for (uint64_t o = 0; o < total; o += STEP) {
+        const uint64_t c = total - o < STEP ? total - o : STEP;
+        long_reads_kernel<<<148 * 16, 256>>>(u, read_seed, first, n_reads, d_off, d_len, o, o + c, sub_permille, d);
+        SCK(cudaGetLastError());
+        SCK(cudaMemcpy(out + o, d, c, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(d_off); cudaFree(d_len); cudaFree(d);
+    return 0;
+}
+
 // One genome as ASCII (for building toy trees with the reference builder and
 // for cross-checking base_of on the host).
 extern "C" void uts_genome_ascii(uint64_t seed, uint32_t n_phyla, uint32_t n_genera, uint32_t n_species,

@@ -22,6 +22,7 @@ def lib():
         L.uts_reads_bytes.restype = C.c_uint64
         L.uts_reads_bytes.argtypes = [C.c_uint64, C.c_uint32]
         L.uts_make_reads.argtypes = [C.c_int, C.c_uint64] + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint64, C.c_uint64] + [C.c_uint32] * 4 + [C.c_void_p]
+        L.uts_make_long_reads.argtypes = [C.c_int, C.c_uint64] + [C.c_uint32] * 5 + [C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
         L.uts_genome_ascii.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.c_void_p]
         L.uts_genome_ascii.restype = None
         L.uts_genome_tax.argtypes = [C.c_uint64] + [C.c_uint32] * 6 + [C.c_char_p, C.c_size_t]
@@ -63,6 +64,22 @@ class Universe:
         if rc:
             raise RuntimeError("uts_make_reads: " + lib().uts_last_error().decode())
         return out[:nb]
+
+    def make_long_reads(self, lengths, read_seed=7, first=0, sub_permille=10, device=0, out=None):
+        """Variable-length records '>r%09u\\n' + bases + '\\n' (long reads, whole-genome queries that run on through
+        the following genomes).  Returns (uint8 array, byte offsets of the records)."""
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        off = np.zeros(lengths.size + 1, dtype=np.uint64)
+        off[1:] = np.cumsum(lengths.astype(np.uint64) + 13)
+        nb = int(off[-1])
+        if out is None:
+            out = np.empty(nb, dtype=np.uint8)
+        assert out.size >= nb
+        rc = lib().uts_make_long_reads(device, *self._args(), read_seed, first, lengths.size, lengths.ctypes.data, sub_permille,
+                                       out.ctypes.data)
+        if rc:
+            raise RuntimeError("uts_make_long_reads: " + lib().uts_last_error().decode())
+        return out[:nb], off
 
     def genome_ascii(self, g):
         buf = np.empty(self.genome_len, dtype=np.uint8)

@@ -97,8 +97,6 @@ def lib():
         L.utb_vote_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
         L.utb_frame_records.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.c_size_t] + [C.c_void_p] * 4 + \
             [C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
-        L.utb_format_results.argtypes = [C.c_void_p, C.c_char_p] + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p, C.c_size_t,
-                                                                                       C.POINTER(C.c_size_t)]
         L.utb_searcher_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.utb_search_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(Stats), C.POINTER(C.c_int)]
         L.utb_search_mem.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p),
@@ -161,17 +159,22 @@ def count_newlines(buf: bytes, threads=1):
     return n.value, bool(z.value)
 
 
-def format_results(ctr, buf: bytes, name_off, name_len, results):
-    """Host formatter (utb_format_results) -> bytes."""
+def format_results(ctr, buf, name_off, name_len, results):
+    """Host formatter (utb_format_results) -> bytes.  buf: bytes or a uint8 numpy array holding the names."""
     results = np.ascontiguousarray(results, dtype=RESULT_DTYPE)
     name_off = np.ascontiguousarray(name_off, dtype=np.uint32)
     name_len = np.ascontiguousarray(name_len, dtype=np.uint32)
-    cap = len(buf) + results.size * 1024 + 64
-    out = C.create_string_buffer(cap)
+    src = np.frombuffer(buf, dtype=np.uint8) if isinstance(buf, (bytes, bytearray)) else np.ascontiguousarray(buf, dtype=np.uint8)
+    if not hasattr(ctr, "_max_label"):
+        ctr._max_label = max((len(ctr.label(i)) for i in range(ctr.max_ix)), default=0)
+    cap = int(name_len.sum()) + results.size * (ctr._max_label + 64) + 64
+    out = np.empty(cap, dtype=np.uint8)
     n = C.c_size_t()
-    _ck(lib().utb_format_results(ctr.h, buf, name_off.ctypes.data, name_len.ctypes.data, results.ctypes.data,
-                                 results.size, out, cap, C.byref(n)))
-    return out.raw[:n.value]
+    L = lib()
+    L.utb_format_results.argtypes = [C.c_void_p, C.c_void_p] + [C.c_void_p] * 3 + [C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+    _ck(L.utb_format_results(ctr.h, src.ctypes.data, name_off.ctypes.data, name_len.ctypes.data, results.ctypes.data,
+                             results.size, out.ctypes.data, cap, C.byref(n)))
+    return out[:n.value].tobytes()
 
 
 def compress_ubt(ubt_path, ctr_path):

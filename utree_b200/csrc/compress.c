@@ -26,6 +26,7 @@
 
 /* Returns UTB_OK; on failure the message is in utb_last_error().  *n_records / *n_labels
  * are optional outputs. */
+static __thread uint64_t g_count_sum;   /* sum of the label counts written by the last utb_compress_ubt on this thread */
 int utb_compress_ubt(const char *ubt_path, const char *ctr_path, uint64_t *n_records, uint32_t *n_labels) {
     if (!ubt_path || !ctr_path) { utb_set_error("utb_compress_ubt: null argument"); return UTB_ERR_ARG; }
     int fd = open(ubt_path, O_RDONLY);
@@ -92,7 +93,9 @@ int utb_compress_ubt(const char *ubt_path, const char *ctr_path, uint64_t *n_rec
         }
     }
     /* label tail: re-emitted through the label reader (itree.c:1270, 1311-1313): distinct labels in order
-     * of first appearance, each with its decimal count */
+     * of first appearance, each with its decimal count.  READ_ADD_SAMPLES stores the count of EVERY line
+     * into SampCnts[sampIX] (itree.c:1208-1209), sampIX being the label added last: a repeated label
+     * overwrites the count of whichever label is newest at that point. */
     {
         uint32_t labels = 0;
         size_t cap = 16, lines = 0;
@@ -100,28 +103,36 @@ int utb_compress_ubt(const char *ubt_path, const char *ctr_path, uint64_t *n_rec
         while (cap < 2 * (lines + 1) + 2) cap <<= 1;
         const char **seen = (const char **)calloc(cap, sizeof(char *));
         size_t *seen_len = (size_t *)calloc(cap, sizeof(size_t));
-        if (!seen || !seen_len) { free(seen); free(seen_len); utb_set_error("out of memory"); rc = UTB_ERR_NOMEM; goto done; }
+        const char **lab = (const char **)malloc((lines + 2) * sizeof(char *));
+        size_t *lab_len = (size_t *)malloc((lines + 2) * sizeof(size_t));
+        unsigned long long *lab_cnt = (unsigned long long *)malloc((lines + 2) * sizeof(unsigned long long));
+#define FREE_LABELS() do { free(seen); free(seen_len); free(lab); free(lab_len); free(lab_cnt); } while (0)
+        if (!seen || !seen_len || !lab || !lab_len || !lab_cnt) { FREE_LABELS(); utb_set_error("out of memory"); rc = UTB_ERR_NOMEM; goto done; }
         for (const char *p = (const char *)tail, *e = p + tail_len; p < e;) {
             const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
             size_t ll = nl ? (size_t)(nl - p) : (size_t)(e - p);
             const char *tb = (const char *)memchr(p, '\t', ll);
-            if (!tb) { free(seen); free(seen_len); utb_set_error("label line %u has no tab", labels); rc = UTB_ERR_FORMAT; goto done; }
+            if (!tb) { FREE_LABELS(); utb_set_error("label line %u has no tab", labels); rc = UTB_ERR_FORMAT; goto done; }
             size_t len = (size_t)(tb - p);
             uint64_t h = 1469598103934665603ull;
             for (size_t k = 0; k < len; ++k) { h ^= (uint8_t)p[k]; h *= 1099511628211ull; }
             size_t s = (size_t)h & (cap - 1);
             int dup = 0;
             while (seen[s]) { if (seen_len[s] == len && !memcmp(seen[s], p, len)) { dup = 1; break; } s = (s + 1) & (cap - 1); }
-            if (!dup) {
-                seen[s] = p; seen_len[s] = len; ++labels;
-                unsigned long long cnt = strtoull(tb + 1, NULL, 10);           /* atol + %llu round trip */
-                if (fwrite(p, 1, len, fo) != len || fprintf(fo, "\t%llu\n", cnt) < 0) { free(seen); free(seen_len); rc = UTB_ERR_IO; goto werr; }
-            }
+            if (!dup) { seen[s] = p; seen_len[s] = len; lab[labels] = p; lab_len[labels] = len; ++labels; }
+            lab_cnt[labels - 1] = strtoull(tb + 1, NULL, 10);      /* atol + %llu round trip */
             if (!nl) break;
             p = nl + 1;
         }
-        free(seen); free(seen_len);
+        uint64_t total = 0;
+        for (uint32_t i = 0; i < labels; ++i) {
+            total += lab_cnt[i];
+            if (fwrite(lab[i], 1, lab_len[i], fo) != lab_len[i] || fprintf(fo, "\t%llu\n", lab_cnt[i]) < 0) { FREE_LABELS(); rc = UTB_ERR_IO; goto werr; }
+        }
+        FREE_LABELS();
+#undef FREE_LABELS
         if (n_labels) *n_labels = labels;
+        g_count_sum = total;
     }
     if (n_records) *n_records = n;
     goto done;
@@ -153,6 +164,7 @@ int utb_compress_main(int argc, char **argv) {
     }
     int rc = utb_compress_ubt(argv[1], argv[2], &n, &labels);
     if (rc) { puts(utb_last_error()); return 0; }                  /* the reference exits 0 on every error here */
-    printf("Total nodes in tree: %llu [%llu labels]\n", (unsigned long long)n, (unsigned long long)labels);
+    (void)n;
+    printf("Total nodes in tree: %llu [%llu labels]\n", (unsigned long long)g_count_sum, (unsigned long long)labels);   /* itree.c:1310-1314: the sum of the label counts */
     return 0;
 }

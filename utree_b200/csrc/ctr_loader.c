@@ -146,6 +146,22 @@ int utb_ctr_open(const char *path, utb_ctr **out) {
     return UTB_OK;
 }
 
+/* What XT_read32 prints before it gives up on a truncated tree (itree.c:754-768): the header fields and the
+ * number of prefix-index entries its fread loop got.  Returns 0 when the header itself is readable and valid. */
+int utb_ctr_probe(const char *path, uint64_t md[4], uint64_t *binix_read) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return -1;
+    int ok = fread(md, 8, 4, f) == 4 && md[3] && md[0] == 8 && md[1] == 0 && (md[2] == 2 || md[2] == 4);
+    if (ok) {
+        struct stat st;
+        const uint64_t e = md[3] < 0xFFFFFFFFull ? 4 : 8;
+        uint64_t got = !fstat(fileno(f), &st) && st.st_size > 32 ? ((uint64_t)st.st_size - 32) / e : 0;
+        *binix_read = got < UTB_NUMBINS ? got : UTB_NUMBINS;
+    }
+    fclose(f);
+    return ok ? 0 : -1;
+}
+
 void utb_ctr_close(utb_ctr *c) {
     if (!c) return;
     if (c->map) munmap(c->map, c->map_len);

@@ -33,6 +33,7 @@
 #include <unistd.h>
 
 int utb_batch_last_ms(utb_batch *b, float ms[4]);
+int utb_ctr_probe(const char *path, uint64_t md[4], uint64_t *binix_read);
 int utb_batch_submit_ex(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
 int utb_host_ptr_is_pinned(const void *p);
 uint64_t utb_batch_launches(const utb_batch *b);
@@ -1111,6 +1112,18 @@ int utb_main(int argc, char **argv) {
 
     utb_ctr *ctr = NULL;
     int rc = utb_ctr_open(argv[1], &ctr);
+    if (rc == UTB_ERR_FORMAT && !strcmp(utb_last_error(), "Error in reading tree.")) {
+        /* truncated tree: XT_read32 prints what it has got so far, then the message, and exits 3 (itree.c:754-768) */
+        uint64_t md[4], got = 0;
+        if (!utb_ctr_probe(argv[1], md, &got)) {
+            puts(md[3] < 0xFFFFFFFFull ? "Using 32-bit counters" : "Holey smokes, a tree of over 4 billion k-mers. Here goes...");
+            printf("%llu elements read.\n", (unsigned long long)got);
+            printf("Nodes in input tree: %llu (PACKSIZE=%u, CNTTYPE=%s, IXTYPE=%s, SZ=%d)\n", (unsigned long long)md[3], 32u, "NA",
+                   TYPEARR[md[2]], (int)(5 + md[2]));
+        }
+        puts("Error in reading tree.");
+        return 3;
+    }
     if (rc) { puts(utb_last_error()); return 0; }                  /* itree.c:735, 738, 750: exit(0) */
     if (ctr->num_nodes < 0xFFFFFFFFull) puts("Using 32-bit counters");   /* itree.c:754-755 */
     else puts("Holey smokes, a tree of over 4 billion k-mers. Here goes...");
