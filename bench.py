@@ -68,7 +68,7 @@ CONFIGS = {
                   desc="small synthetic CTR (108 genomes x 0.4 Mb, complevel 2) vs 400k x 150bp reads, RC"),
 }
 SEED = 20260101
-CHUNK_BYTES = 3_400_000_000          # raw bytes of one resident batch (positions must fit 32 bits)
+CHUNK_BYTES = 1_900_000_000          # raw bytes of one resident batch (positions x 2 strands must fit 32 bits)
 
 
 def log(*a):
@@ -268,10 +268,12 @@ def chunks_of(off, limit=CHUNK_BYTES, max_reads=10_000_000):
 
 def cli_run(exe, ctr_path, fasta, out, threads):
     t = time.time()
-    p = subprocess.run([exe, ctr_path, fasta, out, str(threads), "RC"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    p = subprocess.run([exe, ctr_path, fasta, out, str(threads), "RC"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                       env=dict(os.environ, UTB_STATS="1"))
     dt = time.time() - t
     if p.returncode:
         raise RuntimeError(f"{exe} exited {p.returncode}: {p.stderr[-300:]}")
+    log(f"cli {os.path.basename(fasta)}: wall {dt:.2f} s | " + " | ".join(p.stderr.strip().splitlines()[-2:]))
     return dt
 
 

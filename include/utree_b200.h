@@ -218,6 +218,17 @@ void utb_free(void *p);
  * stdout banner, exit codes.  Returns the process exit code. */
 int utb_main(int argc, char **argv);
 
+/* ---- the non-GG search binary (utree-search, itree.c with -D SEARCH) ---- */
+/* Same loader, packing and lookups; the slide skips PACKSIZE/SPARSITY - 1 = 7
+ * windows after every hit (itree.c:948-951) and the vote is the shallow top-2
+ * plurality of itree.c:969-1007 with its 4-column "%f" line.  That vote is
+ * single-threaded in the reference and reads one entry past the hit list of
+ * a read (itree.c:982), i.e. depends on the reads before it: the device looks
+ * up and selects, the formatter thread votes read by read.  Call before the
+ * first search; utb_search_file / utb_search_mem then produce that output. */
+int utb_searcher_set_shallow(utb_searcher *s, int on);
+int utb_main_shallow(int argc, char **argv);
+
 /* ---- utree-compress equivalent (XT_cmp32, itree.c:1234-1315) -- */
 /* .ubt -> .ctr, byte-identical to the reference compressor (first-bin quirk
  * included).  Host only. */

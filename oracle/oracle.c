@@ -220,10 +220,10 @@ int orc_pack_word(const char *b, uint64_t *out) {
 /* itree.c:887-898 + 906-933.  Bytes >= 0x80 index C2Xb/RC with a negative
  * char in the reference (UB); scope is 7-bit input and they are treated as
  * non-ACGT here. */
-uint64_t orc_slide(const OrcDB *db, const char *seq, uint32_t len0, int do_rc,
-                   uint32_t *hits, uint64_t cap,
-                   uint64_t *words, uint64_t cap_words, uint64_t *n_words,
-                   OrcStats *st) {
+static uint64_t slide_impl(const OrcDB *db, const char *seq, uint32_t len0, int do_rc,
+                           uint32_t *hits, uint64_t cap,
+                           uint64_t *words, uint64_t cap_words, uint64_t *n_words,
+                           OrcStats *st, int skip) {
     init_tables();
     char *buf = NULL; const char *src = seq; int length = (int)len0;
     if (do_rc) {                                                        /* :891-897 */
@@ -256,11 +256,22 @@ uint64_t orc_slide(const OrcDB *db, const char *seq, uint32_t len0, int do_rc,
             if (hits && found < cap) hits[found] = ix;
             ++found;
             if (st) st->hits++;
+            i += skip;                                                  /* XT_SHALLOWVOTE :950: PACKSIZE/SPARSITY - 1 (0 for the GG vote) */
         }
     }
     if (n_words) *n_words = nw;
     free(buf);
     return found;
+}
+uint64_t orc_slide(const OrcDB *db, const char *seq, uint32_t len0, int do_rc,
+                   uint32_t *hits, uint64_t cap,
+                   uint64_t *words, uint64_t cap_words, uint64_t *n_words,
+                   OrcStats *st) {
+    return slide_impl(db, seq, len0, do_rc, hits, cap, words, cap_words, n_words, st, 0);
+}
+/* the non-GG binary (-D SEARCH): after a hit the next window looked up ends 8 bases on */
+uint64_t orc_slide_shallow(const OrcDB *db, const char *seq, uint32_t len0, int do_rc, uint32_t *hits, uint64_t cap, OrcStats *st) {
+    return slide_impl(db, seq, len0, do_rc, hits, cap, NULL, 0, NULL, st, ORC_SHALLOW_SKIP);
 }
 
 /* ---- vote: itree.c:1028-1098 --------------------------------------------- */
@@ -436,6 +447,63 @@ int orc_search_file(const OrcDB *db, const char *fasta, const char *out,
     tot.reads = li;
     if (stats) *stats = tot;
     free(recs); free(outs); free(outn); free(line); free(line2);
+    fclose(fp); fclose(fo);
+    return rc;
+}
+
+/* ---- the non-GG search binary (-D SEARCH): itree.c:860-901 reader, :903-933 slide with the SPARSITY
+ * skip (:948-951), shallow vote :969-1007.  Single-threaded in the reference (no omp parallel around it),
+ * and order matters: AllTheKingsHorses is allocated once (:970) and `if (!kingsMen++)` (:982) both
+ * never fires (kingsMen == foundUniq >= 1 there) and bumps the count, so the tally loops (:984-997)
+ * run over foundUniq + 1 entries -- the last one is whatever an EARLIER read left at that index of
+ * the array (0 from the fresh allocation if none did). */
+int orc_search_file_shallow(const OrcDB *db, const char *fasta, const char *out, int do_rc,
+                            OrcStats *stats, char *err, size_t errlen) {
+    init_tables();
+    FILE *fp = fopen(fasta, "rb");
+    if (!fp) { seterr(err, errlen, "Invalid input files"); return 1; }  /* :835 */
+    FILE *fo = fopen(out, "wb");
+    if (!fo) { fclose(fp); seterr(err, errlen, "cannot open output"); return 1; }
+    char *line = (char *)malloc((size_t)LINELEN + 2), *line2 = (char *)malloc((size_t)LINELEN + 2);
+    uint32_t *horses = (uint32_t *)calloc((size_t)LINELEN * 2, sizeof(uint32_t));    /* :970 (fresh pages read as 0) */
+    uint32_t *tally = (uint32_t *)calloc(db->max_ix ? db->max_ix : 1, sizeof(uint32_t));   /* :971 Hashes */
+    OrcStats tot; memset(&tot, 0, sizeof(tot));
+    uint64_t li = 0; int rc = 0;
+    for (;;) {
+        if (!fgets(line, LINELEN, fp)) break;                           /* :869 */
+        if (!fgets(line2, LINELEN, fp)) {                                /* :871-872 */
+            char m[96]; snprintf(m, sizeof m, "ERROR: can't read sequence L %u", (unsigned)li);
+            seterr(err, errlen, m); rc = 2; break;
+        }
+        ++li;
+        if (line[0] != '>') { seterr(err, errlen, "ERROR: no header '>'"); rc = 2; break; }
+        char *src = line;
+        while (*++src && *src != ' ' && *src != '\n');
+        *src = 0;
+        if (line2[0] == '>') { seterr(err, errlen, "ERROR: sequence begins '>'"); rc = 2; break; }
+        int length = (int)strlen(line2);
+        if (!length) { seterr(err, errlen, "ERROR: empty query line"); rc = 2; break; }
+        if (line2[length - 1] == '\n') --length;
+        if (length > 0 && line2[length - 1] == '\r') --length;
+        const uint64_t n = orc_slide_shallow(db, line2, (uint32_t)length, do_rc, horses, (uint64_t)LINELEN * 2, &tot);   /* :976-978 */
+        if (!n) continue;                                               /* :979 */
+        ++tot.good_finds;                                               /* :980 */
+        const uint64_t men = n + 1;                                     /* :982: kingsMen++ */
+        for (uint64_t i = 0; i < men; ++i) ++tally[horses[i]];          /* :984-985 */
+        uint32_t most = 0, second = 0, most_ix = 0;
+        for (uint64_t i = 0; i < men; ++i) {                            /* :988-997 */
+            const uint32_t h = tally[horses[i]];
+            if (h > most) { second = most; most_ix = horses[i]; most = h; }
+            else if (h > second) second = h;
+            tally[horses[i]] = 0;
+        }
+        if (most < 2 || most < 2 * second) --tot.good_finds;            /* :1000: TOLERANCE_THRESHOLD 2, SLACK 2 */
+        else tot.out_bytes += (uint64_t)fprintf(fo, "%s\t%s\t%f\t%d\n", line + 1, db->labels[most_ix],
+                                                (double)1 - (double)second / most, (int)most);   /* :1002 */
+    }
+    tot.reads = li;
+    if (stats) *stats = tot;
+    free(line); free(line2); free(horses); free(tally);
     fclose(fp); fclose(fo);
     return rc;
 }

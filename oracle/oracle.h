@@ -6,10 +6,11 @@
  *
  * Parity status: the reference ships no tests or golden vectors
  * (SURVEY.md 4.1), so this oracle is pinned by EXECUTING the reference:
- * tests/test_oracle_vs_ref.py diffs its output byte-for-byte against
- * oracle/_ref/utree-search_gg (built from /root/reference/itree.c by
- * oracle/Makefile) and against the committed fixtures in tests/golden/ that
- * were produced by that same binary (scripts/make_golden.py).
+ * tests/test_oracle_golden.py diffs its output byte-for-byte against the
+ * committed fixtures in tests/golden/ that were produced by
+ * oracle/_ref/utree-search_gg and oracle/_ref/utree-search (built from
+ * /root/reference/itree.c by oracle/Makefile; scripts/make_golden*.py), and
+ * tests/test_gpu_scale.py runs those binaries live beside the CUDA path.
  *
  * Every function cites the reference lines it restates (file itree.c).
  */
@@ -89,6 +90,15 @@ size_t orc_format(const OrcDB *db, const char *name, const OrcVote *v, char *buf
 int orc_search_file(const OrcDB *db, const char *fasta, const char *out,
                     int do_rc, int threads, uint64_t max_reads,
                     OrcStats *st, char *err, size_t errlen);
+
+/* The non-GG binary (-D SEARCH, itree.c:948-951, 969-1007): the slide skips
+ * PACKSIZE/SPARSITY - 1 windows after a hit, the vote is a top-2 plurality
+ * over the hits plus one stale entry left by an earlier read; sequential. */
+#define ORC_SHALLOW_SKIP 7
+uint64_t orc_slide_shallow(const OrcDB *db, const char *seq, uint32_t len, int do_rc,
+                           uint32_t *hits, uint64_t cap, OrcStats *st);
+int orc_search_file_shallow(const OrcDB *db, const char *fasta, const char *out, int do_rc,
+                            OrcStats *st, char *err, size_t errlen);
 
 /* helpers exported for unit tests */
 uint64_t orc_revcomp_word(uint64_t w);                 /* rc of a 32-mer word */

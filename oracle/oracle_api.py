@@ -47,6 +47,7 @@ def oracle():
         O.orc_vote.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(OrcVote)]
         O.orc_search_file.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_uint64,
                                       C.POINTER(OrcStats), C.c_char_p, C.c_size_t]
+        O.orc_search_file_shallow.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(OrcStats), C.c_char_p, C.c_size_t]
         O.orc_revcomp_word.restype = C.c_uint64
         O.orc_revcomp_word.argtypes = [C.c_uint64]
         _orc = O
@@ -91,6 +92,13 @@ class OracleDb:
         err = C.create_string_buffer(256)
         rc = oracle().orc_search_file(self.h, os.fsencode(fasta), os.fsencode(out), int(do_rc), threads,
                                       max_reads, C.byref(st), err, 256)
+        return rc, st.as_dict(), err.value.decode()
+
+    def search_file_shallow(self, fasta, out, do_rc=True):
+        """The non-GG binary (-D SEARCH): SPARSITY-skip slide + shallow top-2 vote, sequential."""
+        st = OrcStats()
+        err = C.create_string_buffer(256)
+        rc = oracle().orc_search_file_shallow(self.h, os.fsencode(fasta), os.fsencode(out), int(do_rc), C.byref(st), err, 256)
         return rc, st.as_dict(), err.value.decode()
 
     def free(self):

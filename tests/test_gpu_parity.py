@@ -496,3 +496,75 @@ def test_cli_reads_fasta_from_a_pipe(ctrs, tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert q.returncode == 0, q.stderr
     assert open(o, "rb").read() == open(gold("toyB_u32_rc.out"), "rb").read()
+
+
+# ---- the non-GG binary (utree-search, -D SEARCH): SPARSITY-skip slide + shallow vote --------------
+import json as _json
+SHALLOW = _json.load(open(os.path.join(conftest.GOLD, "meta_shallow.json")))
+
+
+@pytest.mark.parametrize("name", sorted(SHALLOW))
+def test_shallow_search_matches_the_reference_binary(ctrs, tmp_path, name):
+    """utb_searcher_set_shallow: the bytes oracle/_ref/utree-search wrote for the same tree and reads (golden files made
+    by scripts/make_golden_shallow.py), "Good finds" and "Searched" included.  The vote of a read depends on the reads
+    before it (itree.c:982), so equality here also pins the input order through the batches."""
+    from utree_b200 import capi
+    m = SHALLOW[name]
+    ctr = capi.Ctr(ctrs[m["db"]])
+    s = capi.Searcher(ctr, devices=(0,), host_threads=3)
+    try:
+        s.set_shallow(True)
+        out = str(tmp_path / "o.out")
+        rc, ex, st = s.search_file(gold(m["reads"]), out, do_rc=bool(m["rc"]))
+        assert rc == 0 and open(out, "rb").read() == open(gold(name), "rb").read()
+        assert [f"Good finds: {st['good_finds']}", f"Searched {st['reads']} queries"] == m["stdout_tail"]
+        # memory API, twice: every search starts from a clean AllTheKingsHorses, like a fresh process
+        for _ in range(2):
+            rc, ex, text, st = s.search_mem(open(gold(m["reads"]), "rb").read(), do_rc=bool(m["rc"]))
+            assert rc == 0 and text == open(gold(name), "rb").read()
+    finally:
+        s.destroy(); ctr.close()
+
+
+@pytest.mark.parametrize("env", [{}, {"UTB_HOST_FRAME": "1"}, {"UTB_SIEVE": "0"}, {"UTB_LOOKUP": "exact"}])
+def test_shallow_search_across_batches_and_lookup_variants(gpu, tmp_path, env):
+    """Several batches (the stale entry of itree.c:982 crosses batch boundaries), device- and host-framed, with the
+    sieve off (dense hit slots instead of the hit map) and with the reference probe sequence: the CPU checker's
+    restatement of the non-GG binary (itself pinned by the golden files) gives the expected bytes."""
+    from utree_b200 import capi
+    ctr, db, orc = gpu["toyA"]
+    data = (open(gold("shallow_reads.fa"), "rb").read() + open(gold("toyA_reads.fa"), "rb").read() + open(gold("long_reads.fa"), "rb").read()) * 40
+    fa, want = str(tmp_path / "in.fa"), str(tmp_path / "want.out")
+    open(fa, "wb").write(data)
+    rc, st, err = orc.search_file_shallow(fa, want, do_rc=True)
+    assert rc == 0, err
+    os.environ.update(env)
+    os.environ["UTB_BATCH_MB"] = "33"
+    try:
+        s = capi.Searcher(ctr, devices=(0, 0), host_threads=4)
+        s.set_shallow(True)
+    finally:
+        for k in list(env) + ["UTB_BATCH_MB"]:
+            del os.environ[k]
+    try:
+        rc, ex, text, st2 = s.search_mem(data, do_rc=True)
+        assert rc == 0 and st2["batches"] >= 2 and text == open(want, "rb").read()
+        assert (st2["good_finds"], st2["reads"]) == (st["good_finds"], st["reads"])
+    finally:
+        s.destroy()
+
+
+def test_shallow_cli_binary(ctrs, tmp_path):
+    """bin/utree-search: argv, banner and output of the reference's non-GG binary."""
+    exe = os.path.join(ROOT, "bin", "utree-search")
+    p = subprocess.run([exe], capture_output=True, text=True)
+    assert p.returncode == 1 and "usage: xtree-search compTree.ctr" in p.stdout
+    out = str(tmp_path / "o.out")
+    p = subprocess.run([exe, ctrs["toyA"], gold("toyA_reads.fa"), out, "2", "RC"], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+    assert open(out, "rb").read() == open(gold("shallow_toyA_toyA_rc.out"), "rb").read()
+    assert p.stdout.splitlines()[-2:] == SHALLOW["shallow_toyA_toyA_rc.out"]["stdout_tail"]
+    ref = os.path.join(ROOT, "oracle", "_ref", "utree-search")
+    if os.path.exists(ref):
+        q = subprocess.run([ref, ctrs["toyA"], gold("toyA_reads.fa"), out + ".ref", "2", "RC"], capture_output=True, text=True)
+        assert q.stdout == p.stdout

@@ -1,5 +1,6 @@
 """The oracle (oracle/oracle.c) against the golden outputs produced by the
 reference binary, and its unit-level pieces.  CPU only."""
+import json
 import os
 
 import numpy as np
@@ -7,7 +8,7 @@ import pytest
 
 import conftest  # noqa: F401  (puts the repo root on sys.path)
 from oracle import oracle_api
-from conftest import BAD_CASES, CASES, gold, read_fasta
+from conftest import BAD_CASES, CASES, GOLD, gold, read_fasta
 
 
 @pytest.fixture(scope="module")
@@ -117,3 +118,22 @@ def test_vote_branches(orcs):
     v = orc.vote(np.array([a] * 5 + [b] * 5, dtype=np.uint32))
     assert v.kind == 2 and v.uix == 2 and (v.sl, v.ol) == (5, 10)      # the failing level is reported (App. D #8)
     assert orc.label(v.label)[:v.cut] == b"k__Bacteria"
+
+
+# ---- the non-GG binary (-D SEARCH): SPARSITY-skip slide + shallow top-2 vote ------------------------
+SHALLOW = json.load(open(os.path.join(GOLD, "meta_shallow.json")))
+
+
+@pytest.mark.parametrize("name", sorted(SHALLOW))
+def test_oracle_shallow_search_reproduces_the_reference(ctrs, tmp_path, name):
+    """oracle/_ref/utree-search (itree.c with -D SEARCH) produced these files (scripts/make_golden_shallow.py); the
+    restatement must give the same bytes and the same "Good finds" / "Searched" counts.  The vote of a read depends on
+    the reads before it (itree.c:982 reads one entry past the hit list), so this also pins the order dependence."""
+    m = SHALLOW[name]
+    orc = oracle_api.OracleDb(ctrs[m["db"]])
+    out = str(tmp_path / "o.out")
+    rc, st, err = orc.search_file_shallow(os.path.join(GOLD, m["reads"]), out, do_rc=bool(m["rc"]))
+    orc.free()
+    assert rc == m["exit"], err
+    assert open(out, "rb").read() == open(os.path.join(GOLD, name), "rb").read()
+    assert [f"Good finds: {st['good_finds']}", f"Searched {st['reads']} queries"] == m["stdout_tail"]

@@ -41,7 +41,7 @@ def _newer(target, sources):
 
 
 def build(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in C_SOURCES + ["kernels.cu", "utb_internal.h", "main.c", "compress_main.c"]]
+    srcs = [os.path.join(CSRC, f) for f in C_SOURCES + ["kernels.cu", "utb_internal.h", "main.c", "main_shallow.c", "compress_main.c"]]
     srcs.append(os.path.join(ROOT, "include", "utree_b200.h"))
     exe = os.path.join(BIN, "utree-search_gg")
     if not force and _newer(LIB, srcs) and _newer(exe, srcs):
@@ -63,6 +63,8 @@ def build(force=False, verbose=False):
                             "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
     shutil.copyfile(exe, os.path.join(BIN, "utree-searchGG"))
     os.chmod(os.path.join(BIN, "utree-searchGG"), 0o755)
+    _run([GCC] + C_FLAGS + [os.path.join(CSRC, "main_shallow.c"), "-o", os.path.join(BIN, "utree-search"), "-L" + CSRC, "-lutree_b200",
+                            "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
     _run([GCC] + C_FLAGS + [os.path.join(CSRC, "compress_main.c"), "-o", os.path.join(BIN, "utree-compress"), "-L" + CSRC,
                             "-lutree_b200", "-Wl,-rpath,$ORIGIN/../utree_b200/csrc"], log)
     with open(os.path.join(CSRC, "build.log"), "w") as f:

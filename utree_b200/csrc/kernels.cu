@@ -1272,6 +1272,65 @@ vote_big_finish_kernel(DevDB db, VoteLong vl, utb_result *__restrict__ results, 
 }
 
 // ---------------------------------------------------------------------------
+// the non-GG binary (-D SEARCH): which hits its slide would have met (itree.c:903-933 with XT_SHALLOWVOTE, :948-951)
+// ---------------------------------------------------------------------------
+// After a hit the reference's loop index jumps PACKSIZE / SPARSITY - 1 = 7 windows ahead, so the windows it
+// looks up depend on the hits before them -- but a lookup is a pure function, so looking up every window
+// (as the GG path does) and then walking the hits in text order, keeping a hit only if it lies 8 or more
+// windows past the last one kept, selects exactly the ids the reference appends to AllTheKingsHorses.  Text
+// order (itree.c:887-898): the forward windows left to right, then the windows of the reverse-complement
+// text, i.e. the reverse-strand slots right to left; the 'N' between the two halves resets the skip.
+// One thread per read; FILL = false counts (sel_cnt), FILL = true writes the ids at sel_off[r].
+#define SH_SKIP 8u
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+shallow_select_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ dims, uint32_t *__restrict__ sel_cnt,
+                      const uint32_t *__restrict__ sel_off, uint32_t *__restrict__ sel) {
+    if (dims) n_reads = dims[0];
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t start, count;
+        vote_range(in, (uint32_t)r, start, count);
+        const uint32_t nstr = in.nstr, nwin = (uint32_t)(count / nstr);
+        uint32_t n = 0;
+        uint32_t *out = FILL ? sel + sel_off[r] : nullptr;
+        for (uint32_t strand = 0; strand < nstr; ++strand) {
+            uint32_t next = 0;                                     // first text position of this half that may be kept
+            if (in.hitmap) {
+                const uint32_t *hm = in.hitmap + (start >> 5);     // start is a multiple of 32
+                const uint32_t nwords = (uint32_t)((count + 31) >> 5);
+                const uint32_t lanes = nstr == 2 ? (strand ? 0xAAAAAAAAu : 0x55555555u) : 0xFFFFFFFFu;
+                for (uint32_t k = 0; k < nwords; ++k) {
+                    const uint32_t w = strand ? nwords - 1 - k : k;
+                    uint32_t m = __ldg(hm + w) & lanes;
+                    while (m) {
+                        const uint32_t bit = strand ? 31u - __clz(m) : __ffs(m) - 1u;
+                        m &= ~(1u << bit);
+                        const uint32_t slot = 32u * w + bit, pos = slot / nstr;
+                        if (pos >= nwin) continue;
+                        const uint32_t tp = strand ? nwin - 1u - pos : pos;          // position in the text of this half
+                        if (tp < next) continue;
+                        const uint32_t h = __ldg(in.hits + start + slot);
+                        if (h >= db.max_ix) continue;
+                        if (FILL) out[n] = h;
+                        ++n; next = tp + SH_SKIP;
+                    }
+                }
+            } else {
+                for (uint32_t tp = 0; tp < nwin; ++tp) {
+                    if (tp < next) { tp = next - 1u; continue; }
+                    const uint32_t pos = strand ? nwin - 1u - tp : tp;
+                    const uint32_t h = __ldg(in.hits + start + (uint64_t)pos * nstr + strand);
+                    if (h >= db.max_ix) continue;
+                    if (FILL) out[n] = h;
+                    ++n; next = tp + SH_SKIP;
+                }
+            }
+        }
+        if (!FILL) sel_cnt[r] = n;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // output text on the device (the fprintf lines of itree.c:1032, 1040, 1096)
 // ---------------------------------------------------------------------------
 // The host formatter competes with the framer for a handful of cores (16 for
@@ -1909,7 +1968,7 @@ struct utb_batch {
     // pinned host
     char *h_bytes; uint64_t *h_seq_off; uint32_t *h_seq_len; uint32_t *h_grp_off;
     utb_result *h_results; unsigned long long *h_counters;
-    uint32_t *h_name_off, *h_name_len; char *h_text; uint32_t *h_text_len; size_t text_cap;   // device-side formatting
+    uint32_t *h_name_off, *h_name_len; char *h_text; uint32_t *h_text_len; size_t text_cap, h_text_cap;   // device-side formatting
     // device
     uint8_t *d_raw; uint64_t *d_seq_off; uint32_t *d_seq_len; uint32_t *d_grp_off;
     uint64_t *d_pk; uint32_t *d_bad; uint32_t *d_hits; uint64_t *d_pkr;
@@ -1918,6 +1977,7 @@ struct utb_batch {
     int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
     vote_scratch vs;
+    uint32_t *d_sel_cnt, *d_sel_off, *d_sel, *d_sel_total, *h_sel_cnt, *h_sel, *h_sel_total; size_t sel_cap;   // non-GG mode (want_text == 3)
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
     // last submit
@@ -1952,6 +2012,8 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results); cudaFree(b->d_pkr);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_warp_list); cudaFree(b->d_warp_count); cudaFree(b->d_counters);
     vs_free(&b->vs);
+    cudaFree(b->d_sel_cnt); cudaFree(b->d_sel_off); cudaFree(b->d_sel); cudaFree(b->d_sel_total);
+    cudaFreeHost(b->h_sel_cnt); cudaFreeHost(b->h_sel); cudaFreeHost(b->h_sel_total);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFreeHost(b->h_frame_err);
     cudaFree(b->d_frame_info); cudaFree(b->d_dims); cudaFreeHost(b->h_dims);
@@ -2098,7 +2160,20 @@ static int launch_stages(utb_batch *b, bool timed) {
         b->launches++;
     }
     if (timed) CK(cudaEventRecord(b->ev[2], b->st));
-    if (n_reads) {
+    if (n_reads && b->want_text == 3) {
+        // non-GG mode: no vote on the device (it depends on the order of the reads, itree.c:982); the ids the
+        // reference's skipping slide would have collected, per read, compacted: count -> scan -> fill
+        VoteIn in;
+        in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
+        in.hitmap = b->used_sieve ? b->d_hitmap : nullptr;
+        const uint32_t nt = (n_reads + SCAN_TILE - 1) / SCAN_TILE;
+        shallow_select_kernel<false><<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(d, in, n_reads, b->dims_dev, b->d_sel_cnt, nullptr, nullptr);
+        scan_sums_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_sel_cnt, n_reads, b->dims_dev, nt, b->d_scan_sums);
+        scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nt, b->d_sel_total);
+        scan_apply_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_sel_cnt, n_reads, b->dims_dev, nt, b->d_scan_sums, b->d_sel_off);
+        shallow_select_kernel<true><<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(d, in, n_reads, b->dims_dev, nullptr, b->d_sel_off, b->d_sel);
+        b->launches += 5;
+    } else if (n_reads) {
         VoteIn in;
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
         in.hitmap = b->used_sieve ? b->d_hitmap : nullptr;
@@ -2123,16 +2198,30 @@ static int launch_stages(utb_batch *b, bool timed) {
     return UTB_OK;
 }
 
-// text buffers are allocated on first use (the device-resident measurement batches never format)
+// Text buffers (the device-resident measurement batches never format): d_text holds the worst case (every read
+// prints its name and the longest label); the page-locked staging h_text is sized for the typical output
+// (about half the input) and grown on demand -- page-locking is the slow part (~0.25 s per GB).
 static int ensure_text_buffers(utb_batch *b) {
     if (b->d_text) return UTB_OK;
     size_t cap = b->max_bytes + b->max_reads * (b->db->max_label + 48) + 64;
     if (cap >= ((size_t)1 << 32)) { utb_set_error("batch too large for device-side formatting"); return UTB_ERR_LIMIT; }
+    const size_t hcap = b->max_bytes / 2 + ((size_t)8 << 20) < cap ? b->max_bytes / 2 + ((size_t)8 << 20) : cap;
     CK(cudaMalloc(&b->d_text, cap));
-    CK(cudaMallocHost(&b->h_text, cap));
-    b->text_cap = cap;
+    CK(cudaMallocHost(&b->h_text, hcap));
+    b->text_cap = cap; b->h_text_cap = hcap;
     return UTB_OK;
 }
+static int grow_text_staging(utb_batch *b, size_t need) {
+    if (need <= b->h_text_cap) return UTB_OK;
+    CK(cudaStreamSynchronize(b->st));
+    cudaFreeHost(b->h_text); b->h_text = nullptr; b->h_text_cap = 0;
+    CK(cudaMallocHost(&b->h_text, need));
+    b->h_text_cap = need;
+    return UTB_OK;
+}
+// Everything a searcher's batch will need, allocated up front (utb_searcher_create) instead of inside its first search.
+extern "C" int utb_batch_prepare(utb_batch *b, int want_text, int chunked);
+static int ensure_shallow_buffers(utb_batch *b);
 
 static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text, uint64_t total_groups);
 static int finish_submit(utb_batch *b, size_t n_bytes);
@@ -2181,10 +2270,17 @@ static int submit_impl(utb_batch *b, const char *src, size_t n_bytes, size_t n_r
         g += utb_read_slots(len);
     }
     if (g > b->max_groups) { utb_set_error("utb_batch_submit: %llu position groups exceed capacity %llu", (unsigned long long)g, (unsigned long long)b->max_groups); return UTB_ERR_LIMIT; }
+    if (g * 32ull * (do_rc ? 2u : 1u) >= 0xFFFFFFFFull) {          // a lookup slot (position x strand) is addressed with 32 bits
+        utb_set_error("utb_batch_submit: %llu positions x %d strands exceed the 32-bit slot space", (unsigned long long)(g * 32ull), do_rc ? 2 : 1);
+        return UTB_ERR_LIMIT;
+    }
     if (!total_groups) b->h_grp_off[n_reads] = (uint32_t)g;
     b->n_reads = n_reads; b->n_groups = (uint32_t)g; b->do_rc = do_rc ? 1 : 0;
     b->want_text = want_text; b->dims_dev = nullptr; b->framed_on_device = 0;
-    if (want_text) {
+    if (want_text == 3) {                                          // non-GG mode: the names stay with the host framer
+        int rt = ensure_shallow_buffers(b);
+        if (rt) return rt;
+    } else if (want_text) {
         int rt = ensure_text_buffers(b);
         if (rt) return rt;
         if (n_reads) {
@@ -2215,7 +2311,17 @@ static int finish_submit(utb_batch *b, size_t n_bytes) {
     const int want_text = b->want_text;
     int rc = launch_stages(b, true);
     if (rc) return rc;
-    if (want_text) {
+    if (want_text == 3) {
+        // per-read counts, the total, and (device-framed batches) where the names are; the id list follows in the wait
+        if (n_reads) {
+            CK(cudaMemcpyAsync(b->h_sel_cnt, b->d_sel_cnt, n_reads * 4, cudaMemcpyDeviceToHost, b->st));
+            if (b->dims_dev) {
+                CK(cudaMemcpyAsync(b->h_name_off, b->d_name_off, n_reads * 4, cudaMemcpyDeviceToHost, b->st));
+                CK(cudaMemcpyAsync(b->h_name_len, b->d_name_len, n_reads * 4, cudaMemcpyDeviceToHost, b->st));
+            }
+        }
+        CK(cudaMemcpyAsync(b->h_sel_total, b->d_sel_total, 4, cudaMemcpyDeviceToHost, b->st));
+    } else if (want_text) {
         // lines built on the device: lengths -> exclusive scan -> one warp per read writes its line
         const uint32_t n = (uint32_t)n_reads, nt = (n + SCAN_TILE - 1) / SCAN_TILE;
         CK(cudaMemsetAsync(b->d_text_len, 0, 4, b->st));
@@ -2236,7 +2342,7 @@ static int finish_submit(utb_batch *b, size_t n_bytes) {
             // common case), wait_text tops it up if it was short
             size_t est = (size_t)(b->db->text_per_byte * 1.15 * (double)n_bytes) + 4096;
             if (b->db->text_per_byte <= 0) est = 0;
-            if (est > b->text_cap) est = b->text_cap;
+            if (est > b->h_text_cap) est = b->h_text_cap;
             b->text_prefetched = est;
             if (est) CK(cudaMemcpyAsync(b->h_text, b->d_text, est, cudaMemcpyDeviceToHost, b->st));
         }
@@ -2255,27 +2361,52 @@ static int finish_submit(utb_batch *b, size_t n_bytes) {
 // the caller knows the record count it is only used as the upper bound the grids are sized for.
 // utb_batch_frame_error() tells after the wait whether the chunk or one of its records was malformed,
 // utb_batch_reads() how many records it held.
+static int ensure_chunk_buffers(utb_batch *b) {
+    if (b->d_nl) return UTB_OK;
+    void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaError_t e = cudaMalloc(&p[0], (2 * b->max_reads + 2) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p[1], (b->max_bytes / FR_BLOCK + 2) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p[2], 4);
+    if (e == cudaSuccess) e = cudaMalloc(&p[3], 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&p[4], 4);
+    if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) cudaFree(p[i]); cudaFreeHost(p[4]); CK(e); }
+    b->d_nl = (uint32_t *)p[0]; b->d_blk = (uint32_t *)p[1]; b->d_frame_err = (uint32_t *)p[2]; b->d_frame_info = (uint32_t *)p[3];
+    b->h_frame_err = (uint32_t *)p[4];
+    return UTB_OK;
+}
+static int ensure_shallow_buffers(utb_batch *b) {
+    if (b->d_sel) return UTB_OK;
+    // a read keeps at most one hit per 8 windows and strand (+ 1 each)
+    b->sel_cap = (size_t)b->max_groups * 32 / 4 + 2 * b->max_reads + 64;
+    CK(cudaMalloc(&b->d_sel_cnt, (b->max_reads + 1) * 4));
+    CK(cudaMalloc(&b->d_sel_off, (b->max_reads + 1) * 4));
+    CK(cudaMalloc(&b->d_sel, b->sel_cap * 4));
+    CK(cudaMalloc(&b->d_sel_total, 4));
+    CK(cudaMemset(b->d_sel_total, 0, 4));
+    CK(cudaMallocHost(&b->h_sel_cnt, (b->max_reads + 1) * 4));
+    CK(cudaMallocHost(&b->h_sel, b->sel_cap * 4));
+    CK(cudaMallocHost(&b->h_sel_total, 4));
+    return UTB_OK;
+}
+extern "C" int utb_batch_prepare(utb_batch *b, int want_text, int chunked) {
+    if (!b) { utb_set_error("utb_batch_prepare: null batch"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    int rc = want_text == 3 ? ensure_shallow_buffers(b) : want_text ? ensure_text_buffers(b) : UTB_OK;
+    if (!rc && chunked) rc = ensure_chunk_buffers(b);
+    return rc;
+}
 extern "C" int utb_batch_submit_chunk(utb_batch *b, const char *src, size_t n_bytes, size_t n_reads, int do_rc, int want_text) {
-    if (!b || !n_bytes || want_text < 1 || want_text > 2) { utb_set_error("utb_batch_submit_chunk: bad argument"); return UTB_ERR_ARG; }
+    if (!b || !n_bytes || want_text < 1 || want_text > 3) { utb_set_error("utb_batch_submit_chunk: bad argument"); return UTB_ERR_ARG; }
     if (n_bytes > b->max_bytes || n_reads > b->max_reads || n_bytes >= 0xFFFFFFFFull) { utb_set_error("utb_batch_submit_chunk: batch over capacity"); return UTB_ERR_LIMIT; }
     CK(cudaSetDevice(b->db->device));
-    if (!b->d_nl) {
-        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-        cudaError_t e = cudaMalloc(&p[0], (2 * b->max_reads + 2) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&p[1], (b->max_bytes / FR_BLOCK + 2) * 4);
-        if (e == cudaSuccess) e = cudaMalloc(&p[2], 4);
-        if (e == cudaSuccess) e = cudaMalloc(&p[3], 8);
-        if (e == cudaSuccess) e = cudaMallocHost(&p[4], 4);
-        if (e != cudaSuccess) { for (int i = 0; i < 4; ++i) cudaFree(p[i]); cudaFreeHost(p[4]); CK(e); }
-        b->d_nl = (uint32_t *)p[0]; b->d_blk = (uint32_t *)p[1]; b->d_frame_err = (uint32_t *)p[2]; b->d_frame_info = (uint32_t *)p[3];
-        b->h_frame_err = (uint32_t *)p[4];
-    }
-    int rt = ensure_text_buffers(b);
+    { int ra = ensure_chunk_buffers(b); if (ra) return ra; }
+    int rt = want_text == 3 ? ensure_shallow_buffers(b) : ensure_text_buffers(b);
     if (rt) return rt;
     // upper bounds the launches are sized for: every read owns ceil((len+1)/32) <= len/32 + 1 groups
     const size_t n_ub = n_reads ? n_reads : b->max_reads;
     uint64_t g_ub = n_bytes / 32 + n_ub + 1;
     if (g_ub > b->max_groups) g_ub = b->max_groups;
+    if (g_ub * 32ull * (do_rc ? 2u : 1u) >= 0xFFFFFFFFull) { utb_set_error("utb_batch_submit_chunk: chunk too large for the 32-bit slot space"); return UTB_ERR_LIMIT; }
     b->n_reads = n_ub; b->n_groups = (uint32_t)g_ub; b->do_rc = do_rc ? 1 : 0;
     b->want_text = want_text; b->dims_dev = b->d_dims; b->framed_on_device = 1;
     *b->h_frame_err = FR_ERR_NONE;
@@ -2336,6 +2467,11 @@ extern "C" int utb_batch_wait_text(utb_batch *b, const char **text, size_t *len,
     if (rc) return rc;
     const size_t n = *b->h_text_len;
     if (n > b->text_cap) { utb_set_error("device text overflow"); return UTB_ERR_LIMIT; }
+    if (n > b->h_text_cap) {                                        // more text than the staging holds: grow it, copy afresh
+        rc = grow_text_staging(b, n + n / 8);
+        if (rc) return rc;
+        b->text_prefetched = 0;
+    }
     if (n > b->text_prefetched) {
         CK(cudaMemcpyAsync(b->h_text + b->text_prefetched, b->d_text + b->text_prefetched, n - b->text_prefetched,
                            cudaMemcpyDeviceToHost, b->st));
@@ -2360,12 +2496,43 @@ extern "C" int utb_batch_wait_len(utb_batch *b, size_t *len, uint64_t *good_find
     if (good_finds) { uint64_t g = 0; for (int i = 0; i < COUNTER_SLOTS; ++i) g += b->h_counters[2 * COUNTER_SLOTS + i]; *good_finds = g; }
     return UTB_OK;
 }
+// want_text == 3 (non-GG mode): blocks until the batch is done and the ids its reads selected are in page-locked host
+// memory: sel_cnt[r] ids per read, back to back in sel; name_off / name_len: where the read names sit in the raw bytes.
+extern "C" int utb_batch_wait_shallow(utb_batch *b, const uint32_t **sel_cnt, const uint32_t **sel, size_t *sel_total,
+                                      const uint32_t **name_off, const uint32_t **name_len) {
+    if (!b || !sel_cnt || !sel || !sel_total) { utb_set_error("utb_batch_wait_shallow: null argument"); return UTB_ERR_ARG; }
+    if (b->want_text != 3) { utb_set_error("utb_batch_wait_shallow: batch was not submitted in the non-GG mode"); return UTB_ERR_ARG; }
+    int rc = utb_batch_wait(b, nullptr);
+    if (rc) return rc;
+    const size_t n = b->n_reads ? *b->h_sel_total : 0;
+    if (n > b->sel_cap) { utb_set_error("selected-hit list overflow"); return UTB_ERR_LIMIT; }
+    if (n) {
+        CK(cudaMemcpyAsync(b->h_sel, b->d_sel, n * 4, cudaMemcpyDeviceToHost, b->st));
+        CK(cudaStreamSynchronize(b->st));
+    }
+    *sel_cnt = b->h_sel_cnt; *sel = b->h_sel; *sel_total = n;
+    if (name_off) *name_off = b->h_name_off;
+    if (name_len) *name_len = b->h_name_len;
+    return UTB_OK;
+}
 // ... and is copied from there straight to its place in the caller's page-locked output (no staging, no host
 // memcpy); asynchronous on the batch's stream, i.e. ordered before the slot's next batch.  utb_batch_sync waits.
 extern "C" int utb_batch_text_to(utb_batch *b, char *dst, size_t len) {
     if (!b || (!dst && len) || len > b->text_cap) { utb_set_error("utb_batch_text_to: bad argument"); return UTB_ERR_ARG; }
     CK(cudaSetDevice(b->db->device));
     if (len) CK(cudaMemcpyAsync(dst, b->d_text, len, cudaMemcpyDeviceToHost, b->st));
+    return UTB_OK;
+}
+// ... or piece by piece through the batch's own page-locked staging (file sinks): bytes [off, off + *len) of the text,
+// *len clipped to the staging size; blocks until they are there.
+extern "C" int utb_batch_text_piece(utb_batch *b, size_t off, size_t *len, const char **piece) {
+    if (!b || !len || !piece || off > b->text_cap) { utb_set_error("utb_batch_text_piece: bad argument"); return UTB_ERR_ARG; }
+    CK(cudaSetDevice(b->db->device));
+    if (*len > b->h_text_cap) *len = b->h_text_cap;
+    if (off + *len > b->text_cap) { utb_set_error("utb_batch_text_piece: beyond the text"); return UTB_ERR_ARG; }
+    if (*len) CK(cudaMemcpyAsync(b->h_text, b->d_text + off, *len, cudaMemcpyDeviceToHost, b->st));
+    CK(cudaStreamSynchronize(b->st));
+    *piece = b->h_text;
     return UTB_OK;
 }
 extern "C" int utb_batch_sync(utb_batch *b) {

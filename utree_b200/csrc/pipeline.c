@@ -43,6 +43,10 @@ size_t utb_batch_reads(const utb_batch *b);
 int utb_batch_wait_len(utb_batch *b, size_t *len, uint64_t *good_finds);
 int utb_batch_text_to(utb_batch *b, char *dst, size_t len);
 int utb_batch_sync(utb_batch *b);
+int utb_batch_text_piece(utb_batch *b, size_t off, size_t *len, const char **piece);
+int utb_batch_prepare(utb_batch *b, int want_text, int chunked);
+int utb_batch_wait_shallow(utb_batch *b, const uint32_t **sel_cnt, const uint32_t **sel, size_t *sel_total,
+                           const uint32_t **name_off, const uint32_t **name_len);
 int utb_pinned_alloc(size_t n, void **out);
 void utb_pinned_free(void *p);
 
@@ -130,6 +134,9 @@ struct utb_searcher {
     int verbose;                   /* CLI: progress lines on stdout */
     int device_format;             /* output lines built on the GPU (default) or by the host formatter team */
     int device_frame;              /* records framed on the GPU (default with device_format): the host only cuts chunks at a "\n>" */
+    int shallow;                   /* the non-GG binary's search (-D SEARCH): SPARSITY-skip slide + shallow vote (utb_searcher_set_shallow) */
+    uint32_t *horses; size_t horses_cap;   /* its AllTheKingsHorses (itree.c:970): survives from read to read within a search */
+    uint32_t *tally;               /* its Hashes (itree.c:971) */
     char *arena; size_t arena_cap; /* page-locked output of utb_search_mem: the devices copy their text straight into it; valid until
                                     * the next search on this searcher or its destruction */
 };
@@ -183,11 +190,29 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
         slot_t *sl = &s->slots[i];
         sl->dev_index = i % n_devices;
         int rc = utb_batch_create(s->dbs[sl->dev_index], s->batch_bytes, s->batch_reads, &sl->b);
+        if (!rc) rc = utb_batch_prepare(sl->b, s->device_format, s->device_frame);   /* nothing is allocated inside a search */
         if (rc) { utb_searcher_destroy(s); return rc; }
         sl->name_off = utb_batch_name_off(sl->b);                  /* pinned: the device formatter reads them too */
         sl->name_len = utb_batch_name_len(sl->b);
     }
     *out = s;
+    return UTB_OK;
+}
+
+/* Switches the searcher to what the reference's OTHER search binary computes (utree-search, itree.c built with
+ * -D SEARCH): the slide skips 7 windows after every hit (itree.c:948-951) and the vote is the shallow top-2
+ * plurality of itree.c:969-1007, whose result for a read depends on the reads before it.  The device looks up and
+ * selects; the order-dependent vote and the "%f" column are done by the formatter thread, read by read. */
+int utb_searcher_set_shallow(utb_searcher *s, int on) {
+    if (!s) { utb_set_error("utb_searcher_set_shallow: null searcher"); return UTB_ERR_ARG; }
+    s->shallow = on ? 1 : 0;
+    if (!on) return UTB_OK;
+    if (!s->tally) s->tally = (uint32_t *)calloc(s->ctr->max_ix ? s->ctr->max_ix : 1, sizeof(uint32_t));
+    if (!s->tally) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    for (int i = 0; i < s->n_slots; ++i) {
+        int rc = utb_batch_prepare(s->slots[i].b, 3, s->device_frame);
+        if (rc) return rc;
+    }
     return UTB_OK;
 }
 
@@ -200,6 +225,7 @@ void utb_searcher_destroy(utb_searcher *s) {
         if (!shared) utb_db_free(s->dbs[d]);
     }
     utb_pinned_free(s->arena);
+    free(s->horses); free(s->tally);
     free(s->slots); free(s->dbs); free(s->devices); free(s);
 }
 
@@ -386,6 +412,63 @@ static void copy_part(void *c_, int part, int nparts) {
     }
 }
 
+/* The shallow vote of the non-GG binary, read by read in input order (itree.c:979-1003).  sel_cnt[r] ids per read,
+ * back to back in sel, are what its slide appended to AllTheKingsHorses; `if (!kingsMen++)` (itree.c:982) never
+ * fires but bumps the count, so the tally runs over ONE MORE entry: whatever an earlier read of this search left
+ * at that index (0 if none did).  Lines go to F->buf[0]. */
+static int shallow_vote(utb_searcher *s, const slot_t *sl, const uint32_t *sel_cnt, const uint32_t *sel, size_t sel_total,
+                        fmt_ctx *F, size_t *n_out, uint64_t *good_out) {
+    const utb_ctr *c = s->ctr;
+    size_t need = 64;
+    for (size_t r = 0; r < sl->n_reads; ++r) if (sel_cnt[r]) need += sl->name_len[r] + s->max_label + 48;
+    if (need > F->cap[0]) {
+        free(F->buf[0]);
+        F->cap[0] = need + (need >> 2);
+        F->buf[0] = (char *)malloc(F->cap[0]);
+        if (!F->buf[0]) { F->cap[0] = 0; utb_set_error("out of memory (formatter)"); return UTB_ERR_NOMEM; }
+    }
+    char *p = F->buf[0];
+    uint64_t good = 0;
+    size_t at = 0;
+    uint32_t *tally = s->tally;
+    for (size_t r = 0; r < sl->n_reads; ++r) {
+        const size_t n = sel_cnt[r];
+        if (!n) continue;                                          /* itree.c:979 */
+        if (at + n > sel_total) { utb_set_error("selected-hit list shorter than its counts"); return UTB_ERR_LIMIT; }
+        if (n + 1 > s->horses_cap) {                               /* the reference's array is one zero-filled 2 x 16 Mi block */
+            size_t nc = s->horses_cap ? s->horses_cap : 1024;
+            while (nc < n + 1) nc <<= 1;
+            uint32_t *h = (uint32_t *)realloc(s->horses, nc * sizeof(uint32_t));
+            if (!h) { utb_set_error("out of memory (formatter)"); return UTB_ERR_NOMEM; }
+            memset(h + s->horses_cap, 0, (nc - s->horses_cap) * sizeof(uint32_t));
+            s->horses = h; s->horses_cap = nc;
+        }
+        uint32_t *horses = s->horses;
+        memcpy(horses, sel + at, n * sizeof(uint32_t));            /* itree.c:951 */
+        at += n;
+        ++good;                                                    /* itree.c:980 */
+        const size_t men = n + 1;                                  /* itree.c:982 */
+        for (size_t i = 0; i < men; ++i) ++tally[horses[i]];       /* itree.c:984-985 */
+        uint32_t most = 0, second = 0, most_ix = 0;
+        for (size_t i = 0; i < men; ++i) {                         /* itree.c:988-997 */
+            const uint32_t h = tally[horses[i]];
+            if (h > most) { second = most; most_ix = horses[i]; most = h; }
+            else if (h > second) second = h;
+            tally[horses[i]] = 0;
+        }
+        if (most < 2 || most < 2 * second) { --good; continue; }   /* itree.c:1000: TOLERANCE_THRESHOLD 2, SLACK 2 */
+        memcpy(p, sl->host_bytes + sl->name_off[r], sl->name_len[r]); p += sl->name_len[r];
+        *p++ = '\t';
+        const char *lab = c->blob + c->off[most_ix];
+        const size_t ll = c->off[most_ix + 1] - c->off[most_ix] - 1;
+        memcpy(p, lab, ll); p += ll;
+        p += sprintf(p, "\t%f\t%d\n", (double)1 - (double)second / most, (int)most);   /* itree.c:1002 */
+    }
+    *n_out = (size_t)(p - F->buf[0]);
+    *good_out = good;
+    return UTB_OK;
+}
+
 static void *formatter_main(void *arg) {
     run_t *R = (run_t *)arg;
     utb_searcher *s = R->s;
@@ -403,8 +486,9 @@ static void *formatter_main(void *arg) {
         const utb_result *res = NULL;
         const char *text = NULL; size_t text_len = 0; uint64_t good = 0;
         double tw = now_s();
-        int rc = direct ? utb_batch_wait_len(sl->b, &text_len, &good)
-                        : s->device_format ? utb_batch_wait_text(sl->b, &text, &text_len, &good) : utb_batch_wait(sl->b, &res);
+        const uint32_t *sel_cnt = NULL, *sel = NULL; size_t sel_total = 0;
+        int rc = s->shallow ? utb_batch_wait_shallow(sl->b, &sel_cnt, &sel, &sel_total, NULL, NULL)
+                            : s->device_format ? utb_batch_wait_len(sl->b, &text_len, &good) : utb_batch_wait(sl->b, &res);
         R->st.fm_wait_gpu += now_s() - tw;
         if (seq < 64) R->tl_gpu_done[seq] = now_s() - R->t0;
         if (rc && !R->error) { R->error = rc; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
@@ -415,15 +499,36 @@ static void *formatter_main(void *arg) {
         const int discard = R->discard;
         pthread_mutex_unlock(&R->mu);
         if (discard) rc = -1;                                      /* nothing of this batch is emitted or counted */
-        if (!rc && s->device_format) {
+        if (!rc && s->shallow) {
+            double tf = now_s();
+            size_t n_out = 0;
+            int r2 = shallow_vote(s, sl, sel_cnt, sel, sel_total, &F, &n_out, &good);
+            if (r2 && !R->error) { R->error = r2; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
+            R->st.fm_format += now_s() - tf;
+            tf = now_s();
+            if (!r2 && n_out && !sink_reserve(R->sink, R->sink->off + n_out)) {
+                F.len[0] = n_out; F.off[0] = R->sink->off;
+                emit_part(&F, 0, 1);
+                F.len[0] = 0;
+                R->sink->off += n_out;
+                R->st.out_bytes += n_out;
+            }
+            R->st.good_finds += good;
+            R->st.fm_emit += now_s() - tf;
+            R->st.d2h_bytes += sl->n_reads * 12 + sel_total * 4 + 4 * 1024 * 8 + 16;
+        } else if (!rc && s->device_format) {
             double tf = now_s();
             if (text_len && !sink_reserve(R->sink, R->sink->off + text_len)) {
                 if (direct) {
                     int r2 = utb_batch_text_to(sl->b, s->arena + R->sink->off, text_len);
                     if (r2 && !R->error) { R->error = r2; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); }
-                } else {
-                    copy_ctx cc = {R->sink, text, text_len, R->sink->off};
+                } else for (size_t o = 0; o < text_len && !R->error;) {   /* file sink: through the slot's page-locked staging */
+                    size_t len = text_len - o;
+                    int r2 = utb_batch_text_piece(sl->b, o, &len, &text);
+                    if (r2) { R->error = r2; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); break; }
+                    copy_ctx cc = {R->sink, text, len, R->sink->off + o};
                     team_run(&R->fmt_team, copy_part, &cc);
+                    o += len;
                 }
                 R->sink->off += text_len;
                 R->st.out_bytes += text_len;
@@ -822,6 +927,7 @@ static int run_search(utb_searcher *s, source_t *src, sink_t *sink, int do_rc, u
     R.t0 = t0;
     uint64_t launches0 = 0;
     for (int i = 0; i < s->n_slots; ++i) { s->slots[i].state = 0; launches0 += utb_batch_launches(s->slots[i].b); }
+    if (s->shallow && s->horses) memset(s->horses, 0, s->horses_cap * sizeof(uint32_t));   /* every search starts like a fresh process */
     /* split the host threads between the two teams */
     /* with the lines built on the device the formatter only moves finished text: most threads frame */
     int T = s->host_threads, n_fm = T >= 4 ? T / 2 : 1, n_rd = T >= 4 ? T - n_fm : 1;
@@ -898,7 +1004,7 @@ read_loop:
         if (!fill) break;                                          /* clean EOF */
 
         sl->src_off = consumed;
-        const int want_text = !s->device_format ? 0 : sink->fd < 0 ? 2 : 1;   /* 2: the device text goes straight into the output arena */
+        const int want_text = s->shallow ? 3 : s->device_format ? 2 : 0;   /* 2: the text stays on the device until the formatter knows where it goes; 3: non-GG mode */
         if (device_frame && fill >= 2 && fill < 0xFFFFFFFFull) {
             /* Fast path: the host does not look at the bytes.  In a well-formed file exactly the header lines
              * begin with '>' (itree.c:880, 886), so the chunk is cut right before the last line that does (at the
@@ -1094,9 +1200,13 @@ int utb_search_mem(utb_searcher *s, const char *fasta, size_t n, int do_rc,
 /* ---- CLI (itree.c:1357-1377; stdout lines of SURVEY App. C) -------------------------------------- */
 static const char *TYPEARR[9] = {"NA", "uint8_t", "uint16_t", "NA", "uint32_t", "NA", "NA", "NA", "uint64_t"};
 
-int utb_main(int argc, char **argv) {
+static int main_impl(int argc, char **argv, int gg);
+int utb_main(int argc, char **argv) { return main_impl(argc, argv, 1); }
+/* the non-GG binary (makefile: utree-search, -D SEARCH): same argv / banner / exit codes, shallow vote */
+int utb_main_shallow(int argc, char **argv) { return main_impl(argc, argv, 0); }
+static int main_impl(int argc, char **argv, int gg) {
     if (argc < 4) {                                                /* itree.c:1358-1360 */
-        printf("[v2.0RF SigNature Edition] usage: xtree-searchGG compTree.ctr fastaToSearch.fa output.txt [threads] [SPEED <X>] [RC]\n");
+        printf("[v2.0RF SigNature Edition] usage: xtree-search%s compTree.ctr fastaToSearch.fa output.txt [threads] [SPEED <X>] [RC]\n", gg ? "GG" : "");
         return 1;
     }
     printf("This is UTree [v2.0RF SigNature Edition]\n");
@@ -1147,6 +1257,8 @@ int utb_main(int argc, char **argv) {
     utb_searcher *s = NULL;
     rc = utb_searcher_create(ctr, devs, n, threads, &s);
     if (rc) { fprintf(stderr, "utree-b200: %s\n", utb_last_error()); utb_ctr_close(ctr); return rc == UTB_ERR_NOMEM ? 3 : 4; }
+    if (!gg) rc = utb_searcher_set_shallow(s, 1);
+    if (rc) { fprintf(stderr, "utree-b200: %s\n", utb_last_error()); utb_searcher_destroy(s); utb_ctr_close(ctr); return rc == UTB_ERR_NOMEM ? 3 : 4; }
     puts("Tree read.");                                            /* itree.c:826 */
     fflush(stdout);
     s->verbose = 1;
