@@ -236,6 +236,25 @@ int utb_compress_ubt(const char *ubt_path, const char *ctr_path, uint64_t *n_rec
 /* The COMPRESS binary's CLI contract (itree.c:1352-1355). */
 int utb_compress_main(int argc, char **argv);
 
+/* ---- utree-build_gg equivalent (itree.c:501-635, 268-307, 1317-1343) ---- */
+typedef struct {
+    uint64_t map_bytes, map_lines;   /* "Parsed map. N bytes, M lines."                     */
+    uint64_t sequences;              /* FASTA records                                       */
+    uint64_t kmers_seen;             /* k-mer occurrences that pass the complevel rule      */
+    uint64_t kmers_made;             /* distinct words ("Done with sequence parse: N k-mers made") */
+    uint64_t records;                /* good words written ("Total nodes in tree")          */
+    uint32_t labels;                 /* label ids handed out, superseded ones included      */
+} utb_build_stats;
+/* FASTA (one header + one sequence line per genome) + two-column map (name <tab> label)
+ * -> .ubt (+ <out>.gg.log), byte-identical to the reference builder for complevel 0..4: the
+ * k-mers are extracted, stably sorted and relabelled on `device`; gg = 0 gives the plain
+ * BUILD rule (a second label makes a word bad).  *ref_exit: the reference's exit code for
+ * malformed input (1, 2, 4). */
+int utb_build_ubt(const char *fasta_path, const char *map_path, const char *out_path, uint32_t complevel, int gg, int ix_bytes,
+                  int device, utb_build_stats *st, int *ref_exit);
+/* The BUILD_GG binary's CLI contract (itree.c:1379-1408). */
+int utb_build_main(int argc, char **argv);
+
 /* ---- measurement helpers --------------------------------------------------- */
 /* Random 32-byte-sector gather bandwidth over a working set of ws_bytes on
  * `device` (the roofline denominator of SURVEY 8d).  loads: sectors read. */

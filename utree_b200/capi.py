@@ -50,7 +50,7 @@ EXPORTS = [
     "utb_batch_submit", "utb_batch_wait", "utb_batch_name_off", "utb_batch_name_len", "utb_batch_submit_text", "utb_batch_wait_text", "utb_batch_rerun_device", "utb_batch_counts", "utb_batch_lookup_detail", "utb_db_clone", "utb_db_device",
     "utb_lookup_words", "utb_pack_sequence", "utb_vote_hits", "utb_vote_hits_sparse", "utb_frame_records", "utb_count_newlines", "utb_format_results",
     "utb_searcher_create", "utb_searcher_destroy", "utb_search_file", "utb_search_mem", "utb_free",
-    "utb_main", "utb_main_shallow", "utb_searcher_set_shallow", "utb_measure_rand32", "utb_compress_ubt", "utb_compress_main",
+    "utb_main", "utb_main_shallow", "utb_build_ubt", "utb_build_main", "utb_searcher_set_shallow", "utb_measure_rand32", "utb_compress_ubt", "utb_compress_main",
 ]
 
 _lib = None

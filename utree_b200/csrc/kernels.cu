@@ -1093,23 +1093,52 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__rest
 //                       words which the whole grid accumulates into that read's histogram, and
 //   vote_big_finish_kernel one CTA per read merges: sort, gather, walk.
 #define VB_THREADS 256
-#define VB_PER_SM 2
+#define VB_PER_SM 4
 #define VB_SORT_MAX 2048u           // touched labels sorted in shared memory; beyond: sweep over all labels in rank order
 #define VBIG_CHUNK_WORDS 2048u      // hit-map words (65,536 lookup slots) a CTA accumulates at a time
-#define VBIG_POOL_MAX 256u          // split reads a batch can hold scratch for
+#define VBIG_POOL_MAX 2048u         // split reads a batch can hold scratch for
+#define VL_CACHE 64u                // per-CTA (label, count) pairs gathered in shared memory before they go to the histogram
 struct VoteLong {
     uint32_t *hist, *tlab, *tcnt;                       // [CTAs of vote_block_kernel][max_ix]
     uint32_t *big_hist, *big_tlab, *big_tcnt;           // [pool][max_ix]
     uint32_t *big_list;                                 // [pool] read index
     uint32_t *big_state;                                // [0] split reads of the batch, then per read: touched labels, hits
+    uint32_t *work;                                     // [0] next entry of the deferral list a CTA of vote_block_kernel takes
     uint32_t pool;
     uint32_t sort_max;                                  // <= VB_SORT_MAX (tests lower it to reach the sweep)
     unsigned long long split_slots;
 };
-// Adds the labels of the hit-map words [w0, w1) of one read (dense mode: of the slots they cover) to hist;
-// labels met for the first time are appended to tlab through *nt.  Block-wide call; returns this thread's hits.
+// A read hits few distinct labels (its own lineage), thousands of times: the hits are gathered in a small
+// shared-memory table first (CAS on the key, add on the count) and only its entries go to the global
+// histogram -- a dependent global atomic per hit was what bound this kernel (profiles/r02_*: 24.6 ms of a
+// 59 ms LONG step).  A label that finds no room in its four probes goes to the histogram directly.
+struct VlCache { uint32_t key[VL_CACHE]; uint32_t cnt[VL_CACHE]; };
+__device__ __forceinline__ void vl_cache_clear(VlCache &c) {
+    for (uint32_t i = threadIdx.x; i < VL_CACHE; i += blockDim.x) { c.key[i] = UTB_BAD32; c.cnt[i] = 0; }
+}
+__device__ __forceinline__ void vl_add(VlCache &c, uint32_t h, uint32_t k, uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
+    uint32_t s = (h * 2654435761u) >> 26;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const uint32_t old = atomicCAS(&c.key[s], UTB_BAD32, h);
+        if (old == UTB_BAD32 || old == h) { atomicAdd(&c.cnt[s], k); return; }
+        s = (s + 1u) & (VL_CACHE - 1u);
+    }
+    if (atomicAdd(&hist[h], k) == 0u) tlab[atomicAdd(nt, 1u)] = h;
+}
+// block-wide, between two barriers: the table's entries into the histogram; labels met for the first time are
+// appended to tlab through *nt
+__device__ __forceinline__ void vl_flush(VlCache &c, uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
+    for (uint32_t i = threadIdx.x; i < VL_CACHE; i += blockDim.x) {
+        const uint32_t h = c.key[i], k = c.cnt[i];
+        if (h != UTB_BAD32 && k && atomicAdd(&hist[h], k) == 0u) tlab[atomicAdd(nt, 1u)] = h;
+        c.key[i] = UTB_BAD32; c.cnt[i] = 0;
+    }
+}
+// Adds the labels of the hit-map words [w0, w1) of one read (dense mode: of the slots they cover) through the
+// table.  Block-wide call; returns this thread's hits.  The caller flushes.
 __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn &in, uint64_t start, uint64_t count, uint64_t w0, uint64_t w1,
-                                                  uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
+                                                  VlCache &cache, uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint32_t n_local = 0;
     if (in.hitmap) {
@@ -1119,10 +1148,7 @@ __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn 
             while (m) {
                 const uint32_t bit = __ffs(m) - 1; m &= m - 1;
                 const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
-                if (h < db.max_ix) {
-                    if (atomicAdd(&hist[h], 1u) == 0u) tlab[atomicAdd(nt, 1u)] = h;
-                    ++n_local;
-                }
+                if (h < db.max_ix) { vl_add(cache, h, 1u, hist, tlab, nt); ++n_local; }
             }
         }
     } else {
@@ -1132,7 +1158,7 @@ __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn 
             const uint32_t h = i < hi ? __ldg(in.hits + start + i) : HIT_NOWIN;
             const bool ok = h < db.max_ix;
             const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-            if (ok && (uint32_t)(__ffs(peers) - 1) == lane && atomicAdd(&hist[h], (uint32_t)__popc(peers)) == 0u) tlab[atomicAdd(nt, 1u)] = h;
+            if (ok && (uint32_t)(__ffs(peers) - 1) == lane) vl_add(cache, h, (uint32_t)__popc(peers), hist, tlab, nt);
             n_local += ok;
         }
     }
@@ -1217,13 +1243,20 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
                   const uint32_t *__restrict__ gen_list, const uint32_t *__restrict__ gen_count,
                   VoteLong vl, unsigned long long *__restrict__ counters) {
     __shared__ VlSmem sm;
-    __shared__ uint32_t s_nt, s_n, s_big;
+    __shared__ VlCache cache;
+    __shared__ uint32_t s_nt, s_n, s_big, s_qi;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint32_t *hist = vl.hist + (size_t)blockIdx.x * db.max_ix;
     uint32_t *tlab = vl.tlab + (size_t)blockIdx.x * db.max_ix;
     uint32_t *tcnt = vl.tcnt + (size_t)blockIdx.x * db.max_ix;
     const uint32_t total = *gen_count;
-    for (uint32_t qi = blockIdx.x; qi < total; qi += gridDim.x) {
+    vl_cache_clear(cache);
+    for (;;) {                                                     // reads differ a hundredfold in length: whoever is free takes the next one
+        __syncthreads();
+        if (tid == 0) s_qi = atomicAdd(vl.work, 1u);
+        __syncthreads();
+        const uint32_t qi = s_qi;
+        if (qi >= total) break;
         const uint32_t r = gen_list[qi];
         uint64_t start, count;
         vote_range(in, r, start, count);
@@ -1235,28 +1268,39 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
             }
         }
         __syncthreads();
-        if (s_big) { __syncthreads(); continue; }
-        uint32_t n_local = vl_accumulate(db, in, start, count, 0, (count + 31) >> 5, hist, tlab, &s_nt);
+        if (s_big) continue;
+        uint32_t n_local = vl_accumulate(db, in, start, count, 0, (count + 31) >> 5, cache, hist, tlab, &s_nt);
         for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
         if (lane == 0 && n_local) atomicAdd(&s_n, n_local);
         __syncthreads();
-        vl_finish(db, hist, tlab, tcnt, s_nt, s_n, vl.sort_max, results + r, counters, sm);
+        vl_flush(cache, hist, tlab, &s_nt);
         __syncthreads();
+        vl_finish(db, hist, tlab, tcnt, s_nt, s_n, vl.sort_max, results + r, counters, sm);
     }
 }
 __global__ void __launch_bounds__(VB_THREADS)
 vote_big_count_kernel(DevDB db, VoteIn in, VoteLong vl) {
+    __shared__ VlCache cache;
     const uint32_t n_big = min(*vl.big_state, vl.pool), lane = threadIdx.x & 31u;
+    vl_cache_clear(cache);
+    __syncthreads();
     for (uint32_t bi = 0; bi < n_big; ++bi) {
         uint64_t start, count;
         vote_range(in, vl.big_list[bi], start, count);
         const uint64_t n_words = (count + 31) >> 5, n_chunks = (n_words + VBIG_CHUNK_WORDS - 1) / VBIG_CHUNK_WORDS;
         uint32_t *hist = vl.big_hist + (size_t)bi * db.max_ix, *tlab = vl.big_tlab + (size_t)bi * db.max_ix;
         uint32_t n_local = 0;
+        bool any = false;
         // the chunks of consecutive reads start at different CTAs, so short tails do not pile up on CTA 0
         for (uint64_t c = (blockIdx.x + gridDim.x - (bi * 61u) % gridDim.x) % gridDim.x; c < n_chunks; c += gridDim.x) {
             const uint64_t w0 = c * VBIG_CHUNK_WORDS, w1 = w0 + VBIG_CHUNK_WORDS < n_words ? w0 + VBIG_CHUNK_WORDS : n_words;
-            n_local += vl_accumulate(db, in, start, count, w0, w1, hist, tlab, vl.big_state + 1 + 2 * bi);
+            n_local += vl_accumulate(db, in, start, count, w0, w1, cache, hist, tlab, vl.big_state + 1 + 2 * bi);
+            any = true;
+        }
+        if (any) {                                                 // block-uniform: the chunk loop's bounds are
+            __syncthreads();
+            vl_flush(cache, hist, tlab, vl.big_state + 1 + 2 * bi);
+            __syncthreads();
         }
         for (int o = 16; o; o >>= 1) n_local += __shfl_xor_sync(0xFFFFFFFFu, n_local, o);
         if (lane == 0 && n_local) atomicAdd(vl.big_state + 2 + 2 * bi, n_local);
@@ -1272,61 +1316,156 @@ vote_big_finish_kernel(DevDB db, VoteLong vl, utb_result *__restrict__ results, 
 }
 
 // ---------------------------------------------------------------------------
-// the non-GG binary (-D SEARCH): which hits its slide would have met (itree.c:903-933 with XT_SHALLOWVOTE, :948-951)
+// the non-GG binary (-D SEARCH): the ids its slide collects (itree.c:903-933 with XT_SHALLOWVOTE, :948-951)
 // ---------------------------------------------------------------------------
-// After a hit the reference's loop index jumps PACKSIZE / SPARSITY - 1 = 7 windows ahead, so the windows it
-// looks up depend on the hits before them -- but a lookup is a pure function, so looking up every window
-// (as the GG path does) and then walking the hits in text order, keeping a hit only if it lies 8 or more
-// windows past the last one kept, selects exactly the ids the reference appends to AllTheKingsHorses.  Text
-// order (itree.c:887-898): the forward windows left to right, then the windows of the reverse-complement
-// text, i.e. the reverse-strand slots right to left; the 'N' between the two halves resets the skip.
-// One thread per read; FILL = false counts (sel_cnt), FILL = true writes the ids at sel_off[r].
-#define SH_SKIP 8u
-template <bool FILL>
+// After a hit the reference's loop index jumps PACKSIZE / SPARSITY - 1 = 7 windows ahead -- and its rolling
+// word does not follow: `w <<= (i-z-1) << 1` (itree.c:920) shifts by 7 bases on top of the 8 per-base shifts
+// of the inner loop, so the word looked up at z + 8 is the last 17 bases before the hit, seven A's, and the 8
+// new bases; the stray A's stay in the word for 24 more windows.  What is looked up after a hit at window end
+// z is therefore: 24 CORRUPTED words at z + 8 .. z + 31 (each can hit by accident, which corrupts the word
+// again), then the true windows from z + 32 on; an ambiguous base (and the 'N' between the read and its
+// reverse complement, itree.c:892) restarts with a clean word.  A lookup is a pure function of its word, so
+// the true windows are taken from the hit map the GG path fills anyway (every window was looked up), and only
+// the corrupted stretches are emulated word by word with direct lookups.  One thread per read walks the two
+// halves of the text in order: forward windows left to right, then the windows of the reverse-complement
+// text, i.e. the reverse-strand slots right to left.  The ids land in the read's own stretch of a gapped
+// buffer (a kept hit uses up >= 8 text positions, so a quarter of the read's slots is room enough);
+// shallow_compact_kernel packs them.
+struct ShallowRead {
+    const uint64_t *pk; const uint32_t *bad;                       // packed stream
+    uint64_t pos0;                                                  // first position of the read in it
+    uint32_t L, nwin, nstr;
+    uint64_t start;                                                 // first lookup slot of the read
+};
+// base at text position t of half `strand` (strand 1: the reverse-complement text); false: not ACGT
+__device__ __forceinline__ bool sh_base(const ShallowRead &R, uint32_t strand, uint32_t t, uint32_t &c) {
+    const uint64_t pos = R.pos0 + (strand ? R.L - 1u - t : t);
+    const uint64_t g = pos >> 5; const uint32_t o = (uint32_t)pos & 31u;
+    if ((R.bad[g] >> o) & 1u) return false;
+    c = (uint32_t)(R.pk[g] >> (62u - 2u * o)) & 3u;
+    if (strand) c = 3u - c;
+    return true;
+}
+__device__ __forceinline__ uint32_t lookup_any(const DevDB &db, uint64_t w) {
+    if (db.ktab) return (db.sieve && !sv_maybe(db, w)) ? HIT_MISS : kt_lookup(db, w);
+    Probe q[1];
+    probe_begin(db, w, q[0]);
+    probe_run<1>(db, q);
+    return probe_end(db, q[0]);
+}
+// first true window of this half, at text index >= from, that hit: its index (nwin if none) and its label
+__device__ __forceinline__ uint32_t sh_next_hit(const DevDB &db, const VoteIn &in, const ShallowRead &R, uint32_t strand, uint32_t from, uint32_t &label) {
+    if (from >= R.nwin) return R.nwin;
+    if (in.hitmap) {
+        const uint32_t *hm = in.hitmap + (R.start >> 5);            // start is a multiple of 32
+        if (!strand) {
+            uint64_t slot = (uint64_t)from * R.nstr;
+            const uint64_t end = (uint64_t)R.nwin * R.nstr;
+            const uint32_t lanes = R.nstr == 2 ? 0x55555555u : 0xFFFFFFFFu;
+            for (uint64_t w = slot >> 5; w * 32 < end; ++w) {
+                uint32_t m = __ldg(hm + w) & lanes;
+                if (w == slot >> 5) m &= 0xFFFFFFFFu << (slot & 31u);
+                while (m) {
+                    const uint32_t bit = __ffs(m) - 1u; m &= m - 1u;
+                    const uint64_t sl = w * 32 + bit;
+                    if (sl >= end) return R.nwin;
+                    const uint32_t h = __ldg(in.hits + R.start + sl);
+                    if (h < db.max_ix) { label = h; return (uint32_t)(sl / R.nstr); }
+                }
+            }
+            return R.nwin;
+        }
+        // reverse-complement text: window q of it is the reverse-strand slot of forward position nwin - 1 - q
+        int64_t slot = (int64_t)(R.nwin - 1u - from) * 2 + 1;
+        for (int64_t w = slot >> 5; w >= 0; --w) {
+            uint32_t m = __ldg(hm + w) & 0xAAAAAAAAu;
+            if (w == slot >> 5 && (slot & 31) != 31) m &= (1u << ((slot & 31) + 1)) - 1u;
+            while (m) {
+                const uint32_t bit = 31u - __clz(m); m &= ~(1u << bit);
+                const uint64_t sl = (uint64_t)w * 32 + bit;
+                const uint32_t h = __ldg(in.hits + R.start + sl);
+                if (h < db.max_ix) { label = h; return R.nwin - 1u - (uint32_t)(sl >> 1); }
+            }
+        }
+        return R.nwin;
+    }
+    for (uint32_t t = from; t < R.nwin; ++t) {                      // dense hit slots (sieve off / probe sequence)
+        const uint32_t pos = strand ? R.nwin - 1u - t : t;
+        const uint32_t h = __ldg(in.hits + R.start + (uint64_t)pos * R.nstr + strand);
+        if (h < db.max_ix) { label = h; return t; }
+    }
+    return R.nwin;
+}
 __global__ void __launch_bounds__(128)
-shallow_select_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ dims, uint32_t *__restrict__ sel_cnt,
-                      const uint32_t *__restrict__ sel_off, uint32_t *__restrict__ sel) {
+shallow_select_kernel(DevDB db, VoteIn in, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, uint32_t n_reads,
+                      const uint32_t *__restrict__ dims, uint32_t *__restrict__ sel_cnt, uint32_t *__restrict__ sel_gap) {
+    if (dims) n_reads = dims[0];
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
+        ShallowRead R;
+        uint64_t count;
+        vote_range(in, (uint32_t)r, R.start, count);
+        R.pk = pk; R.bad = bad; R.nstr = in.nstr;
+        R.L = __ldg(in.seq_len + r); R.nwin = R.L >= 32u ? R.L - 31u : 0u;
+        R.pos0 = (uint64_t)__ldg(in.grp_off + r) * 32u;
+        uint32_t *out = sel_gap + (R.start >> 2);
+        uint32_t n = 0;
+        for (uint32_t strand = 0; strand < R.nstr && R.nwin; ++strand) {
+            uint32_t from = 0;                                      // first true window that may be looked up next
+            for (;;) {
+                uint32_t lab;
+                const uint32_t p = sh_next_hit(db, in, R, strand, from, lab);
+                if (p >= R.nwin) break;
+                out[n++] = lab;                                     // itree.c:951
+                // the true word of that window, then the reference's arithmetic from there on
+                uint64_t w = 0;
+                {
+                    const uint32_t fp = strand ? R.nwin - 1u - p : p;
+                    window_at(pk, bad, (uint32_t)(R.pos0 + fp), w);
+                    if (strand) w = revcomp_word(w);
+                }
+                uint32_t z = p + 31u;                               // text index of the hit's last base
+                bool half_done = false;
+                for (;;) {                                          // one corrupted stretch per round
+                    uint32_t i = z + 8u;                            // itree.c:950 + the loop's ++i
+                    if (i >= R.L) { half_done = true; break; }      // forward half: the 'N' follows; reverse half / no RC: i < length fails
+                    w <<= 14;                                       // itree.c:920 with i - z - 1 = 7
+                    bool clean = false;
+                    for (uint32_t j = z + 1u; j <= i; ++j) {        // itree.c:922-925
+                        uint32_t c;
+                        if (!sh_base(R, strand, j, c)) { from = j + 1u; clean = true; break; }   // a clean word restarts after the bad base
+                        w = (w << 2) | c;
+                    }
+                    if (clean) break;
+                    bool again = false;
+                    for (uint32_t left = 24u;;) {                   // windows z + 8 .. z + 31 carry the stray A's
+                        const uint32_t h = lookup_any(db, w);
+                        if (h < db.max_ix) { out[n++] = h; z = i; again = true; break; }   // an accidental hit: corrupted again from here
+                        if (--left == 0u) { from = i + 1u - 31u; clean = true; break; }    // the next window is a true one
+                        ++i;
+                        if (i >= R.L) { half_done = true; break; }
+                        uint32_t c;
+                        if (!sh_base(R, strand, i, c)) { from = i + 1u; clean = true; break; }
+                        w = (w << 2) | c;
+                    }
+                    if (!again) break;
+                }
+                if (half_done) break;
+            }
+        }
+        sel_cnt[r] = n;
+    }
+}
+// gapped -> packed: one thread per read
+__global__ void __launch_bounds__(128)
+shallow_compact_kernel(VoteIn in, uint32_t n_reads, const uint32_t *__restrict__ dims, const uint32_t *__restrict__ sel_cnt,
+                       const uint32_t *__restrict__ sel_off, const uint32_t *__restrict__ sel_gap, uint32_t *__restrict__ sel) {
     if (dims) n_reads = dims[0];
     for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t start, count;
         vote_range(in, (uint32_t)r, start, count);
-        const uint32_t nstr = in.nstr, nwin = (uint32_t)(count / nstr);
-        uint32_t n = 0;
-        uint32_t *out = FILL ? sel + sel_off[r] : nullptr;
-        for (uint32_t strand = 0; strand < nstr; ++strand) {
-            uint32_t next = 0;                                     // first text position of this half that may be kept
-            if (in.hitmap) {
-                const uint32_t *hm = in.hitmap + (start >> 5);     // start is a multiple of 32
-                const uint32_t nwords = (uint32_t)((count + 31) >> 5);
-                const uint32_t lanes = nstr == 2 ? (strand ? 0xAAAAAAAAu : 0x55555555u) : 0xFFFFFFFFu;
-                for (uint32_t k = 0; k < nwords; ++k) {
-                    const uint32_t w = strand ? nwords - 1 - k : k;
-                    uint32_t m = __ldg(hm + w) & lanes;
-                    while (m) {
-                        const uint32_t bit = strand ? 31u - __clz(m) : __ffs(m) - 1u;
-                        m &= ~(1u << bit);
-                        const uint32_t slot = 32u * w + bit, pos = slot / nstr;
-                        if (pos >= nwin) continue;
-                        const uint32_t tp = strand ? nwin - 1u - pos : pos;          // position in the text of this half
-                        if (tp < next) continue;
-                        const uint32_t h = __ldg(in.hits + start + slot);
-                        if (h >= db.max_ix) continue;
-                        if (FILL) out[n] = h;
-                        ++n; next = tp + SH_SKIP;
-                    }
-                }
-            } else {
-                for (uint32_t tp = 0; tp < nwin; ++tp) {
-                    if (tp < next) { tp = next - 1u; continue; }
-                    const uint32_t pos = strand ? nwin - 1u - tp : tp;
-                    const uint32_t h = __ldg(in.hits + start + (uint64_t)pos * nstr + strand);
-                    if (h >= db.max_ix) continue;
-                    if (FILL) out[n] = h;
-                    ++n; next = tp + SH_SKIP;
-                }
-            }
-        }
-        if (!FILL) sel_cnt[r] = n;
+        const uint32_t *src = sel_gap + (start >> 2);
+        uint32_t *dst = sel + sel_off[r];
+        for (uint32_t k = 0, n = sel_cnt[r]; k < n; ++k) dst[k] = src[k];
     }
 }
 
@@ -1912,7 +2051,7 @@ extern "C" int utb_db_device(const utb_db *db) { return db ? db->device : -1; }
 struct vote_scratch { VoteLong vl; unsigned n_cta; };
 static void vs_free(vote_scratch *vs) {
     cudaFree(vs->vl.hist); cudaFree(vs->vl.tlab); cudaFree(vs->vl.tcnt);
-    cudaFree(vs->vl.big_hist); cudaFree(vs->vl.big_tlab); cudaFree(vs->vl.big_tcnt); cudaFree(vs->vl.big_list); cudaFree(vs->vl.big_state);
+    cudaFree(vs->vl.big_hist); cudaFree(vs->vl.big_tlab); cudaFree(vs->vl.big_tcnt); cudaFree(vs->vl.big_list); cudaFree(vs->vl.big_state); cudaFree(vs->vl.work);
     memset(vs, 0, sizeof *vs);
 }
 // max_bytes: raw bytes a batch can hold -- a read of more than max_bytes / pool bases cannot occur more than pool times
@@ -1920,12 +2059,12 @@ static int vs_alloc(const utb_db *db, size_t max_bytes, vote_scratch *vs) {
     memset(vs, 0, sizeof *vs);
     const size_t nl = db->d.max_ix ? db->d.max_ix : 1;
     vs->n_cta = (unsigned)db->sm_count * VB_PER_SM;
-    size_t pool = ((size_t)96 << 20) / (12 * nl);
+    size_t pool = ((size_t)384 << 20) / (12 * nl);                 // at most 384 MB of histograms for the split reads of a batch
     if (pool > VBIG_POOL_MAX) pool = VBIG_POOL_MAX;
     if (pool < 1) pool = 1;
     vs->vl.pool = (uint32_t)pool;
-    size_t split_bases = max_bytes / pool + 1;
-    if (split_bases < ((size_t)256 << 10)) split_bases = (size_t)256 << 10;
+    size_t split_bases = max_bytes / pool + 1;                     // no more than `pool` reads of a batch can be longer than that
+    if (split_bases < ((size_t)64 << 10)) split_bases = (size_t)64 << 10;
     vs->vl.split_slots = 2ull * split_bases;
     const char *e = getenv("UTB_VOTE_SPLIT_SLOTS");                // tests: a small threshold sends short "long" reads through the split path
     if (e && atoll(e) > 0) vs->vl.split_slots = (unsigned long long)atoll(e);
@@ -1940,6 +2079,7 @@ static int vs_alloc(const utb_db *db, size_t max_bytes, vote_scratch *vs) {
     if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_tcnt, pool * nl * 4);
     if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_list, pool * 4);
     if (err == cudaSuccess) err = cudaMalloc(&vs->vl.big_state, (1 + 2 * pool) * 4);
+    if (err == cudaSuccess) err = cudaMalloc(&vs->vl.work, 4);
     if (err == cudaSuccess) err = cudaMemset(vs->vl.hist, 0, (size_t)vs->n_cta * nl * 4);      // the kernels leave the histograms zeroed
     if (err == cudaSuccess) err = cudaMemset(vs->vl.big_hist, 0, pool * nl * 4);
     if (err != cudaSuccess) { vs_free(vs); CK(err); }
@@ -1948,6 +2088,7 @@ static int vs_alloc(const utb_db *db, size_t max_bytes, vote_scratch *vs) {
 static int launch_long_vote(const utb_db *db, const VoteIn &in, utb_result *results, const uint32_t *gen_list, const uint32_t *gen_count,
                             vote_scratch *vs, unsigned long long *counters, cudaStream_t st) {
     CK(cudaMemsetAsync(vs->vl.big_state, 0, (1 + 2 * (size_t)vs->vl.pool) * 4, st));
+    CK(cudaMemsetAsync(vs->vl.work, 0, 4, st));
     vote_block_kernel<<<vs->n_cta, VB_THREADS, 0, st>>>(db->d, in, results, gen_list, gen_count, vs->vl, counters);
     vote_big_count_kernel<<<(unsigned)db->sm_count * 4, VB_THREADS, 0, st>>>(db->d, in, vs->vl);
     vote_big_finish_kernel<<<vs->vl.pool < (uint32_t)db->sm_count ? vs->vl.pool : (unsigned)db->sm_count, VB_THREADS, 0, st>>>(db->d, vs->vl, results, counters);
@@ -1977,7 +2118,7 @@ struct utb_batch {
     int want_text; cudaEvent_t text_len_ready; size_t text_prefetched;
     unsigned long long *d_counters;   // [4][COUNTER_SLOTS]: lookups, hits, good finds, exact-path sectors (summed on the host)
     vote_scratch vs;
-    uint32_t *d_sel_cnt, *d_sel_off, *d_sel, *d_sel_total, *h_sel_cnt, *h_sel, *h_sel_total; size_t sel_cap;   // non-GG mode (want_text == 3)
+    uint32_t *d_sel_cnt, *d_sel_off, *d_sel, *d_sel_gap, *d_sel_total, *h_sel_cnt, *h_sel, *h_sel_total; size_t sel_cap;   // non-GG mode (want_text == 3)
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
     // last submit
@@ -2012,7 +2153,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     cudaFree(b->d_pk); cudaFree(b->d_bad); cudaFree(b->d_hits); cudaFree(b->d_results); cudaFree(b->d_pkr);
     cudaFree(b->d_gen_list); cudaFree(b->d_gen_count); cudaFree(b->d_warp_list); cudaFree(b->d_warp_count); cudaFree(b->d_counters);
     vs_free(&b->vs);
-    cudaFree(b->d_sel_cnt); cudaFree(b->d_sel_off); cudaFree(b->d_sel); cudaFree(b->d_sel_total);
+    cudaFree(b->d_sel_cnt); cudaFree(b->d_sel_off); cudaFree(b->d_sel); cudaFree(b->d_sel_gap); cudaFree(b->d_sel_total);
     cudaFreeHost(b->h_sel_cnt); cudaFreeHost(b->h_sel); cudaFreeHost(b->h_sel_total);
     cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
     cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFreeHost(b->h_frame_err);
@@ -2167,11 +2308,11 @@ static int launch_stages(utb_batch *b, bool timed) {
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
         in.hitmap = b->used_sieve ? b->d_hitmap : nullptr;
         const uint32_t nt = (n_reads + SCAN_TILE - 1) / SCAN_TILE;
-        shallow_select_kernel<false><<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(d, in, n_reads, b->dims_dev, b->d_sel_cnt, nullptr, nullptr);
+        shallow_select_kernel<<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(d, in, b->d_pk, b->d_bad, n_reads, b->dims_dev, b->d_sel_cnt, b->d_sel_gap);
         scan_sums_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_sel_cnt, n_reads, b->dims_dev, nt, b->d_scan_sums);
         scan_top_kernel<<<1, 1024, 0, b->st>>>(b->d_scan_sums, nt, b->d_sel_total);
         scan_apply_kernel<<<gs_grid(b, nt, 1, 8), 256, 0, b->st>>>(b->d_sel_cnt, n_reads, b->dims_dev, nt, b->d_scan_sums, b->d_sel_off);
-        shallow_select_kernel<true><<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(d, in, n_reads, b->dims_dev, nullptr, b->d_sel_off, b->d_sel);
+        shallow_compact_kernel<<<gs_grid(b, n_reads, 128, 32), 128, 0, b->st>>>(in, n_reads, b->dims_dev, b->d_sel_cnt, b->d_sel_off, b->d_sel_gap, b->d_sel);
         b->launches += 5;
     } else if (n_reads) {
         VoteIn in;
@@ -2376,8 +2517,9 @@ static int ensure_chunk_buffers(utb_batch *b) {
 }
 static int ensure_shallow_buffers(utb_batch *b) {
     if (b->d_sel) return UTB_OK;
-    // a read keeps at most one hit per 8 windows and strand (+ 1 each)
-    b->sel_cap = (size_t)b->max_groups * 32 / 4 + 2 * b->max_reads + 64;
+    // a kept hit uses up >= 8 text positions: a quarter of the lookup slots is room for every read's ids
+    b->sel_cap = (size_t)b->max_groups * 32 * 2 / 4 + 64;
+    CK(cudaMalloc(&b->d_sel_gap, b->sel_cap * 4));
     CK(cudaMalloc(&b->d_sel_cnt, (b->max_reads + 1) * 4));
     CK(cudaMalloc(&b->d_sel_off, (b->max_reads + 1) * 4));
     CK(cudaMalloc(&b->d_sel, b->sel_cap * 4));
