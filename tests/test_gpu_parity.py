@@ -568,3 +568,45 @@ def test_shallow_cli_binary(ctrs, tmp_path):
     if os.path.exists(ref):
         q = subprocess.run([ref, ctrs["toyA"], gold("toyA_reads.fa"), out + ".ref", "2", "RC"], capture_output=True, text=True)
         assert q.stdout == p.stdout
+
+
+# ---- utree-build_gg on the GPU ---------------------------------------------------------------------
+BUILD_CASES = [
+    # name, make_genomes kwargs, complevel, ix_bytes, golden .ubt made by the reference builder (scripts/make_golden.py)
+    ("toyA", dict(seed=11, n_phyla=2, n_genera=2, n_species=2, n_strains=2, length=4000), 0, 2, "toyA.ubt"),
+    ("toyB", dict(seed=21, n_phyla=3, n_genera=2, n_species=2, n_strains=2, length=6000, quirky_tax=True), 1, 4, "toyB_u32.ubt"),
+    ("mid2", dict(seed=5, n_phyla=3, n_genera=3, n_species=3, n_strains=2, length=30000), 2, 2, None),
+    ("mid4", dict(seed=6, n_phyla=2, n_genera=3, n_species=2, n_strains=3, length=60000, quirky_tax=True), 4, 2, None),
+]
+
+
+@pytest.mark.parametrize("name,kw,complevel,ix_bytes,golden", BUILD_CASES)
+def test_gpu_builder_is_byte_identical_to_the_reference_builder(built, tmp_path, name, kw, complevel, ix_bytes, golden):
+    """FASTA + map -> .ubt on the GPU: the bytes the reference's serial builder writes (words, label ids in its
+    order of registration incl. superseded derived labels, counts, .gg.log), against the committed .ubt fixtures
+    and, where oracle/_ref is present, against the reference builder run live on the same input."""
+    from tools import synth
+    from utree_b200 import capi
+    genomes = synth.make_genomes(**kw)
+    fa, mp, out = str(tmp_path / "g.fa"), str(tmp_path / "g.map"), str(tmp_path / "ours.ubt")
+    synth.write_fasta_and_map(genomes, fa, mp)
+    rc, ex, st = capi.build_ubt(fa, mp, out, complevel=complevel, gg=True, ix_bytes=ix_bytes)
+    assert rc == 0, capi.lib().utb_last_error()
+    got = open(out, "rb").read()
+    assert st["records"] == int.from_bytes(got[24:32], "little") > 0
+    if golden:
+        assert got == open(gold(golden), "rb").read()
+    ref = os.path.join(ROOT, "oracle", "_ref", "utree-build_gg" + ("_u32" if ix_bytes == 4 else ""))
+    if os.path.exists(ref):
+        rout = str(tmp_path / "ref.ubt")
+        q = subprocess.run([ref, fa, mp, rout, "1", str(complevel)], capture_output=True, text=True)
+        assert q.returncode == 0
+        assert got == open(rout, "rb").read()
+        assert open(out + ".gg.log", "rb").read() == open(rout + ".gg.log", "rb").read()
+        if ix_bytes == 2:                                           # the CLI: same stdout lines
+            env = dict(os.environ)
+            p = subprocess.run([os.path.join(ROOT, "bin", "utree-build_gg"), fa, mp, out + "2", "1", str(complevel)], capture_output=True, text=True, env=env)
+            assert p.returncode == 0 and open(out + "2", "rb").read() == got
+            assert p.stdout == q.stdout
+    else:
+        assert golden, "neither a golden .ubt nor oracle/_ref to compare with"

@@ -185,6 +185,19 @@ def compress_ubt(ubt_path, ctr_path):
     return n.value, nl.value
 
 
+class BuildStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("map_bytes", "map_lines", "sequences", "kmers_seen", "kmers_made", "records")] + [("labels", C.c_uint32)]
+
+
+def build_ubt(fasta, map_path, out, complevel=1, gg=True, ix_bytes=2, device=0):
+    """utree-build_gg on the GPU (utb_build_ubt).  Returns (rc, ref_exit, stats dict)."""
+    st, ex = BuildStats(), C.c_int()
+    L = lib()
+    L.utb_build_ubt.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.POINTER(BuildStats), C.POINTER(C.c_int)]
+    rc = L.utb_build_ubt(os.fsencode(fasta), os.fsencode(map_path), os.fsencode(out), complevel, int(gg), ix_bytes, device, C.byref(st), C.byref(ex))
+    return rc, ex.value, {n: getattr(st, n) for n, _ in st._fields_}
+
+
 def device_count():
     n = C.c_int()
     _ck(lib().utb_device_count(C.byref(n)))
