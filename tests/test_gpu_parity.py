@@ -533,7 +533,7 @@ def test_shallow_search_across_batches_and_lookup_variants(gpu, tmp_path, env):
     restatement of the non-GG binary (itself pinned by the golden files) gives the expected bytes."""
     from utree_b200 import capi
     ctr, db, orc = gpu["toyA"]
-    data = (open(gold("shallow_reads.fa"), "rb").read() + open(gold("toyA_reads.fa"), "rb").read() + open(gold("long_reads.fa"), "rb").read()) * 40
+    data = (open(gold("shallow_reads.fa"), "rb").read() + open(gold("toyA_reads.fa"), "rb").read() + open(gold("long_reads.fa"), "rb").read()) * 110   # 42 MB
     fa, want = str(tmp_path / "in.fa"), str(tmp_path / "want.out")
     open(fa, "wb").write(data)
     rc, st, err = orc.search_file_shallow(fa, want, do_rc=True)

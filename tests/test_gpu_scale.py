@@ -159,3 +159,48 @@ def test_long_and_whole_genome_queries_match_reference(bench_mod, tmp_path):
     assert got == want
     assert want.count(b"\n") == len(recs)
     print(f"long queries: {sum(len(s) for _, s in recs) / 1e6:.1f} Mb, reference {t_ref:.1f} s (incl. load), ours {st['seconds_total']:.2f} s")
+
+
+def test_tree_with_more_than_2_32_records(bench_mod):
+    """4,295,000,000 records: the CTR carries 8-byte prefix-index entries (itree.c:757, 1303) and record indices
+    beyond 32 bits.  Content is closed-form (tools/synth.cu big_word), so members, their labels and non-members
+    are known by arithmetic; both device paths -- the sector hash table (+ sieve) built from the index, and the
+    reference probe sequence on the on-disk image -- must agree with it."""
+    import shutil
+    from tools import synthgpu
+    from utree_b200 import capi
+    wd = bench_mod.work_dir()
+    n, n_labels = 4_295_000_000, 1000
+    if shutil.disk_usage(wd).free < 40 * 10 ** 9:
+        pytest.skip("not enough room in " + wd)
+    path = os.path.join(wd, "big64.ctr")
+    try:
+        synthgpu.build_big_ctr(path, n, n_labels)
+        ctr = capi.Ctr(path)
+        assert ctr.binix_bytes == 8 and ctr.num_nodes == n and ctr.max_ix == n_labels
+        rng = np.random.default_rng(3)
+        idx = np.concatenate([np.array([0, 1, 2, 2 ** 32 - 2, 2 ** 32 - 1, 2 ** 32, 2 ** 32 + 1, n - 2, n - 1], dtype=np.uint64),
+                              rng.integers(0, n, 300_000, dtype=np.uint64), rng.integers(2 ** 32, n, 50_000, dtype=np.uint64)])
+        words, labels = synthgpu.big_ctr_word_label(idx, n, n_labels)
+        nxt, _ = synthgpu.big_ctr_word_label(np.minimum(idx + np.uint64(1), np.uint64(n - 1)), n, n_labels)
+        strangers = words + np.uint64(1)
+        ok = strangers != nxt                                       # word + 1 is a member only if it is the next record
+        q = np.concatenate([words, strangers[ok]])
+        want = np.concatenate([labels, np.full(int(ok.sum()), 0xFFFFFFFF, dtype=np.uint32)])
+        for env in ({}, {"UTB_LOOKUP": "exact"}):
+            os.environ.update(env)
+            try:
+                db = capi.Db(ctr, 0)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            try:
+                assert db.lookup_mode() == (0 if env else 1)
+                got = db.lookup_words(q)
+                assert np.array_equal(got, want), (env, int((got != want).sum()))
+            finally:
+                db.free()
+        ctr.close()
+    finally:
+        if os.path.exists(path):
+            os.remove(path)

@@ -439,6 +439,70 @@ extern "C" int uts_make_long_reads(int device, uint64_t seed, uint32_t n_phyla, 
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// a CTR with >= 2^32 - 1 records (8-byte BinIx entries, itree.c:757, 1303): closed-form content, so that lookups
+// can be checked against arithmetic instead of a second 30 GB copy in the checker
+// ---------------------------------------------------------------------------
+// word(i) = i * S + mix64(i) % S with S = floor(2^64 / n): strictly increasing; label(i) = mix64(i ^ 0x5555) % n_labels.
+__host__ __device__ inline uint64_t big_word(uint64_t i, uint64_t S) { return i * S + mix64(i) % S; }
+__global__ void __launch_bounds__(256)
+big_records_kernel(uint64_t i0, uint64_t count, uint64_t S, uint32_t n_labels, uint8_t *__restrict__ out) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const uint64_t i = i0 + k, w = big_word(i, S);
+    const uint32_t lab = (uint32_t)(mix64(i ^ 0x5555ull) % n_labels);
+    uint8_t *r = out + k * 7;
+    for (int b = 0; b < 5; ++b) r[b] = (uint8_t)(w >> (8 * b));
+    r[5] = (uint8_t)lab; r[6] = (uint8_t)(lab >> 8);
+}
+__global__ void __launch_bounds__(256)
+big_binix_kernel(uint64_t n, uint64_t S, uint64_t *__restrict__ binix) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > (1ull << 24)) return;
+    if (p == (1ull << 24)) { binix[p] = n; return; }
+    const uint64_t T = p << 40, c = T / S;                          // first record whose word is >= T
+    uint64_t f = c < n && big_word(c, S) >= T ? c : c + 1;
+    binix[p] = f < n ? f : n;
+}
+extern "C" int uts_build_big_ctr(int device, uint64_t n, uint32_t n_labels, const char *out_path) {
+    if (!out_path || n < 2 || !n_labels || n_labels > 65000) { snprintf(g_err, sizeof g_err, "bad argument"); return 1; }
+    SCK(cudaSetDevice(device));
+    const uint64_t S = ~0ull / n;
+    FILE *f = fopen(out_path, "wb");
+    if (!f) { snprintf(g_err, sizeof g_err, "cannot open %s", out_path); return 2; }
+    int rc = 0;
+    const uint64_t md[4] = {8, 0, 2, n};
+    rc |= fwrite(md, 8, 4, f) != 4;
+    {
+        uint64_t *d_b;
+        SCK(cudaMalloc(&d_b, ((1ull << 24) + 1) * 8));
+        big_binix_kernel<<<(unsigned)(((1ull << 24) + 1 + 255) / 256), 256>>>(n, S, d_b);
+        SCK(cudaGetLastError());
+        std::vector<uint64_t> h((1ull << 24) + 1);
+        SCK(cudaMemcpy(h.data(), d_b, h.size() * 8, cudaMemcpyDeviceToHost));
+        cudaFree(d_b);
+        if (n < 0xFFFFFFFFull) { std::vector<uint32_t> h32(h.begin(), h.end()); rc |= fwrite(h32.data(), 4, h32.size(), f) != h32.size(); }
+        else rc |= fwrite(h.data(), 8, h.size(), f) != h.size();
+    }
+    {
+        const uint64_t STEP = (uint64_t)32 << 20;                   // records per chunk
+        uint8_t *d; void *hbuf;
+        SCK(cudaMalloc(&d, STEP * 7)); SCK(cudaMallocHost(&hbuf, STEP * 7));
+        for (uint64_t i0 = 0; i0 < n && !rc; i0 += STEP) {
+            const uint64_t c = n - i0 < STEP ? n - i0 : STEP;
+            big_records_kernel<<<(unsigned)((c + 255) / 256), 256>>>(i0, c, S, n_labels, d);
+            SCK(cudaGetLastError());
+            SCK(cudaMemcpy(hbuf, d, c * 7, cudaMemcpyDeviceToHost));
+            rc |= fwrite(hbuf, 7, c, f) != c;
+        }
+        cudaFree(d); cudaFreeHost(hbuf);
+    }
+    for (uint32_t l = 0; l < n_labels && !rc; ++l) rc |= fprintf(f, "k__K;p__P%u;c__C%u\t1\n", l % 97, l) < 0;
+    if (fclose(f)) rc = 1;
+    if (rc) snprintf(g_err, sizeof g_err, "write error on %s", out_path);
+    return rc ? 2 : 0;
+}
+
 // One genome as ASCII (for building toy trees with the reference builder and
 // for cross-checking base_of on the host).
 extern "C" void uts_genome_ascii(uint64_t seed, uint32_t n_phyla, uint32_t n_genera, uint32_t n_species,

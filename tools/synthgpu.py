@@ -31,6 +31,34 @@ def lib():
     return _lib
 
 
+M64 = (1 << 64) - 1
+
+
+def _mix64(x):
+    """tools/synth.cu mix64 on numpy uint64 arrays."""
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def build_big_ctr(path, n_records, n_labels=1000, device=0):
+    """A CTR with closed-form content (word(i) = i * S + mix64(i) % S, label(i) = mix64(i ^ 0x5555) % n_labels): for trees of
+    >= 2^32 - 1 records (8-byte prefix index) that no second copy in RAM has to vouch for."""
+    lib().uts_build_big_ctr.argtypes = [C.c_int, C.c_uint64, C.c_uint32, C.c_char_p]
+    rc = lib().uts_build_big_ctr(device, n_records, n_labels, os.fsencode(path))
+    if rc:
+        raise RuntimeError("uts_build_big_ctr: " + lib().uts_last_error().decode())
+
+
+def big_ctr_word_label(i, n_records, n_labels=1000):
+    """word(i), label(i) of build_big_ctr for an array of record indices."""
+    i = np.ascontiguousarray(i, dtype=np.uint64)
+    S = np.uint64(M64 // n_records)
+    with np.errstate(over="ignore"):
+        return i * S + _mix64(i) % S, (_mix64(i ^ np.uint64(0x5555)) % np.uint64(n_labels)).astype(np.uint32)
+
+
 class Universe:
     """n_phyla x n_genera x n_species x n_strains genomes of genome_len bases."""
 

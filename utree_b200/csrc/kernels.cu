@@ -124,15 +124,28 @@ pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_of
             uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ dims,
             uint64_t *__restrict__ pk, uint32_t *__restrict__ bad, uint64_t *__restrict__ pkr) {
     if (dims) { n_reads = dims[0]; n_groups = dims[1]; }          // device-side framing: the host only knows upper bounds
-    for (uint64_t g64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g64 < (uint64_t)n_groups + PK_GUARD; g64 += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t g = (uint32_t)g64;
-        if (g >= n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; continue; }   // guard groups: all positions bad
-        // read owning group g: largest r with grp_off[r] <= g
-        uint32_t lo = 0, hi = n_reads;                     // invariant: grp_off[lo] <= g < grp_off[hi]
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(grp_off + mid) <= g) lo = mid; else hi = mid;
+    const uint32_t lane = threadIdx.x & 31u;
+    // a warp takes 32 consecutive groups per round (warp-uniform loop)
+    for (uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ull; gw < (uint64_t)n_groups + PK_GUARD; gw += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)gw + lane;
+        // read owning the warp's first group: largest r with grp_off[r] <= g0 (one bisection per warp); every read owns
+        // >= 1 group, so the reads of the other 31 groups start at one of the next 31 boundaries: a coalesced load of
+        // those, a warp-wide OR of "a read starts at group g0 + j", and a population count give each lane its read
+        uint32_t lo = 0;
+        const uint32_t g0 = (uint32_t)gw;
+        if (g0 < n_groups) {
+            uint32_t hi = n_reads;                             // invariant: grp_off[lo] <= g0 < grp_off[hi]
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(grp_off + mid) <= g0) lo = mid; else hi = mid;
+            }
+            const uint32_t nb = lo + 1u + lane;                // boundary held by this lane
+            const uint32_t bnd = nb < n_reads ? __ldg(grp_off + nb) : 0xFFFFFFFFu;
+            const uint32_t starts = __reduce_or_sync(0xFFFFFFFFu, bnd - g0 < 32u ? 1u << (bnd - g0) : 0u);
+            lo += __popc(starts & (0xFFFFFFFFu >> (31u - lane)));   // boundaries at groups g0 + 1 .. g0 + lane
         }
+        if (g >= n_groups + PK_GUARD) continue;
+        if (g >= n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; continue; }   // guard groups: all positions bad
         uint32_t k = g - __ldg(grp_off + lo);
         uint32_t len = __ldg(seq_len + lo);
         uint32_t b0 = k * 32u;
