@@ -7,10 +7,7 @@ import bench
 from utree_b200 import capi
 cfg = dict(bench.CONFIGS["l2s"]); n = int(os.environ.get("E2E_READS", "10000000")); reps = int(os.environ.get("E2E_REPS", "3"))
 ctr_path, _ = bench.ensure_ctr("l2s", cfg, 0)
-rec = 12 + cfg["read_len"] + 1
-pinned = torch.empty(n * rec, dtype=torch.uint8, pin_memory=True)
-reads = pinned.numpy()
-bench.make_reads(cfg, 0, n, 0, out=reads)
+reads, _ = bench.make_reads(cfg, 0, n, 0, pin=True)
 ctr = capi.Ctr(ctr_path)
 s = capi.Searcher(ctr, devices=(0,), host_threads=int(os.environ.get("E2E_THREADS", os.cpu_count())))
 for i in range(reps):
