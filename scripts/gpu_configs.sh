@@ -12,6 +12,6 @@ d=json.load(open('gpurun_out/${T}_bench_$c.json'))
 print('$c', 'value', d['value'], 'ms', d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_step'], 'bases/s', d.get('bases_per_s'), 'lookups/s', d['lookups_per_s'])
 print('   stage', d['roofline']['stage_ms'], d['roofline']['phase_a_ms'], 'surv', d['roofline']['lookup_stage']['survivor_kernel_ms'], 'hit_rate', d['hit_rate'])
 print('   cpu', d.get('cpu_baseline'))
-print('   file', d.get('e2e_file'), 'pageable', d.get('e2e_pageable'), 'parity', d.get('parity'))
+print('   file', d.get('e2e_file'), 'cli', d.get('e2e_cli'), 'pageable', d.get('e2e_pageable'), 'parity', d.get('parity'))
 E
 done

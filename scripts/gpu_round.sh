@@ -18,7 +18,7 @@ print(d['value'], d['ms_per_step'], 'e2e', d['e2e']['value'], d['e2e']['ms_per_s
 print(d['roofline']['stage_ms'], d['roofline']['phase_a_ms'], d['roofline']['lookup_stage'])
 print(d['roofline']['kernels'])
 print(d['e2e']['host_phase_s'])
-print('file', d.get('e2e_file'), 'pageable', d.get('e2e_pageable'), 'parity', d.get('parity'), 'cpu', d.get('cpu_baseline'))
+print('file', d.get('e2e_file'), 'cli', d.get('e2e_cli'), 'pageable', d.get('e2e_pageable'), 'parity', d.get('parity'), 'cpu', d.get('cpu_baseline'))
 E
 [ -n "$SKIP_NCU" ] && exit 0
 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/${T}_launches.csv \

@@ -130,6 +130,45 @@ def test_search_file_matches_reference(gpu, tmp_path, db_name, reads, out, rc):
         s.destroy()
 
 
+def test_file_sinks_mapping_pwrite_and_fifo_agree(gpu, tmp_path, monkeypatch):
+    """The three ways a file sink is written (shared mapping on a memory file system, parallel pwrite,
+    sequential write into something that cannot seek) produce the same bytes, over several batches."""
+    import threading
+    from utree_b200 import capi
+    ctr = gpu["toyA"][0]
+    one = open(gold("toyA_reads.fa"), "rb").read()
+    reads = one * (72_000_000 // len(one) + 1)                      # the smallest batch holds one maximal record (2 x 16 MiB)
+    fa = tmp_path / "in.fa"
+    fa.write_bytes(reads)
+    shm = "/dev/shm/utb_test_%d.out" % os.getpid()
+    monkeypatch.setenv("UTB_BATCH_MB", "1")
+    s = capi.Searcher(ctr, devices=(0,), host_threads=3)
+    try:
+        code, _, want, st0 = s.search_mem(reads, do_rc=True)
+        assert code == 0 and st0["batches"] >= 2 and want.count(b"\n") > 1000
+        for mode, target in (("1", shm), ("0", shm), (None, str(tmp_path / "o.txt"))):
+            if mode is None:
+                monkeypatch.delenv("UTB_OUT_MMAP", raising=False)
+            else:
+                monkeypatch.setenv("UTB_OUT_MMAP", mode)
+            open(target, "wb").write(b"stale" * 1000)               # an existing longer file must end up truncated
+            code, ref_exit, st = s.search_file(str(fa), target, do_rc=True)
+            assert code == 0 and ref_exit == 0
+            assert open(target, "rb").read() == want, (mode, target)
+        fifo = str(tmp_path / "pipe")
+        os.mkfifo(fifo)
+        got = []
+        t = threading.Thread(target=lambda: got.append(open(fifo, "rb").read()))
+        t.start()
+        code, ref_exit, st = s.search_file(str(fa), fifo, do_rc=True)
+        t.join(60)
+        assert code == 0 and got and got[0] == want
+    finally:
+        s.destroy()
+        if os.path.exists(shm):
+            os.remove(shm)
+
+
 def test_search_counts_match_oracle(gpu, tmp_path):
     from utree_b200 import capi
     ctr, db, orc = gpu["toyA"]

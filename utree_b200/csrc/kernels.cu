@@ -747,16 +747,17 @@ __device__ __forceinline__ uint32_t cutoff_of(uint32_t x) {   // itree.c:1044-10
 // scalar state, the character scans are done 32 bytes at a time with ballots.
 // T_lab/T_cnt: the distinct labels of the read in strcmp order with counts
 // (shared or global memory).
+// S / S_off: the label strings of T_lab[0 .. uix) staged back to back (string z at S + S_off[z]), or null: read from the blob
 __device__ void walk_warp(const DevDB &db, const uint32_t *T_lab, const uint32_t *T_cnt,
-                          uint32_t uix, uint32_t n, utb_result *out) {
+                          uint32_t uix, uint32_t n, utb_result *out, const char *S = nullptr, const uint32_t *S_off = nullptr) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t EMPTY = 0xFFFFFFFFu;
     uint32_t cutoff = cutoff_of(n), st = 0, ed = uix, dv = EMPTY, orun = n, sl = 0, ol = 0;
     for (;;) {                                                      // itree.c:1047
         uint32_t run = T_cnt[st], td = dv;
         for (uint32_t z = st + 1; z < ed; ++z) {                    // itree.c:1050
-            const char *s1 = db.blob + __ldg(db.off + T_lab[z - 1]);
-            const char *s2 = db.blob + __ldg(db.off + T_lab[z]);
+            const char *s1 = S ? S + S_off[z - 1] : db.blob + __ldg(db.off + T_lab[z - 1]);
+            const char *s2 = S ? S + S_off[z] : db.blob + __ldg(db.off + T_lab[z]);
             if (!s1[dv + (dv == EMPTY)]) {                          // itree.c:1052
                 run = T_cnt[z]; st = z;
                 orun -= T_cnt[z - 1];
@@ -1156,14 +1157,29 @@ __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn 
     uint32_t n_local = 0;
     if (in.hitmap) {
         const uint32_t *hm = in.hitmap + (start >> 5);             // start is a multiple of 32
+        // a long read's hits name its own lineage over and over: each thread keeps the two labels it met last in
+        // registers and only sends a (label, count) pair on when a third one displaces it -- every thread of the
+        // CTA hammering the same two shared-memory words was what this loop spent its time on
+        uint32_t l0 = UTB_BAD32, c0 = 0, l1 = UTB_BAD32, c1 = 0;
+        uint32_t m_next = w0 + tid < w1 ? __ldg(hm + w0 + tid) : 0u;
         for (uint64_t wi = w0 + tid; wi < w1; wi += VB_THREADS) {
-            uint32_t m = __ldg(hm + wi);
+            uint32_t m = m_next;
+            m_next = wi + VB_THREADS < w1 ? __ldg(hm + wi + VB_THREADS) : 0u;
             while (m) {
                 const uint32_t bit = __ffs(m) - 1; m &= m - 1;
                 const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
-                if (h < db.max_ix) { vl_add(cache, h, 1u, hist, tlab, nt); ++n_local; }
+                if (h >= db.max_ix) continue;
+                ++n_local;
+                if (h == l0) ++c0;
+                else if (h == l1) ++c1;
+                else {
+                    if (c1) vl_add(cache, l1, c1, hist, tlab, nt);
+                    l1 = l0; c1 = c0; l0 = h; c0 = 1;
+                }
             }
         }
+        if (c0) vl_add(cache, l0, c0, hist, tlab, nt);
+        if (c1) vl_add(cache, l1, c1, hist, tlab, nt);
     } else {
         const uint64_t lo = w0 * 32u, hi = w1 * 32u < count ? w1 * 32u : count;
         for (uint64_t base = lo; base < hi; base += VB_THREADS) {
@@ -1178,9 +1194,55 @@ __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn 
     return n_local;
 }
 struct VlSmem { unsigned long long key[VB_SORT_MAX]; uint32_t warp[VB_THREADS / 32]; uint32_t base; };
+// The walk compares neighbouring label strings level by level: a chain of dependent loads (label id -> offset ->
+// characters) per comparison, ~2 us each from global memory with one warp at work -- 250 us for a read that touched a
+// hundred labels, which is what the long-query vote spent its time on.  So the whole CTA first stages ids, counts
+// and strings in shared memory (the sort keys' space is free by then), and the walk runs on that copy.
+#define VL_STAGE_MAX 512u           // labels
+#define VL_STR_BYTES 24576u         // their strings, NULs included
+struct VlStage { uint32_t off[VL_STAGE_MAX + 1], lab[VL_STAGE_MAX], cnt[VL_STAGE_MAX]; };
+static_assert(sizeof(VlStage) <= sizeof(unsigned long long) * VB_SORT_MAX, "VlStage lives in VlSmem::key");
+// block-wide; false (block-uniform): too many labels or bytes, walk from global memory
+__device__ bool vl_stage(const DevDB &db, const uint32_t *tlab, const uint32_t *tcnt, uint32_t uix, VlSmem &sm, char *str) {
+    if (uix > VL_STAGE_MAX) return false;
+    VlStage *sg = reinterpret_cast<VlStage *>(sm.key);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+    for (uint32_t i = tid; i < uix; i += VB_THREADS) { sg->lab[i] = tlab[i]; sg->cnt[i] = tcnt[i]; }
+    for (uint32_t i = wid; i < uix; i += VB_THREADS / 32) {        // lengths, NUL included: a warp per label
+        const char *p = db.blob + __ldg(db.off + tlab[i]);
+        uint32_t t0 = 0, len;
+        for (;;) {
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, p[t0 + lane] == 0);   // the blob is padded: reading on past the NUL is fine
+            if (m) { len = t0 + (uint32_t)__ffs(m); break; }
+            t0 += 32u;
+        }
+        if (lane == 0) sg->off[i + 1] = len;
+    }
+    __syncthreads();
+    if (wid == 0) {                                                // lengths -> offsets
+        uint32_t carry = 0;
+        for (uint32_t base = 0; base < uix; base += 32u) {
+            const uint32_t i = base + lane;
+            uint32_t v = i < uix ? sg->off[i + 1] : 0u;
+            for (uint32_t o = 1; o < 32u; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o); if (lane >= o) v += t; }
+            if (i < uix) sg->off[i + 1] = carry + v;
+            carry += __shfl_sync(0xFFFFFFFFu, v, 31);
+        }
+        if (lane == 0) { sg->off[0] = 0; sm.base = carry; }
+    }
+    __syncthreads();
+    if (sm.base + 32u > VL_STR_BYTES) return false;                // the walk reads up to 31 bytes past a NUL
+    for (uint32_t i = wid; i < uix; i += VB_THREADS / 32) {
+        const char *p = db.blob + __ldg(db.off + sg->lab[i]);
+        const uint32_t a = sg->off[i], len = sg->off[i + 1] - a;
+        for (uint32_t j = lane; j < len; j += 32u) str[a + j] = p[j];
+    }
+    __syncthreads();
+    return true;
+}
 // hist holds the label counts of one read, tlab[0 .. nt) the labels touched (any order), n the hits.  Block-wide.
 __device__ void vl_finish(const DevDB &db, uint32_t *hist, uint32_t *tlab, uint32_t *tcnt, uint32_t nt, uint32_t n, uint32_t sort_max,
-                          utb_result *out, unsigned long long *__restrict__ counters, VlSmem &sm) {
+                          utb_result *out, unsigned long long *__restrict__ counters, VlSmem &sm, char *str) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
     if (n == 0) {                                                  // block-uniform
         if (tid == 0) { out->kind = UTB_NONE; out->label = 0; out->cut = 0; out->found = 0; out->uix = 0; out->sl = 0; out->ol = 0; out->_pad = 0; }
@@ -1243,10 +1305,14 @@ __device__ void vl_finish(const DevDB &db, uint32_t *hist, uint32_t *tlab, uint3
     }
     __threadfence();
     __syncthreads();
+    const bool staged = uix > 1 && vl_stage(db, tlab, tcnt, uix, sm, str);
     if (wid == 0) {
         if (lane == 0) atomicAdd(counters + 2 * COUNTER_SLOTS + (blockIdx.x & (COUNTER_SLOTS - 1)), 1ull);   // good finds (itree.c:1029)
         if (uix == 1) {                                            // itree.c:1031-1032, 1039-1040
             if (lane == 0) { out->kind = UTB_STAR; out->label = tlab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
+        } else if (staged) {
+            const VlStage *sg = reinterpret_cast<const VlStage *>(sm.key);
+            walk_warp(db, sg->lab, sg->cnt, uix, n, out, str, sg->off);
         } else walk_warp(db, tlab, tcnt, uix, n, out);
     }
     __syncthreads();
@@ -1257,6 +1323,7 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
                   VoteLong vl, unsigned long long *__restrict__ counters) {
     __shared__ VlSmem sm;
     __shared__ VlCache cache;
+    __shared__ char str[VL_STR_BYTES];
     __shared__ uint32_t s_nt, s_n, s_big, s_qi;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint32_t *hist = vl.hist + (size_t)blockIdx.x * db.max_ix;
@@ -1288,7 +1355,7 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
         __syncthreads();
         vl_flush(cache, hist, tlab, &s_nt);
         __syncthreads();
-        vl_finish(db, hist, tlab, tcnt, s_nt, s_n, vl.sort_max, results + r, counters, sm);
+        vl_finish(db, hist, tlab, tcnt, s_nt, s_n, vl.sort_max, results + r, counters, sm, str);
     }
 }
 __global__ void __launch_bounds__(VB_THREADS)
@@ -1322,10 +1389,11 @@ vote_big_count_kernel(DevDB db, VoteIn in, VoteLong vl) {
 __global__ void __launch_bounds__(VB_THREADS)
 vote_big_finish_kernel(DevDB db, VoteLong vl, utb_result *__restrict__ results, unsigned long long *__restrict__ counters) {
     __shared__ VlSmem sm;
+    __shared__ char str[VL_STR_BYTES];
     const uint32_t n_big = min(*vl.big_state, vl.pool);
     for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x)
         vl_finish(db, vl.big_hist + (size_t)bi * db.max_ix, vl.big_tlab + (size_t)bi * db.max_ix, vl.big_tcnt + (size_t)bi * db.max_ix,
-                  vl.big_state[1 + 2 * bi], vl.big_state[2 + 2 * bi], vl.sort_max, results + vl.big_list[bi], counters, sm);
+                  vl.big_state[1 + 2 * bi], vl.big_state[2 + 2 * bi], vl.sort_max, results + vl.big_list[bi], counters, sm, str);
 }
 
 // ---------------------------------------------------------------------------

@@ -29,6 +29,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/vfs.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -50,7 +51,7 @@ int utb_batch_wait_shallow(utb_batch *b, const uint32_t **sel_cnt, const uint32_
 int utb_pinned_alloc(size_t n, void **out);
 void utb_pinned_free(void *p);
 
-#define SLOTS_PER_DEVICE 6                         /* measured on B200: 3 slots 89 ms, 4 slots 78 ms, 6 slots 71 ms per 10 M reads */
+#define SLOTS_PER_DEVICE 4                         /* measured on B200, ms per 10 M reads (profiles/r02_e2e_sweep.txt): 2 slots 42.9, 3: 36.0, 4: 35.5, 5: 38.0, 6: 37.6 */
 #define DEFAULT_BATCH_BYTES ((size_t)128 << 20)   /* ~2.3 ms of PCIe per batch: launch and sync costs are a few percent of that */
 #define RAMP_BYTES ((size_t)32 << 20)              /* first / last batches: small, so the pipeline fills and drains fast */
 #define MAX_TEAM 64
@@ -279,15 +280,72 @@ static ssize_t src_fill(source_t *s, team_t *team, char *dst, size_t cap) {
  * final place in it (utb_batch_text_to): no staging buffer, no host memcpy.  The arena is kept for the next
  * search of this searcher (page-locking ~1 GB costs far more than a search). */
 typedef struct {
-    int fd;                 /* >= 0: file sink (pwrite at off); < 0: memory sink */
+    int fd;                 /* >= 0: file sink; < 0: memory sink */
     utb_searcher *s;
     size_t off;             /* bytes emitted so far */
     size_t hint;            /* expected output size (first allocation) */
     int failed;
+    /* file sinks.  stream: not seekable (pipe, tty): plain sequential write().  mapped: a file on a memory
+     * file system is written through a moving shared mapping -- pwrite()s to one file serialise on the inode
+     * lock (~2.7 GB/s whatever the thread count), page faults of a mapping do not.  Otherwise parallel pwrite. */
+    int stream, mapped;
+    char *map; size_t map_lo, map_hi, file_len;
 } sink_t;
+#define SINK_WINDOW ((size_t)256 << 20)
+
+static void sink_unmap(sink_t *k) {
+    if (k->map) munmap(k->map, k->map_hi - k->map_lo);
+    k->map = NULL; k->map_lo = k->map_hi = 0;
+}
+/* file sink: sets up how the file is written (after open) */
+static void sink_open_file(sink_t *k) {
+    struct stat st;
+    if (fstat(k->fd, &st) || !S_ISREG(st.st_mode)) { k->stream = 1; return; }
+    const char *e = getenv("UTB_OUT_MMAP");
+    int want = -1;
+    if (e) want = atoi(e) != 0;
+    struct statfs fs;
+    if (want < 0) want = !fstatfs(k->fd, &fs) && (fs.f_type == 0x01021994 /* tmpfs */ || fs.f_type == 0x858458f6 /* ramfs */);
+    if (want && (fcntl(k->fd, F_GETFL) & O_ACCMODE) == O_RDWR) k->mapped = 1;
+}
+/* at the end of the search: the file gets its true length */
+static int sink_close_file(sink_t *k) {
+    int bad = 0;
+    if (k->mapped || k->file_len) {
+        sink_unmap(k);
+        if (k->file_len != k->off && ftruncate(k->fd, (off_t)k->off)) bad = 1;
+    }
+    return bad;
+}
+/* writes n bytes at file offset o (any thread of a team; stream sinks: the caller keeps them in order) */
+static void sink_put(sink_t *k, const char *p, size_t n, size_t o) {
+    if (k->fd < 0) { memcpy(k->s->arena + o, p, n); return; }
+    if (k->map && o >= k->map_lo && o + n <= k->map_hi) { memcpy(k->map + (o - k->map_lo), p, n); return; }
+    while (n) {
+        ssize_t w = k->stream ? write(k->fd, p, n) : pwrite(k->fd, p, n, (off_t)o);
+        if (w < 0) { if (errno == EINTR) continue; k->failed = 1; return; }
+        p += w; o += (size_t)w; n -= (size_t)w;
+    }
+}
 
 static int sink_reserve(sink_t *k, size_t upto) {
-    if (k->fd >= 0) return 0;
+    if (k->fd >= 0) {
+        if (!k->mapped || upto <= k->map_hi) return 0;
+        /* move the window: [off rounded down to a page, at least SINK_WINDOW further); the file grows with it (sparse) */
+        sink_unmap(k);
+        const size_t lo = k->off & ~(size_t)4095;
+        size_t hi = lo + SINK_WINDOW;
+        if (hi < upto) hi = (upto + 4095) & ~(size_t)4095;
+        if (hi > k->file_len) {
+            struct statfs fs;                                      /* a store into a mapping of a full file system is a SIGBUS, not an error code */
+            if (fstatfs(k->fd, &fs) || (size_t)fs.f_bavail * (size_t)fs.f_bsize < 2 * (hi - lo) || ftruncate(k->fd, (off_t)hi)) { k->mapped = 0; return 0; }
+            k->file_len = hi;
+        }
+        void *m = mmap(NULL, hi - lo, PROT_READ | PROT_WRITE, MAP_SHARED, k->fd, (off_t)lo);
+        if (m == MAP_FAILED) { k->mapped = 0; return 0; }          /* pwrite from here on; the file is cut to its length at the end */
+        k->map = (char *)m; k->map_lo = lo; k->map_hi = hi;
+        return 0;
+    }
     utb_searcher *s = k->s;
     if (upto <= s->arena_cap) return 0;
     size_t nc = s->arena_cap ? s->arena_cap + s->arena_cap / 2 : (k->hint > ((size_t)1 << 24) ? k->hint : (size_t)1 << 24);
@@ -386,30 +444,23 @@ static void fmt_part(void *c_, int part, int nparts) {
 static void emit_part(void *c_, int part, int nparts) {
     fmt_ctx *f = (fmt_ctx *)c_;
     (void)nparts;
-    size_t n = f->len[part];
-    if (!n) return;
-    if (f->sink->fd < 0) { memcpy(f->sink->s->arena + f->off[part], f->buf[part], n); return; }
-    const char *p = f->buf[part];
-    off_t o = (off_t)f->off[part];
-    while (n) {
-        ssize_t k = pwrite(f->sink->fd, p, n, o);
-        if (k < 0) { if (errno == EINTR) continue; f->sink->failed = 1; return; }
-        p += k; o += k; n -= (size_t)k;
-    }
+    if (f->len[part]) sink_put(f->sink, f->buf[part], f->len[part], f->off[part]);
+}
+/* every part of the host formatter's output; in order by one thread when the sink is a stream */
+static void emit_all(team_t *team, fmt_ctx *f) {
+    if (f->sink->fd >= 0 && f->sink->stream) { for (int p = 0; p < team->n; ++p) emit_part(f, p, team->n); }
+    else team_run(team, emit_part, f);
 }
 
 typedef struct { sink_t *sink; const char *text; size_t len, off; } copy_ctx;
 static void copy_part(void *c_, int part, int nparts) {
     copy_ctx *c = (copy_ctx *)c_;
     size_t a = c->len * (size_t)part / (size_t)nparts, b = c->len * (size_t)(part + 1) / (size_t)nparts;
-    if (a == b) return;
-    if (c->sink->fd < 0) { memcpy(c->sink->s->arena + c->off + a, c->text + a, b - a); return; }
-    const char *p = c->text + a; size_t n = b - a; off_t o = (off_t)(c->off + a);
-    while (n) {
-        ssize_t k = pwrite(c->sink->fd, p, n, o);
-        if (k < 0) { if (errno == EINTR) continue; c->sink->failed = 1; return; }
-        p += k; o += k; n -= (size_t)k;
-    }
+    if (a != b) sink_put(c->sink, c->text + a, b - a, c->off + a);
+}
+static void copy_all(team_t *team, copy_ctx *c) {
+    if (c->sink->fd >= 0 && c->sink->stream) sink_put(c->sink, c->text, c->len, c->off);
+    else team_run(team, copy_part, c);
 }
 
 /* The shallow vote of the non-GG binary, read by read in input order (itree.c:979-1003).  sel_cnt[r] ids per read,
@@ -527,7 +578,7 @@ static void *formatter_main(void *arg) {
                     int r2 = utb_batch_text_piece(sl->b, o, &len, &text);
                     if (r2) { R->error = r2; snprintf(R->errmsg, sizeof R->errmsg, "%s", utb_last_error()); break; }
                     copy_ctx cc = {R->sink, text, len, R->sink->off + o};
-                    team_run(&R->fmt_team, copy_part, &cc);
+                    copy_all(&R->fmt_team, &cc);
                     o += len;
                 }
                 R->sink->off += text_len;
@@ -546,7 +597,7 @@ static void *formatter_main(void *arg) {
             for (int p = 0; p < R->fmt_team.n; ++p) { F.off[p] = R->sink->off + tot; tot += F.len[p]; R->st.good_finds += F.good[p]; F.good[p] = 0; }
             if (F.nomem) { R->error = UTB_ERR_NOMEM; snprintf(R->errmsg, sizeof R->errmsg, "out of memory (formatter)"); }
             else if (!sink_reserve(R->sink, R->sink->off + tot)) {
-                team_run(&R->fmt_team, emit_part, &F);
+                emit_all(&R->fmt_team, &F);
                 R->sink->off += tot;
                 R->st.out_bytes += tot;
             }
@@ -1174,14 +1225,17 @@ int utb_search_file(utb_searcher *s, const char *fasta_path, const char *out_pat
     if (ref_exit) *ref_exit = 0;
     int fd = open(fasta_path, O_RDONLY);
     if (fd < 0) { utb_set_error("Invalid input files"); if (ref_exit) *ref_exit = 1; return UTB_ERR_IO; }   /* itree.c:835 */
-    int fo = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    int fo = open(out_path, O_RDWR | O_CREAT | O_TRUNC, 0644);   /* read access only for the shared mapping of sink_reserve */
+    if (fo < 0) fo = open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (fo < 0) { close(fd); utb_set_error("cannot open output file %s", out_path); if (ref_exit) *ref_exit = 1; return UTB_ERR_IO; }
     source_t src; memset(&src, 0, sizeof src); src.fd = fd;
     struct stat st;
     if (!fstat(fd, &st) && S_ISREG(st.st_mode)) { src.seekable = 1; src.file_size = st.st_size; if (!st.st_size) src.eof = 1; }
     sink_t sink; memset(&sink, 0, sizeof sink); sink.fd = fo; sink.s = s;
+    sink_open_file(&sink);
     int rc = run_search(s, &src, &sink, do_rc, stats, ref_exit);
-    if (close(fo) && !rc) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
+    int bad = sink_close_file(&sink);
+    if ((close(fo) || bad) && !rc) { rc = UTB_ERR_IO; utb_set_error("write error on output"); }
     close(fd);
     return rc;
 }
