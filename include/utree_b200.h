@@ -149,9 +149,9 @@ int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len,
  * (itree.c:1028-1098). */
 int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *off,
                   size_t n_reads, utb_result *results);
-/* The same vote through the representation the batch pipeline uses (slots of a
- * read aligned to 32, 1-bit-per-slot hit map; thread-per-read kernel, with the
- * warp and block kernels behind it for label-rich and long reads). */
+/* The same vote through the representation the batch pipeline uses (per read
+ * the list of the labels that hit, misses left out; thread-per-read kernel, with
+ * the warp and block kernels behind it for label-rich and long reads). */
 int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint64_t *off,
                          size_t n_reads, utb_result *results);
 

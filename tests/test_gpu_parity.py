@@ -86,7 +86,7 @@ def test_vote_matches_oracle(gpu, dbname, sparse, env):
         if h.size > 2:
             lists.append(rng.permutation(h))
     for k in range(400):      # random multisets over few and many labels (forces the warp and block paths too)
-        nl = int(rng.integers(1, min(ctr.max_ix, 90 if k % 2 else 8)))
+        nl = int(rng.integers(1, min(ctr.max_ix, (700 if k % 10 == 1 else 90) if k % 2 else 8)))   # > 64: block kernel; > 32: several chunks of its walk; > 512: unstaged walk
         labs = rng.choice(ctr.max_ix, nl, replace=False)
         cnt = rng.integers(1, 40, nl)
         h = np.repeat(labs, cnt).astype(np.uint32)
@@ -109,6 +109,77 @@ def test_vote_matches_oracle(gpu, dbname, sparse, env):
         assert (r["label"], r["found"], r["uix"]) == (v.label, v.found, v.uix), i
         if v.kind == 2:
             assert (r["cut"], r["sl"], r["ol"]) == (v.cut, v.sl, v.ol), i
+
+
+def _taxonomy_labels(rng, n_target):
+    """A quirky taxonomy with ~n_target distinct labels: shared prefixes, labels that stop at every rank, empty
+    ranks, tokens that are prefixes of other tokens, names with underscores -- every branch of itree.c:1052-1069."""
+    ranks = [b"k__", b"p__", b"c__", b"o__", b"f__", b"g__", b"s__", b"t__"]
+    labels = set()
+    names = [b"A", b"Ab", b"Ab_c", b"B", b"Ba", b"C_", b"", b"Zeta", b"Zet", b"Q_1", b"Q_12", b"m"]
+    while len(labels) < n_target:
+        depth = int(rng.integers(1, 9))
+        toks = []
+        for d in range(depth):
+            pool = 2 if d < 2 else 4 if d < 4 else len(names)
+            toks.append(ranks[d] + names[int(rng.integers(0, pool))] + (b"%d" % rng.integers(0, 3) if d >= 5 and rng.random() < 0.5 else b""))
+            labels.add(b";".join(toks))
+    return sorted(labels, key=lambda _: rng.random())
+
+
+def test_vote_with_hundreds_of_labels_per_read(built, tmp_path):
+    """Long queries touch hundreds of labels: the block kernels' walk over a staged copy of the label strings (32
+    neighbour pairs per step, several steps per level), the unstaged walk beyond 512 labels, and the split path."""
+    from tools import synth
+    from utree_b200 import capi
+    rng = np.random.default_rng(77)
+    labels = _taxonomy_labels(rng, 900)
+    words = np.sort(rng.choice(2 ** 62, len(labels) * 3, replace=False).astype(np.uint64))
+    ixs = np.arange(words.size) % len(labels)
+    path = str(tmp_path / "many.ctr")
+    synth.ctr_write(path, words, ixs, synth._label_tail(labels, np.bincount(ixs, minlength=len(labels))), ix_bytes=2)
+    ctr = capi.Ctr(path)
+    assert ctr.max_ix == len(labels)
+    orc = oracle_api.OracleDb(path)
+    by_str = sorted(range(len(labels)), key=lambda i: labels[i])
+    lists = []
+    for k in range(300):
+        nl = int(rng.integers(2, [40, 120, 500, 880][k % 4]))
+        # a lineage (a stretch of neighbours in string order) that holds most of the hits, plus strays
+        a = int(rng.integers(0, len(labels) - 1))
+        width = int(rng.integers(1, max(2, nl // 2)))
+        core = [by_str[(a + j) % len(labels)] for j in range(width)]
+        stray = rng.choice(len(labels), max(1, nl - width), replace=False)
+        heavy = int(rng.integers(1, 2000))
+        h = np.concatenate([np.repeat(core, rng.integers(1, heavy + 1, len(core))), np.repeat(stray, rng.integers(1, 4, stray.size))])
+        lists.append(rng.permutation(h).astype(np.uint32))
+    off = np.zeros(len(lists) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([l.size for l in lists])
+    flat = np.concatenate(lists)
+    kinds = set()
+    try:
+        for env in ({}, {"UTB_VOTE_SPLIT_SLOTS": "64"}):
+            os.environ.update(env)
+            try:
+                db = capi.Db(ctr, 0)
+                try:
+                    for sparse in (False, True):
+                        res = db.vote_hits(flat, off, sparse=sparse)
+                        for i, h in enumerate(lists):
+                            v = orc.vote(h)
+                            r = res[i]
+                            kinds.add((v.kind, v.cut == 0xFFFFFFFE))
+                            assert (r["kind"], r["label"], r["found"], r["uix"]) == (v.kind, v.label, v.found, v.uix), (env, sparse, i)
+                            if v.kind == 2:
+                                assert (r["cut"], r["sl"], r["ol"]) == (v.cut, v.sl, v.ol), (env, sparse, i)
+                finally:
+                    db.free()
+            finally:
+                for k in env:
+                    del os.environ[k]
+    finally:
+        orc.free(); ctr.close()
+    assert len(kinds) >= 2
 
 
 @pytest.mark.parametrize("db_name,reads,out,rc", CASES)

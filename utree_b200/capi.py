@@ -227,7 +227,7 @@ class Db:
         return fwd, rc, valid
 
     def vote_hits(self, hits, off, sparse=False):
-        """sparse=True: through the pipeline's hit-map representation (thread -> warp -> block kernels)."""
+        """sparse=True: through the pipeline's per-read hit lists (thread -> warp -> block kernels)."""
         hits = np.ascontiguousarray(hits, dtype=np.uint32)
         off = np.ascontiguousarray(off, dtype=np.uint64)
         n = off.size - 1

@@ -19,7 +19,8 @@
 //             k-mer word order of itree.c:924) and a bad-base bit mask.  Every
 //             read is padded to a multiple of 32 positions with >= 1 bad
 //             position, so a 32-mer window can never straddle two reads.
-//   hits    : one u32 per (position, strand): label id; valid where hitmap is set
+//   hits    : sieve on (GG path): per read the labels of its hits back to back from the read's first slot, hcnt[read]
+//             of them; otherwise one u32 per (position, strand), with a 1-bit-per-slot hitmap in the non-GG path
 //   results : one utb_result per read;  text : the output lines
 //
 // Kernels: nl_count / nl_index / frame_parse (XT_INITIATE_WS, itree.c:860-901),
@@ -117,12 +118,13 @@ __device__ __forceinline__ uint64_t revcomp_word(uint64_t w) {
 }
 #define PK_GUARD 8u               // all-bad groups behind the last read: the sieve kernel walks whole tiles without bounds checks
 // pkr (optional): the reverse complement of every packed group, so that the reverse-complement window of a
-// position is a funnel shift of two pkr words exactly as the forward window is one of two pk words
+// position is a funnel shift of two pkr words exactly as the forward window is one of two pk words; rid (optional):
+// the read every group belongs to
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_off,
             const uint32_t *__restrict__ seq_len, const uint32_t *__restrict__ grp_off,
             uint32_t n_reads, uint32_t n_groups, const uint32_t *__restrict__ dims,
-            uint64_t *__restrict__ pk, uint32_t *__restrict__ bad, uint64_t *__restrict__ pkr) {
+            uint64_t *__restrict__ pk, uint32_t *__restrict__ bad, uint64_t *__restrict__ pkr, uint32_t *__restrict__ rid) {
     if (dims) { n_reads = dims[0]; n_groups = dims[1]; }          // device-side framing: the host only knows upper bounds
     const uint32_t lane = threadIdx.x & 31u;
     // a warp takes 32 consecutive groups per round (warp-uniform loop)
@@ -148,6 +150,7 @@ pack_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restrict__ seq_of
         if (g >= n_groups) { pk[g] = 0; bad[g] = 0xFFFFFFFFu; if (pkr) pkr[g] = 0; continue; }   // guard groups: all positions bad
         uint32_t k = g - __ldg(grp_off + lo);
         uint32_t len = __ldg(seq_len + lo);
+        if (rid) rid[g] = lo;                                      // group -> read (phase B files a hit under its read)
         uint32_t b0 = k * 32u;
         uint32_t nv = len > b0 ? min(32u, len - b0) : 0u;  // real bases in this group
         uint64_t word = 0;
@@ -529,20 +532,36 @@ __device__ __forceinline__ void wq_reserve(WarpQueue &q, uint32_t c, uint32_t la
     q.used = 0;
     q.have = q.base + Q_CHUNK <= q_cap;                            // beyond capacity: the caller resolves inline
 }
+// Where the labels of the hits go.  List mode (cnt != null, the GG path): appended to the hit list of the READ the slot
+// belongs to -- the list starts at the read's first slot in `hits`, cnt[read] counts it; rid maps a 32-position
+// group to its read.  The vote then reads one or two sectors per read instead of a hit map plus one gather per hit,
+// and phase B writes next to what it wrote before instead of read-modify-writing a random line of `hits` and one of
+// the map per hit.  Scatter mode (cnt == null, the non-GG path, which needs positions): hits[slot] + a bit in hitmap.
+struct HitSink {
+    uint32_t *hits;
+    uint32_t *hitmap;
+    const uint32_t *rid, *grp_off;
+    uint32_t *cnt;
+    uint32_t sh;                                                    // log2(slots per group): 5 + (strands == 2)
+};
+__device__ __forceinline__ void sink_put(const HitSink &k, uint32_t slot, uint32_t r) {   // one hit, any thread
+    if (k.cnt) {
+        const uint32_t rd = __ldg(k.rid + (slot >> k.sh));
+        k.hits[((uint64_t)__ldg(k.grp_off + rd) << k.sh) + atomicAdd(k.cnt + rd, 1u)] = r;
+    } else { k.hits[slot] = r; atomicOr(k.hitmap + (slot >> 5), 1u << (slot & 31u)); }
+}
 // queue overflow: the exact lookup right here (rare)
-__device__ __noinline__ uint32_t resolve_inline(const DevDB &db, uint64_t w, uint32_t slot, uint32_t *__restrict__ hits,
-                                                uint32_t *__restrict__ hitmap) {
+__device__ __noinline__ uint32_t resolve_inline(const DevDB &db, uint64_t w, uint32_t slot, const HitSink &sink) {
     const uint32_t r = kt_lookup(db, w);
     if (r == HIT_MISS) return 0;
-    hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u));
+    sink_put(sink, slot, r);
     return 1;
 }
 // Appends the survivors of one warp step (warp-uniform call).
 template <int NSTR>
 __device__ __forceinline__ uint32_t emit_survivors(const DevDB &db, WarpQueue &wq, uint32_t lane, bool passF, bool passR, uint64_t w, uint64_t rc,
                                                    uint32_t pos, uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots,
-                                                   unsigned long long *__restrict__ q_count, uint64_t q_cap,
-                                                   uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap) {
+                                                   unsigned long long *__restrict__ q_count, uint64_t q_cap, const HitSink &sink) {
     const uint32_t bF = __ballot_sync(0xFFFFFFFFu, passF);
     const uint32_t bR = NSTR == 2 ? __ballot_sync(0xFFFFFFFFu, passR) : 0u;
     const uint32_t cF = __popc(bF), c = cF + __popc(bR);
@@ -555,8 +574,8 @@ __device__ __forceinline__ uint32_t emit_survivors(const DevDB &db, WarpQueue &w
         if (passF) { const uint64_t i = at + __popc(bF & lt); q_words[i] = w; q_slots[i] = pos * NSTR; }
         if (passR) { const uint64_t i = at + cF + __popc(bR & lt); q_words[i] = rc; q_slots[i] = pos * NSTR + 1u; }
     } else {
-        if (passF) nh += resolve_inline(db, w, pos * NSTR, hits, hitmap);
-        if (passR) nh += resolve_inline(db, rc, pos * NSTR + 1u, hits, hitmap);
+        if (passF) nh += resolve_inline(db, w, pos * NSTR, sink);
+        if (passR) nh += resolve_inline(db, rc, pos * NSTR + 1u, sink);
     }
     wq.used += c;
     return nh;
@@ -602,10 +621,9 @@ __device__ __forceinline__ void sv_prefetch(const void *p) { asm volatile("prefe
 template <int NSTR, int SV_U, int SV_MINB>
 __global__ void __launch_bounds__(256, SV_MINB)
 sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restrict__ bad, const uint64_t *__restrict__ pkr, uint32_t n_pos,
-             const uint32_t *__restrict__ n_groups_dev,
-             uint32_t *__restrict__ hits, unsigned long long *__restrict__ counters,
+             const uint32_t *__restrict__ n_groups_dev, unsigned long long *__restrict__ counters,
              uint64_t *__restrict__ q_words, uint32_t *__restrict__ q_slots, unsigned long long *__restrict__ q_count,
-             uint64_t q_cap, uint32_t *__restrict__ hitmap) {
+             uint64_t q_cap, const HitSink sink) {
     if (n_groups_dev) n_pos = *n_groups_dev * 32u;
     const uint32_t lane = threadIdx.x & 31u;
     const bool upper = lane >= 16u;
@@ -665,8 +683,8 @@ sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restri
                 if (__any_sync(0xFFFFFFFFu, live)) {               // the padding group behind every read holds no window at all
                     const bool tF = sv_test(v[u], st[u].wh, st[u].wl), tR = NSTR == 2 && sv_test(v[u], st[u].rh, st[u].rl);
                     nh += emit_survivors<NSTR>(db, wq, lane, live & tF, live & tR, ((uint64_t)st[u].wh << 32) | st[u].wl, ((uint64_t)st[u].rh << 32) | st[u].rl,
-                                               (s + u) * 32u + lane, q_words, q_slots, q_count, q_cap, hits, hitmap);
-                    nv += live ? NSTR : 0;                         // hits[] is only valid where hitmap is set: nothing to store for misses
+                                               (s + u) * 32u + lane, q_words, q_slots, q_count, q_cap, sink);
+                    nv += live ? NSTR : 0;                         // nothing is stored for a miss
                 }
             }
             st[0] = st[SV_U];
@@ -681,24 +699,44 @@ sieve_kernel(DevDB db, const uint64_t *__restrict__ pk, const uint32_t *__restri
     }
 }
 
-// Phase B: one survivor per thread, ONE random 32-byte table access each (no chain to wait for)
+// Phase B: one survivor per thread, ONE random 32-byte table access each (no chain to wait for).  LISTS: the hits
+// of a warp that belong to the same read (neighbours in the queue do) reserve their places in that read's list
+// with one atomic and store side by side.
+template <bool LISTS>
 __global__ void __launch_bounds__(256, 6)
 queue_lookup_kernel(DevDB db, const uint64_t *__restrict__ q_words, const uint32_t *__restrict__ q_slots,
                     const unsigned long long *__restrict__ q_count, uint64_t q_cap,
-                    uint32_t *__restrict__ hits, uint32_t *__restrict__ hitmap, unsigned long long *__restrict__ counters) {
+                    const HitSink sink, unsigned long long *__restrict__ counters) {
     const uint64_t n = *q_count < q_cap ? *q_count : q_cap;       // both multiples of Q_CHUNK: every entry below n was written
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31u;
     uint32_t nh = 0, nsect = 0;
+    // n and the stride are multiples of 32: the lanes of a warp leave the loop together
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const uint32_t slot = q_slots[i];
-        if (slot == Q_INVALID) continue;                           // padding of a retired chunk
-        uint32_t sc;
-        const uint32_t r = kt_lookup(db, q_words[i], &sc);
-        nsect += sc;
-        if (r != HIT_MISS) { hits[slot] = r; atomicOr(hitmap + (slot >> 5), 1u << (slot & 31u)); ++nh; }
+        uint32_t r = HIT_MISS;
+        if (slot != Q_INVALID) {                                   // else: padding of a retired chunk
+            uint32_t sc;
+            r = kt_lookup(db, q_words[i], &sc);
+            nsect += sc;
+        }
+        const bool hit = r != HIT_MISS;
+        nh += hit;
+        if (!LISTS) {
+            if (hit) { sink.hits[slot] = r; atomicOr(sink.hitmap + (slot >> 5), 1u << (slot & 31u)); }
+            continue;
+        }
+        if (!__any_sync(0xFFFFFFFFu, hit)) continue;
+        const uint32_t rd = hit ? __ldg(sink.rid + (slot >> sink.sh)) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, rd);
+        const uint32_t leader = (uint32_t)__ffs(peers) - 1u;
+        uint32_t base = 0;
+        if (hit && lane == leader) base = atomicAdd(sink.cnt + rd, (uint32_t)__popc(peers));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (hit) sink.hits[((uint64_t)__ldg(sink.grp_off + rd) << sink.sh) + base + __popc(peers & ((1u << lane) - 1u))] = r;
     }
     for (int o = 16; o; o >>= 1) { nh += __shfl_xor_sync(0xFFFFFFFFu, nh, o); nsect += __shfl_xor_sync(0xFFFFFFFFu, nsect, o); }
-    if ((threadIdx.x & 31u) == 0) {
+    if (lane == 0) {
         const uint32_t c = blockIdx.x & (COUNTER_SLOTS - 1);
         if (nh) atomicAdd(counters + COUNTER_SLOTS + c, (unsigned long long)nh);
         if (nsect) atomicAdd(counters + 3 * COUNTER_SLOTS + c, (unsigned long long)nsect);
@@ -747,17 +785,16 @@ __device__ __forceinline__ uint32_t cutoff_of(uint32_t x) {   // itree.c:1044-10
 // scalar state, the character scans are done 32 bytes at a time with ballots.
 // T_lab/T_cnt: the distinct labels of the read in strcmp order with counts
 // (shared or global memory).
-// S / S_off: the label strings of T_lab[0 .. uix) staged back to back (string z at S + S_off[z]), or null: read from the blob
 __device__ void walk_warp(const DevDB &db, const uint32_t *T_lab, const uint32_t *T_cnt,
-                          uint32_t uix, uint32_t n, utb_result *out, const char *S = nullptr, const uint32_t *S_off = nullptr) {
+                          uint32_t uix, uint32_t n, utb_result *out) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t EMPTY = 0xFFFFFFFFu;
     uint32_t cutoff = cutoff_of(n), st = 0, ed = uix, dv = EMPTY, orun = n, sl = 0, ol = 0;
     for (;;) {                                                      // itree.c:1047
         uint32_t run = T_cnt[st], td = dv;
         for (uint32_t z = st + 1; z < ed; ++z) {                    // itree.c:1050
-            const char *s1 = S ? S + S_off[z - 1] : db.blob + __ldg(db.off + T_lab[z - 1]);
-            const char *s2 = S ? S + S_off[z] : db.blob + __ldg(db.off + T_lab[z]);
+            const char *s1 = db.blob + __ldg(db.off + T_lab[z - 1]);
+            const char *s2 = db.blob + __ldg(db.off + T_lab[z]);
             if (!s1[dv + (dv == EMPTY)]) {                          // itree.c:1052
                 run = T_cnt[z]; st = z;
                 orun -= T_cnt[z - 1];
@@ -803,25 +840,28 @@ __device__ void walk_warp(const DevDB &db, const uint32_t *T_lab, const uint32_t
     }
 }
 
-struct VoteIn {            // where a read's hit slots live
-    const uint32_t *hits;
-    const uint32_t *grp_off;   // batch mode: position space
-    const uint32_t *seq_len;
-    const uint64_t *off;       // stage-level mode: explicit ranges (overrides batch mode)
-    uint32_t nstr;
-    // two-phase lookup: one bit per slot that holds a label; hits[] is then only valid where the bit is set
-    const uint32_t *hitmap;
+struct VoteIn {            // where a read's hits live
+    const uint32_t *hits = nullptr;
+    const uint32_t *grp_off = nullptr;   // batch mode: position space
+    const uint32_t *seq_len = nullptr;
+    const uint64_t *off = nullptr;       // stage-level mode: explicit ranges (overrides batch mode)
+    uint32_t nstr = 1;
+    // two-phase lookup: the survivor kernel appends the labels of a read's hits back to back from the read's first
+    // slot and counts them here (any order: the vote is over a multiset); null: one entry per (position, strand)
+    const uint32_t *cnt = nullptr;
+    // non-GG mode (needs the positions): one bit per slot that holds a label; hits[] is only valid where it is set
+    const uint32_t *hitmap = nullptr;
 };
 __device__ __forceinline__ void vote_range(const VoteIn &in, uint32_t r, uint64_t &start, uint64_t &count) {
     if (in.off) { start = in.off[r]; count = in.off[r + 1] - start; return; }
+    start = (uint64_t)__ldg(in.grp_off + r) * 32u * in.nstr;
+    if (in.cnt) { count = in.cnt[r]; return; }
     uint32_t len = __ldg(in.seq_len + r);
     uint64_t nwin = len >= 32u ? len - 31u : 0u;
-    start = (uint64_t)__ldg(in.grp_off + r) * 32u * in.nstr;
     count = nwin * in.nstr;
 }
-
 #define VW_SLOTS 64u            // distinct labels a warp can hold in shared memory
-#define VW_MAXHITS 16384u       // hit slots a single warp will scan
+#define VW_MAXHITS 4096u        // entries a single warp will scan (longer reads hold more labels than a warp's table anyway)
 #define VW_WARPS 8
 
 // Warp per read: hits -> (label,count) multiset in a shared-memory hash table
@@ -846,31 +886,7 @@ __device__ void vote_warp_read(const DevDB &db, const VoteIn &in, uint32_t r, ut
     __syncwarp();
     uint32_t n = 0;
     bool overflow = false;
-    if (in.hitmap) {
-        // sparse: scan the read's words of the hit map (1/32 of the slot bytes), gather only the flagged slots
-        const uint32_t *hm = in.hitmap + (start >> 5);             // start is a multiple of 32 in batch mode
-        const uint32_t nwords = (uint32_t)((count + 31) >> 5);
-        for (uint32_t wbase = 0; wbase < nwords; wbase += 32) {
-            uint32_t m = wbase + lane < nwords ? __ldg(hm + wbase + lane) : 0u;
-            while (__any_sync(0xFFFFFFFFu, m != 0)) {
-                uint32_t h = HIT_NOWIN;
-                if (m) { const uint32_t bit = __ffs(m) - 1; m &= m - 1; h = __ldg(in.hits + start + 32ull * (wbase + lane) + bit); }
-                const bool ok = h < db.max_ix;
-                n += __popc(__ballot_sync(0xFFFFFFFFu, ok));
-                const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-                if (ok && (uint32_t)(__ffs(peers) - 1) == lane) {
-                    uint32_t cc = __popc(peers), slot = (h * 2654435761u) >> 26;
-                    for (uint32_t tries = 0;; ++tries) {
-                        if (tries == VW_SLOTS) { overflow = true; break; }
-                        uint32_t old = atomicCAS(&key[slot], UTB_BAD32, h);
-                        if (old == UTB_BAD32 || old == h) { atomicAdd(&cnt[slot], cc); break; }
-                        slot = (slot + 1) & (VW_SLOTS - 1);
-                    }
-                }
-                __syncwarp();
-            }
-        }
-    } else {
+    {
     // dense: 128 slots per round (one uint4 per lane); a round without a label costs one ballot
     const uint32_t mis = (uint32_t)((4u - (start & 3u)) & 3u);     // slots before the first 16-byte boundary
     for (uint64_t base = 0; base < count + 128; base += 128) {
@@ -965,15 +981,15 @@ vote_warp_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__restri
 }
 
 // ---- thread per read (the common case) ----------------------------------------------
-// A 150-base read owns 10 words of the hit map and holds a handful of hits on 1-3 distinct labels;
-// a warp per read spends ~800 issue slots on it, almost all of them with one useful lane (the
-// aufbau walk compares two label strings character by character).  Here every lane walks its own
-// read: hit map words -> flagged slots -> (label, count) pairs kept sorted by label rank in
-// registers -> the same walk as walk_warp, scalar.  Reads with more than VT_K distinct labels or
-// more than VT_MAXWORDS hit-map words are deferred to vote_warp_kernel through `list`.
+// A 150-base read holds a handful of hits on 1-3 distinct labels; a warp per read spends ~800 issue
+// slots on it, almost all of them with one useful lane (the aufbau walk compares two label strings
+// character by character).  Here every lane walks its own read: the read's hit list (one or two
+// sectors, written back to back by the survivor kernel) -> (label, count) pairs kept in registers,
+// sorted by label rank -> the same walk as walk_warp, scalar.  Reads with more than VT_K distinct
+// labels or more than VT_MAXHITS entries are deferred to vote_warp_kernel through `list`.
 #define VT_K 6u
 #define VT_THREADS 128
-#define VT_MAXWORDS 64u
+#define VT_MAXHITS 512u
 __device__ __forceinline__ void walk_thread(const DevDB &db, const uint32_t *T_lab, const uint32_t *T_cnt,   // [k * VT_THREADS]
                                             uint32_t uix, uint32_t n, utb_result *out) {
 #define TL(z) T_lab[(z) * VT_THREADS]
@@ -1034,30 +1050,24 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__rest
         if (r >= n_reads) break;
         uint64_t start, count;
         vote_range(in, r, start, count);
-        const uint32_t nwords = (uint32_t)((count + 31) >> 5);
-        bool defer = nwords > VT_MAXWORDS;
+        bool defer = count > VT_MAXHITS;
         uint32_t lab[VT_K], cnt[VT_K], n = 0, uix = 0;
 #pragma unroll
         for (uint32_t k = 0; k < VT_K; ++k) { lab[k] = UTB_BAD32; cnt[k] = 0; }
         if (!defer) {
-            const uint32_t *hm = in.hitmap + (start >> 5);         // start is a multiple of 32 in batch mode
-            for (uint32_t w = 0; w < nwords && !defer; ++w) {
-                uint32_t m = __ldg(hm + w);
-                if (w == nwords - 1 && (count & 31u)) m &= (1u << (count & 31u)) - 1u;
-                while (m) {
-                    const uint32_t bit = __ffs(m) - 1; m &= m - 1;
-                    const uint32_t h = __ldg(in.hits + start + 32ull * w + bit);
-                    if (h >= db.max_ix) continue;
-                    ++n;
-                    bool seen = false;
+            const uint32_t *hp = in.hits + start;
+            for (uint32_t i = 0; i < (uint32_t)count; ++i) {
+                const uint32_t h = __ldg(hp + i);
+                if (h >= db.max_ix) continue;
+                ++n;
+                bool seen = false;
 #pragma unroll
-                    for (uint32_t k = 0; k < VT_K; ++k) if (lab[k] == h) { ++cnt[k]; seen = true; }
-                    if (!seen) {
-                        if (uix == VT_K) { defer = true; break; }
+                for (uint32_t k = 0; k < VT_K; ++k) if (lab[k] == h) { ++cnt[k]; seen = true; }
+                if (!seen) {
+                    if (uix == VT_K) { defer = true; break; }
 #pragma unroll
-                        for (uint32_t k = 0; k < VT_K; ++k) if (k == uix) { lab[k] = h; cnt[k] = 1; }
-                        ++uix;
-                    }
+                    for (uint32_t k = 0; k < VT_K; ++k) if (k == uix) { lab[k] = h; cnt[k] = 1; }
+                    ++uix;
                 }
             }
         }
@@ -1095,21 +1105,21 @@ vote_thread_kernel(DevDB db, VoteIn in, uint32_t n_reads, const uint32_t *__rest
 }
 
 // ---- long queries and label-rich reads ---------------------------------------------------
-// Reads the warp kernel defers (more than VW_MAXHITS lookup slots or more than VW_SLOTS distinct
+// Reads the warp kernel defers (more than VW_MAXHITS entries or more than VW_SLOTS distinct
 // labels) are voted from a dense per-label histogram in global memory; the labels a read touches
 // are appended to a list the moment their count leaves zero, so what follows costs O(touched
 // labels), not O(max_ix): the list is sorted by label rank in shared memory (itree.c:1041), the
 // counts are gathered and the scratch is left clean, then the same walk runs.
 //   vote_block_kernel   one CTA per read, CTA-private scratch; reads with more than `split_slots`
-//                       lookup slots (north_star: "long and whole-genome queries split across
+//                       entries (north_star: "long and whole-genome queries split across
 //                       blocks and merged") are handed on to
-//   vote_big_count_kernel  the hit map of every such read is cut into chunks of VBIG_CHUNK_WORDS
-//                       words which the whole grid accumulates into that read's histogram, and
+//   vote_big_count_kernel  the hit list of every such read is cut into chunks of 32 * VBIG_CHUNK_WORDS
+//                       entries which the whole grid accumulates into that read's histogram, and
 //   vote_big_finish_kernel one CTA per read merges: sort, gather, walk.
 #define VB_THREADS 256
 #define VB_PER_SM 4
 #define VB_SORT_MAX 2048u           // touched labels sorted in shared memory; beyond: sweep over all labels in rank order
-#define VBIG_CHUNK_WORDS 2048u      // hit-map words (65,536 lookup slots) a CTA accumulates at a time
+#define VBIG_CHUNK_WORDS 2048u      // x 32 = 65,536 entries of a read's hits a CTA accumulates at a time
 #define VBIG_POOL_MAX 2048u         // split reads a batch can hold scratch for
 #define VL_CACHE 64u                // per-CTA (label, count) pairs gathered in shared memory before they go to the histogram
 struct VoteLong {
@@ -1149,47 +1159,20 @@ __device__ __forceinline__ void vl_flush(VlCache &c, uint32_t *__restrict__ hist
         c.key[i] = UTB_BAD32; c.cnt[i] = 0;
     }
 }
-// Adds the labels of the hit-map words [w0, w1) of one read (dense mode: of the slots they cover) through the
-// table.  Block-wide call; returns this thread's hits.  The caller flushes.
+// Adds the labels of entries [32 * w0, 32 * w1) of one read's hits through the table.  Block-wide call; returns this
+// thread's hits.  The caller flushes.
 __device__ __forceinline__ uint32_t vl_accumulate(const DevDB &db, const VoteIn &in, uint64_t start, uint64_t count, uint64_t w0, uint64_t w1,
                                                   VlCache &cache, uint32_t *__restrict__ hist, uint32_t *__restrict__ tlab, uint32_t *nt) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint32_t n_local = 0;
-    if (in.hitmap) {
-        const uint32_t *hm = in.hitmap + (start >> 5);             // start is a multiple of 32
-        // a long read's hits name its own lineage over and over: each thread keeps the two labels it met last in
-        // registers and only sends a (label, count) pair on when a third one displaces it -- every thread of the
-        // CTA hammering the same two shared-memory words was what this loop spent its time on
-        uint32_t l0 = UTB_BAD32, c0 = 0, l1 = UTB_BAD32, c1 = 0;
-        uint32_t m_next = w0 + tid < w1 ? __ldg(hm + w0 + tid) : 0u;
-        for (uint64_t wi = w0 + tid; wi < w1; wi += VB_THREADS) {
-            uint32_t m = m_next;
-            m_next = wi + VB_THREADS < w1 ? __ldg(hm + wi + VB_THREADS) : 0u;
-            while (m) {
-                const uint32_t bit = __ffs(m) - 1; m &= m - 1;
-                const uint32_t h = __ldg(in.hits + start + 32ull * wi + bit);
-                if (h >= db.max_ix) continue;
-                ++n_local;
-                if (h == l0) ++c0;
-                else if (h == l1) ++c1;
-                else {
-                    if (c1) vl_add(cache, l1, c1, hist, tlab, nt);
-                    l1 = l0; c1 = c0; l0 = h; c0 = 1;
-                }
-            }
-        }
-        if (c0) vl_add(cache, l0, c0, hist, tlab, nt);
-        if (c1) vl_add(cache, l1, c1, hist, tlab, nt);
-    } else {
-        const uint64_t lo = w0 * 32u, hi = w1 * 32u < count ? w1 * 32u : count;
-        for (uint64_t base = lo; base < hi; base += VB_THREADS) {
-            const uint64_t i = base + tid;
-            const uint32_t h = i < hi ? __ldg(in.hits + start + i) : HIT_NOWIN;
-            const bool ok = h < db.max_ix;
-            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);
-            if (ok && (uint32_t)(__ffs(peers) - 1) == lane) vl_add(cache, h, (uint32_t)__popc(peers), hist, tlab, nt);
-            n_local += ok;
-        }
+    const uint64_t lo = w0 * 32u, hi = w1 * 32u < count ? w1 * 32u : count;
+    for (uint64_t base = lo; base < hi; base += VB_THREADS) {
+        const uint64_t i = base + tid;
+        const uint32_t h = i < hi ? __ldg(in.hits + start + i) : HIT_NOWIN;
+        const bool ok = h < db.max_ix;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, h);   // a long read names its own lineage over and over: one add per distinct label of the warp
+        if (ok && (uint32_t)(__ffs(peers) - 1) == lane) vl_add(cache, h, (uint32_t)__popc(peers), hist, tlab, nt);
+        n_local += ok;
     }
     return n_local;
 }
@@ -1202,6 +1185,82 @@ struct VlSmem { unsigned long long key[VB_SORT_MAX]; uint32_t warp[VB_THREADS / 
 #define VL_STR_BYTES 24576u         // their strings, NULs included
 struct VlStage { uint32_t off[VL_STAGE_MAX + 1], lab[VL_STAGE_MAX], cnt[VL_STAGE_MAX]; };
 static_assert(sizeof(VlStage) <= sizeof(unsigned long long) * VB_SORT_MAX, "VlStage lives in VlSmem::key");
+// The walk over the staged copy, one warp, 32 neighbour pairs at a time.  What the reference decides for a pair
+// (z-1, z) at a level -- the first string ended (K), same token (S), a new run that also shrinks the outer run (O),
+// different token (D) -- depends only on the two strings and the level's depth dv, so every lane classifies its own
+// pair (a short scalar scan over one token); the sequential state of itree.c:1050-1070 then is a segmented sum of the
+// counts (a new segment wherever the class is not S), a prefix sum of what K / O pairs take off the outer run, and
+// the walk stops at the first D pair whose run so far reaches the cutoff of the outer run so far.  Same results as
+// walk_warp, about a tenth of its instructions for a read that touched hundreds of labels.
+__device__ void walk_warp_staged(const VlStage *sg, const char *str, uint32_t uix, uint32_t n, utb_result *out) {
+    const uint32_t lane = threadIdx.x & 31u, FULL = 0xFFFFFFFFu, EMPTY = 0xFFFFFFFFu;
+    enum { CLS_S = 0, CLS_K = 1, CLS_O = 2, CLS_D = 3 };
+    const uint32_t *T_cnt = sg->cnt, *S_off = sg->off;
+    uint32_t st = 0, ed = uix, dv = EMPTY, orun = n, sl = 0, ol = 0, cutoff;
+    for (;;) {                                                      // itree.c:1047
+        uint32_t run = T_cnt[st], td = dv;
+        const uint32_t ed0 = ed;
+        for (uint32_t zb = st + 1; zb < ed0; zb += 32u) {           // itree.c:1050
+            const uint32_t z = zb + lane;
+            const bool valid = z < ed0;
+            uint32_t cls = CLS_S, tdz = 0, cz = 0, cprev = 0;
+            if (valid) {
+                cz = T_cnt[z]; cprev = T_cnt[z - 1];
+                const char *s1 = str + S_off[z - 1], *s2 = str + S_off[z];
+                if (!s1[dv + (dv == EMPTY)]) cls = CLS_K;           // itree.c:1052
+                else {
+                    uint32_t t = dv + 1u;                           // itree.c:1060-1061
+                    char a, b;
+                    for (;; ++t) { a = s1[t]; b = s2[t]; if (a == 0 || a != b || a == ';') break; }
+                    tdz = t;
+                    if (a == b) cls = CLS_S;                        // itree.c:1062
+                    else if ((!a && b == ';') || ((a == ';' || !a) && t > 0 && s1[t - 1] == '_')) cls = CLS_O;   // itree.c:1063
+                    else cls = CLS_D;                               // itree.c:1068-1069
+                }
+            }
+            const uint32_t hm = __ballot_sync(FULL, valid && cls != CLS_S);          // pairs that start a new run
+            const uint32_t nk = __ballot_sync(FULL, valid && cls != CLS_K);          // pairs that set td
+            uint32_t pv = cz, ps = (cls == CLS_K || cls == CLS_O) ? cprev : 0u;      // inclusive prefix sums over the lanes
+#pragma unroll
+            for (uint32_t o = 1; o < 32u; o <<= 1) {
+                const uint32_t t1 = __shfl_up_sync(FULL, pv, o), t2 = __shfl_up_sync(FULL, ps, o);
+                if (lane >= o) { pv += t1; ps += t2; }
+            }
+            const uint32_t lower = hm & (0xFFFFFFFFu >> (31u - lane));               // run starts at lanes <= this one
+            const int hs = lower ? 31 - __clz(lower) : -1;
+            const uint32_t before_hs = __shfl_sync(FULL, pv - cz, hs < 0 ? 0 : hs);
+            const uint32_t run_z = hs < 0 ? run + pv : pv - before_hs;               // run / outer run after pair z
+            const uint32_t orun_z = orun - ps;
+            uint32_t run_b = __shfl_up_sync(FULL, run_z, 1), orun_b = __shfl_up_sync(FULL, orun_z, 1);   // ... and before it
+            if (lane == 0) { run_b = run; orun_b = orun; }
+            const uint32_t bm = __ballot_sync(FULL, valid && cls == CLS_D && run_b >= cutoff_of(orun_b));
+            if (bm) {                                               // itree.c:1068: the run ends before pair zb + L
+                const uint32_t L = (uint32_t)__ffs(bm) - 1u;
+                ed = zb + L;
+                run = __shfl_sync(FULL, run_b, L); orun = __shfl_sync(FULL, orun_b, L);
+                const uint32_t hb = hm & ((1u << L) - 1u);
+                if (hb) st = zb + (31u - (uint32_t)__clz(hb));
+                td = __shfl_sync(FULL, tdz, L);
+                break;
+            }
+            run = __shfl_sync(FULL, run_z, 31); orun = __shfl_sync(FULL, orun_z, 31);
+            if (hm) st = zb + (31u - (uint32_t)__clz(hm));
+            if (nk) td = __shfl_sync(FULL, tdz, 31 - __clz(nk));
+        }
+        cutoff = cutoff_of(orun);                                   // the cutoff always is that of the outer run (itree.c:1044-1046, 1055, 1066, 1085)
+        sl = run; ol = orun;                                        // itree.c:1071
+        if (run < cutoff) break;                                    // itree.c:1072
+        if (st + 1 >= ed) {                                         // itree.c:1073-1080
+            if (T_cnt[ed - 1] >= cutoff) dv = 0xFFFFFFFEu;
+            break;
+        }
+        orun = run; dv = td;                                        // itree.c:1082-1085
+    }
+    if (lane == 0) {
+        out->kind = UTB_WALK; out->label = sg->lab[ed - 1]; out->cut = dv;
+        out->found = n; out->uix = uix; out->sl = sl; out->ol = ol; out->_pad = 0;
+    }
+}
 // block-wide; false (block-uniform): too many labels or bytes, walk from global memory
 __device__ bool vl_stage(const DevDB &db, const uint32_t *tlab, const uint32_t *tcnt, uint32_t uix, VlSmem &sm, char *str) {
     if (uix > VL_STAGE_MAX) return false;
@@ -1311,8 +1370,7 @@ __device__ void vl_finish(const DevDB &db, uint32_t *hist, uint32_t *tlab, uint3
         if (uix == 1) {                                            // itree.c:1031-1032, 1039-1040
             if (lane == 0) { out->kind = UTB_STAR; out->label = tlab[0]; out->cut = 0; out->found = n; out->uix = 1; out->sl = 0; out->ol = 0; out->_pad = 0; }
         } else if (staged) {
-            const VlStage *sg = reinterpret_cast<const VlStage *>(sm.key);
-            walk_warp(db, sg->lab, sg->cnt, uix, n, out, str, sg->off);
+            walk_warp_staged(reinterpret_cast<const VlStage *>(sm.key), str, uix, n, out);
         } else walk_warp(db, tlab, tcnt, uix, n, out);
     }
     __syncthreads();
@@ -2202,8 +2260,9 @@ struct utb_batch {
     uint32_t *d_sel_cnt, *d_sel_off, *d_sel, *d_sel_gap, *d_sel_total, *h_sel_cnt, *h_sel, *h_sel_total; size_t sel_cap;   // non-GG mode (want_text == 3)
     uint64_t *d_qwords; uint32_t *d_qslots; unsigned long long *d_qcount; uint64_t q_cap;   // filter survivors
     uint32_t *d_hitmap;
+    uint32_t *d_rid, *d_hcnt;     // group -> read, hits per read (list mode of the survivor kernel)
     // last submit
-    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_sieve;
+    size_t n_reads; uint32_t n_groups; int do_rc; int in_flight; int used_sieve, used_lists;
     uint64_t launches;
     // device-side framing
     uint32_t *d_nl, *d_blk, *d_frame_err, *h_frame_err; int framed_on_device;
@@ -2236,7 +2295,7 @@ extern "C" void utb_batch_destroy(utb_batch *b) {
     vs_free(&b->vs);
     cudaFree(b->d_sel_cnt); cudaFree(b->d_sel_off); cudaFree(b->d_sel); cudaFree(b->d_sel_gap); cudaFree(b->d_sel_total);
     cudaFreeHost(b->h_sel_cnt); cudaFreeHost(b->h_sel); cudaFreeHost(b->h_sel_total);
-    cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap);
+    cudaFree(b->d_qwords); cudaFree(b->d_qslots); cudaFree(b->d_qcount); cudaFree(b->d_hitmap); cudaFree(b->d_rid); cudaFree(b->d_hcnt);
     cudaFree(b->d_nl); cudaFree(b->d_blk); cudaFree(b->d_frame_err); cudaFreeHost(b->h_frame_err);
     cudaFree(b->d_frame_info); cudaFree(b->d_dims); cudaFreeHost(b->h_dims);
     if (b->done) cudaEventDestroy(b->done);
@@ -2306,6 +2365,8 @@ extern "C" int utb_batch_create(utb_db *db, size_t max_bytes, size_t max_reads, 
         BK(cudaMalloc(&b->d_qcount, 8));
         BK(cudaMalloc(&b->d_hitmap, (npos * 2 / 32 + 8) * 4));
         BK(cudaMalloc(&b->d_pkr, (b->max_groups + PK_GUARD + 2) * 8));
+        BK(cudaMalloc(&b->d_rid, (b->max_groups + PK_GUARD + 2) * 4));
+        BK(cudaMalloc(&b->d_hcnt, (max_reads + 1) * 4));
     }
     if (db->l2_window) {
         cudaStreamAttrValue a;
@@ -2339,7 +2400,7 @@ static int launch_stages(utb_batch *b, bool timed) {
     if (timed) CK(cudaEventRecord(b->ev[0], b->st));
     if (n_reads) {
         pack_kernel<<<gs_grid(b, (uint64_t)n_groups + PK_GUARD, 256, 32), 256, 0, b->st>>>(b->d_raw, b->d_seq_off, b->d_seq_len, b->d_grp_off,
-                                                                   n_reads, n_groups, b->dims_dev, b->d_pk, b->d_bad, b->d_pkr);
+                                                                   n_reads, n_groups, b->dims_dev, b->d_pk, b->d_bad, b->d_pkr, b->d_rid);
         b->launches++;
     }
     if (timed) CK(cudaEventRecord(b->ev[1], b->st));
@@ -2348,20 +2409,27 @@ static int launch_stages(utb_batch *b, bool timed) {
         // sieve on while misses dominate (it only adds a fetch to lookups that hit)
         const bool sieve = b->db->sieve && (b->db->sieve_mode == 1 || (b->db->sieve_mode == 2 && b->db->ema_hit_rate < 0.40));
         const unsigned sms = (unsigned)b->db->sm_count;
-        b->used_sieve = sieve;
+        b->used_sieve = sieve; b->used_lists = 0;
         if (b->db->use_table && sieve) {
             CK(cudaMemsetAsync(b->d_qcount, 0, 8, b->st));
-            // hits are sparse (only sieve survivors that really match): the survivor kernel flags them in a
-            // 1-bit-per-slot map, the vote reads the map and gathers only flagged slots
-            CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st));
+            // hits are sparse (only sieve survivors that really match).  GG path: the survivor kernel files every label
+            // under its read (list mode, see HitSink); non-GG path: by slot, flagged in a 1-bit-per-slot map
+            HitSink sink;
+            sink.hits = b->d_hits; sink.sh = nstr == 2 ? 6u : 5u;
+            const bool lists = b->want_text != 3;
+            if (lists) { sink.hitmap = nullptr; sink.rid = b->d_rid; sink.grp_off = b->d_grp_off; sink.cnt = b->d_hcnt;
+                         CK(cudaMemsetAsync(b->d_hcnt, 0, ((size_t)n_reads + 1) * 4, b->st)); }
+            else { sink.hitmap = b->d_hitmap; sink.rid = nullptr; sink.grp_off = nullptr; sink.cnt = nullptr;
+                   CK(cudaMemsetAsync(b->d_hitmap, 0, ((size_t)n_pos * nstr / 32 + 4) * 4, b->st)); }
+            b->used_lists = lists;
             if (timed) CK(cudaEventRecord(b->ev[4], b->st));
             // persistent: MINB CTAs per SM, every warp a contiguous range of steps (small batches: one tile per warp)
             static const int sv_variant = [] { const char *e = getenv("UTB_SV_VARIANT"); return e ? atoi(e) : 0; }();
 #define SV_LAUNCH(U, MINB) do { \
                 const unsigned wb = (n_groups + 8u * U - 1) / (8u * U); \
                 const unsigned pb = wb < sms * MINB ? (wb ? wb : 1u) : sms * MINB; \
-                if (nstr == 2) sieve_kernel<2, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap); \
-                else sieve_kernel<1, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hitmap); } while (0)
+                if (nstr == 2) sieve_kernel<2, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink); \
+                else sieve_kernel<1, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink); } while (0)
             switch (sv_variant) {                                   // measured on B200, 10 M x 150 bp: 8.62 / 8.83 / 10.47 / 10.54 ms
             case 1: SV_LAUNCH(4, 3); break;
             case 2: SV_LAUNCH(2, 5); break;
@@ -2370,7 +2438,8 @@ static int launch_stages(utb_batch *b, bool timed) {
             }
 #undef SV_LAUNCH
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
-            queue_lookup_kernel<<<sms * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, b->d_hits, b->d_hitmap, b->d_counters);
+            if (lists) queue_lookup_kernel<true><<<sms * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink, b->d_counters);
+            else queue_lookup_kernel<false><<<sms * 6, 256, 0, b->st>>>(d, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink, b->d_counters);
             b->launches++;
         } else if (b->db->use_table) {
             if (nstr == 2) lookup_kernel<2, true><<<nb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_hits, b->d_counters);
@@ -2398,8 +2467,8 @@ static int launch_stages(utb_batch *b, bool timed) {
     } else if (n_reads) {
         VoteIn in;
         in.hits = b->d_hits; in.grp_off = b->d_grp_off; in.seq_len = b->d_seq_len; in.off = nullptr; in.nstr = nstr;
-        in.hitmap = b->used_sieve ? b->d_hitmap : nullptr;
-        if (in.hitmap) {
+        in.cnt = b->used_lists ? b->d_hcnt : nullptr;
+        if (in.cnt) {
             // thread per read for the common case; label-rich or long reads fall through to the warp kernel
             // (and from there to the block kernel) by way of device-side lists
             CK(cudaMemsetAsync(b->d_warp_count, 0, 4, b->st));
@@ -2857,7 +2926,7 @@ extern "C" int utb_pack_sequence(utb_db *db, const char *seq, uint32_t len, uint
     CK(cudaMemcpy(d_off, &off, 8, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_len, &len, 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_grp, grp, 8, cudaMemcpyHostToDevice));
-    pack_kernel<<<(n_groups + PK_GUARD + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad, nullptr);
+    pack_kernel<<<(n_groups + PK_GUARD + 255) / 256, 256>>>(d_raw, d_off, d_len, d_grp, 1, n_groups, nullptr, d_pk, d_bad, nullptr, nullptr);
     expand_windows_kernel<<<(n_pos + 255) / 256, 256>>>(d_pk, d_bad, n_pos, d_f, d_r, d_v);
     CK(cudaGetLastError());
     CK(cudaMemcpy(fwd, d_f, (size_t)len * 8, cudaMemcpyDeviceToHost));
@@ -2890,44 +2959,38 @@ extern "C" int utb_vote_hits(utb_db *db, const uint32_t *hits, const uint64_t *o
     return UTB_OK;
 }
 
-// Same vote through the sparse representation the batch pipeline uses: every read's slots start at a
-// multiple of 32, a 1-bit-per-slot hit map flags the labels, and the reads go thread kernel -> warp
-// kernel -> block kernel by way of the device-side deferral lists.
+// Same vote through the representation the batch pipeline uses: per read a list of the labels that hit (misses
+// and windowless slots are not in it), and the reads go thread kernel -> warp kernel -> block kernel by way of the
+// device-side deferral lists.
 extern "C" int utb_vote_hits_sparse(utb_db *db, const uint32_t *hits, const uint64_t *off, size_t n_reads, utb_result *results) {
     if (!db || !off || !results || (!hits && n_reads && off[n_reads])) { utb_set_error("utb_vote_hits_sparse: null argument"); return UTB_ERR_ARG; }
     if (!n_reads) return UTB_OK;
     CK(cudaSetDevice(db->device));
     uint64_t *poff = (uint64_t *)malloc((n_reads + 1) * 8);
-    if (!poff) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    uint32_t *ph = (uint32_t *)malloc((off[n_reads] + 1) * 4);
+    if (!poff || !ph) { free(poff); free(ph); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     uint64_t tot = 0;
-    for (size_t r = 0; r < n_reads; ++r) { poff[r] = tot; tot += (off[r + 1] - off[r] + 31) / 32 * 32; }
+    for (size_t r = 0; r < n_reads; ++r) {
+        poff[r] = tot;
+        for (uint64_t i = off[r]; i < off[r + 1]; ++i) if (hits[i] < HIT_NOWIN) ph[tot++] = hits[i];
+    }
     poff[n_reads] = tot;
-    uint32_t *ph = (uint32_t *)malloc((tot + 32) * 4), *pm = (uint32_t *)calloc(tot / 32 + 2, 4);
-    if (!ph || !pm) { free(poff); free(ph); free(pm); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
-    for (uint64_t i = 0; i < tot + 32; ++i) ph[i] = HIT_MISS;
-    for (size_t r = 0; r < n_reads; ++r)
-        for (uint64_t i = 0; i < off[r + 1] - off[r]; ++i) {
-            const uint32_t h = hits[off[r] + i];
-            ph[poff[r] + i] = h;
-            if (h < HIT_NOWIN) pm[(poff[r] + i) >> 5] |= 1u << ((poff[r] + i) & 31u);
-        }
-    uint32_t *d_hits, *d_map, *d_gl, *d_gc, *d_wl, *d_wc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt; vote_scratch vs;
-    CK(cudaMalloc(&d_hits, (tot + 32) * 4)); CK(cudaMalloc(&d_map, (tot / 32 + 2) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
+    uint32_t *d_hits, *d_gl, *d_gc, *d_wl, *d_wc; uint64_t *d_off; utb_result *d_res; unsigned long long *d_cnt; vote_scratch vs;
+    CK(cudaMalloc(&d_hits, (tot + 1) * 4)); CK(cudaMalloc(&d_off, (n_reads + 1) * 8));
     CK(cudaMalloc(&d_res, n_reads * sizeof(utb_result)));
     CK(cudaMalloc(&d_gl, n_reads * 4)); CK(cudaMalloc(&d_gc, 4)); CK(cudaMalloc(&d_wl, n_reads * 4)); CK(cudaMalloc(&d_wc, 4));
     CK(cudaMalloc(&d_cnt, 4 * COUNTER_SLOTS * 8));
     { int rv = vs_alloc(db, (size_t)tot / 2 + 1, &vs); if (rv) return rv; }
     CK(cudaMemset(d_gc, 0, 4)); CK(cudaMemset(d_wc, 0, 4)); CK(cudaMemset(d_cnt, 0, 4 * COUNTER_SLOTS * 8));
-    CK(cudaMemcpy(d_hits, ph, (tot + 32) * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_map, pm, (tot / 32 + 2) * 4, cudaMemcpyHostToDevice));
+    if (tot) CK(cudaMemcpy(d_hits, ph, tot * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_off, poff, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
-    free(poff); free(ph); free(pm);
-    VoteIn in; in.hits = d_hits; in.grp_off = nullptr; in.seq_len = nullptr; in.off = d_off; in.nstr = 1; in.hitmap = d_map;
+    free(poff); free(ph);
+    VoteIn in; in.hits = d_hits; in.off = d_off; in.nstr = 1;
     vote_thread_kernel<<<(unsigned)((n_reads + VT_THREADS - 1) / VT_THREADS), VT_THREADS>>>(db->d, in, (uint32_t)n_reads, nullptr, d_res, d_wl, d_wc, d_cnt);
     vote_warp_kernel<<<(unsigned)db->sm_count * 6, VW_WARPS * 32>>>(db->d, in, (uint32_t)n_reads, nullptr, d_wl, d_wc, d_res, d_gl, d_gc, d_cnt);
     { int rv = launch_long_vote(db, in, d_res, d_gl, d_gc, &vs, d_cnt, 0); if (rv) return rv; }
     CK(cudaMemcpy(results, d_res, n_reads * sizeof(utb_result), cudaMemcpyDeviceToHost));
-    cudaFree(d_hits); cudaFree(d_map); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_wl); cudaFree(d_wc);
+    cudaFree(d_hits); cudaFree(d_off); cudaFree(d_res); cudaFree(d_gl); cudaFree(d_gc); cudaFree(d_wl); cudaFree(d_wc);
     cudaFree(d_cnt); vs_free(&vs);
     return UTB_OK;
 }
