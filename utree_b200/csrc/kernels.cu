@@ -68,8 +68,8 @@ struct DevDB {
     const uint32_t *by_rank;
     uint32_t quirk_bin;        // bucket whose record 0 is the folded foreign record, else 0xFFFFFFFF
     // regular CTRs only: the records re-keyed into a sector hash table (binix / recs are then freed)
-    const uint64_t *ktab;      // kt_sectors x 4 entries of 8 bytes
-    const uint32_t *kvals;     // IXTYPE uint32_t: the label ids, parallel to ktab (null for uint16_t: the id is in the entry)
+    const uint64_t *ktab;      // kt_sectors x 32 bytes: 4 entries of 8 bytes (uint16_t labels) or 3 wide entries (uint32_t labels)
+    uint32_t kt_wide;          // IXTYPE uint32_t: three entries per sector, the label id inside
     uint64_t kt_sectors;
     // membership pre-filter over all record words: blocked Bloom, line chosen by the word's minimizer
     const uint2 *sieve;        // sv_lines x 16 blocks of 8 bytes
@@ -81,14 +81,14 @@ struct utb_db {
     DevDB d;
     int regular;               // every bucket strictly sorted (modulo quirk_bin): the record words are distinct, a hash table is exact
     int use_table;             // lookup variant in use: 1 sector hash table (+ sieve), 0 the reference's probe sequence
-    void *binix, *recs, *blob, *off, *rank, *by_rank, *ktab, *kvals, *sieve;
+    void *binix, *recs, *blob, *off, *rank, *by_rank, *ktab, *sieve;
     int sieve_mode;            // 0 off, 1 always, 2 auto (on while the observed hit rate is low)
     volatile double ema_hit_rate;   // of the batches seen so far (written by the formatter thread, read at submit)
     size_t max_label;          // longest label, bytes
     volatile double text_per_byte;  // running estimate of output bytes per input byte (sizes the speculative text D2H)
     uint64_t hbm_bytes;
     int sm_count;              // multiprocessors of the device (grid sizing)
-    size_t nb_binix, nb_recs, nb_blob, nb_lab, nb_ktab, nb_kvals, nb_sieve;   // bytes behind the device pointers (utb_db_clone)
+    size_t nb_binix, nb_recs, nb_blob, nb_lab, nb_ktab, nb_sieve;   // bytes behind the device pointers (utb_db_clone)
     int l2_window;             // reference probe sequence only: persisting-L2 window over binix configured
     size_t l2_window_bytes;
     float l2_hit_ratio;
@@ -101,14 +101,17 @@ struct utb_db {
 // 32-bit loads (neighbouring threads share cache lines, so the raw bytes move
 // once from L2), classified four at a time with byte-SIMD compares.
 __device__ __forceinline__ uint32_t classify4(uint32_t w, uint32_t &badbits) {
-    uint32_t u = w | 0x20202020u;                      // fold case (itree.c:114-117)
-    uint32_t isA = __vcmpeq4(u, 0x61616161u), isC = __vcmpeq4(u, 0x63636363u);
-    uint32_t isG = __vcmpeq4(u, 0x67676767u), isT = __vcmpeq4(u, 0x74747474u);
-    uint32_t code = (isC & 0x01010101u) | (isG & 0x02020202u) | (isT & 0x03030303u);
-    uint32_t inval = ~(isA | isC | isG | isT) & 0x01010101u;
-    badbits = (inval * 0x01020408u) >> 24;             // bit j = byte j is not ACGTacgt
-    // first base most significant
-    return ((code & 3u) << 6) | (((code >> 8) & 3u) << 4) | (((code >> 16) & 3u) << 2) | ((code >> 24) & 3u);
+    const uint32_t u = w | 0x20202020u;                            // fold case (itree.c:114-117)
+    // bits 1 and 2 of the letter give its code: a 0x61 -> 0, c 0x63 -> 1, g 0x67 -> 2, t 0x74 -> 3 (C2Xb, itree.c:110-121)
+    const uint32_t code = ((u >> 1) ^ (u >> 2)) & 0x03030303u;
+    // a byte is a base iff it IS the letter of its code: 0x61 + {0, 2, 6, 0x13}[code], built bytewise from the code's two bits
+    const uint32_t c0 = code & 0x01010101u, c1 = (code >> 1) & 0x01010101u;
+    const uint32_t both = c0 & c1;
+    const uint32_t expect = 0x61616161u + (((c0 | c1) << 1) | ((c1 & ~c0) << 2)) + both * 0x11u;
+    const uint32_t x = u ^ expect;                                  // nonzero byte = not ACGTacgt
+    const uint32_t inval = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
+    badbits = (inval * 0x01020408u) >> 24;                          // bit j = byte j is not a base
+    return (code * 0x40100401u) >> 24;                              // first base most significant: b0 << 6 | b1 << 4 | b2 << 2 | b3
 }
 
 // reverse complement of a 32-mer word: reverse the 2-bit fields of ~w
@@ -277,8 +280,11 @@ __device__ __forceinline__ uint32_t probe_end(const DevDB &db, const Probe &q) {
 //     h = mix64(word)  (a bijection)      home sector = floor(h * S / 2^64)
 //     entry (8 B) = low 48 bits of h << 16 | tag        4 entries per sector
 // uint16_t labels: tag = 0xFFFF - id (never 0: 0xFFFE/0xFFFF are the builder's
-// sentinels, itree.c:105-107); uint32_t labels: tag = 1 and the id sits in a
-// parallel u32 array.  An entry that does not fit its home sector goes to the
+// sentinels, itree.c:105-107).  uint32_t labels: THREE entries per sector with the
+// id inside (words 0-2 the ids, 3-5 the low 32 bits of the remainders, 6-7 their
+// upper 16 bits and three "occupied" bits) -- a parallel id array costs a second
+// random access per hit, which is what bound the lookups on uint32_t trees
+// (profiles/r02_*: 22 ms of a 44 ms step).  An entry that does not fit its home sector goes to the
 // next one (linear probing over sectors, displacement <= KT_MAXD, load <= 0.5),
 // so a lookup is ONE random 32-byte access (1.06 on average) with no index in
 // front of it.  Uniqueness of the 48-bit remainder: an entry found within
@@ -292,8 +298,32 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {           // murmur3 fin
     x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
     return x ^ (x >> 33);
 }
+// uint32_t labels (see above).  Sector as two uint4: a = {id0, id1, id2, lo0}, b = {lo1, lo2, hi0 | hi1 << 16, hi2 | occupied << 16}
+__device__ __forceinline__ uint32_t kt_lookup_wide(const DevDB &db, uint64_t word, uint32_t *sect) {
+    const uint64_t h = mix64(word);
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32) & 0xFFFFu;
+    uint64_t s = __umul64hi(h, db.kt_sectors);
+    uint32_t ns = 0, r = HIT_MISS;
+    for (uint32_t d = 0; d <= KT_MAXD; ++d) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(db.ktab + s * 4);
+        const uint4 a = __ldg(p), b = __ldg(p + 1);
+        ++ns;
+        const uint32_t occ = b.w >> 16;
+        uint32_t ix = HIT_MISS;
+        bool found = false;
+        if ((occ & 1u) && a.w == lo && (b.z & 0xFFFFu) == hi) { ix = a.x; found = true; }
+        if ((occ & 2u) && b.x == lo && (b.z >> 16) == hi) { ix = a.y; found = true; }
+        if ((occ & 4u) && b.y == lo && (b.w & 0xFFFFu) == hi) { ix = a.z; found = true; }
+        if (found) { r = ix < db.max_ix ? ix : HIT_MISS; break; }   // itree.c:929
+        if (occ != 7u) break;                                      // a free slot: the word was never displaced past here
+        if (++s == db.kt_sectors) s = 0;
+    }
+    if (sect) *sect = ns;
+    return r;
+}
 // sect (optional): 32-byte sectors this lookup touched
 __device__ __forceinline__ uint32_t kt_lookup(const DevDB &db, uint64_t word, uint32_t *sect = nullptr) {
+    if (db.kt_wide) return kt_lookup_wide(db, word, sect);
     const uint64_t h = mix64(word), rem = h << 16;
     uint64_t s = __umul64hi(h, db.kt_sectors);
     uint32_t ns = 0, r = HIT_MISS;
@@ -307,9 +337,7 @@ __device__ __forceinline__ uint32_t kt_lookup(const DevDB &db, uint64_t word, ui
 #pragma unroll
         for (int j = 0; j < 4; ++j) if (e[j] && ((e[j] ^ rem) >> 16) == 0) { at = j; tag = (uint32_t)(e[j] & 0xFFFFu); }
         if (at >= 0) {
-            uint32_t ix;
-            if (db.kvals) { ix = __ldg(db.kvals + s * 4 + at); ++ns; }
-            else ix = 0xFFFFu - tag;
+            const uint32_t ix = 0xFFFFu - tag;
             r = ix < db.max_ix ? ix : HIT_MISS;                    // itree.c:929
             break;
         }
@@ -322,7 +350,7 @@ __device__ __forceinline__ uint32_t kt_lookup(const DevDB &db, uint64_t word, ui
 // G lanes per prefix bin walk the bin's records (bins are taken as the index gives them, itree.c:722-726)
 template <int G>
 __global__ void __launch_bounds__(256)
-ktab_build_kernel(DevDB db, unsigned long long *__restrict__ ktab, uint32_t *__restrict__ kvals, uint64_t n_sectors,
+ktab_build_kernel(DevDB db, unsigned long long *__restrict__ ktab, uint32_t wide, uint64_t n_sectors,
                   uint32_t *__restrict__ overflow) {
     const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t p = t / G;
@@ -337,17 +365,35 @@ ktab_build_kernel(DevDB db, unsigned long long *__restrict__ ktab, uint32_t *__r
         const uint64_t word = (p << 40) | load_suffix(db.recs, i * db.sz);
         const uint32_t ix = load_ix(db, i);
         const uint64_t h = mix64(word);
-        const unsigned long long entry = (h << 16) | (kvals ? 1ull : (unsigned long long)(0xFFFFu - (ix & 0xFFFFu)));
-        if (!kvals && ix >= 0xFFFEu) continue;                     // sentinel ids never pass ix < maxIX (itree.c:929)
         uint64_t s = __umul64hi(h, n_sectors);
         bool placed = false;
-        for (uint32_t d = 0; d <= KT_MAXD && !placed; ++d) {
+        if (wide) {
+            if (ix >= db.max_ix) continue;                         // never passes ix < maxIX (itree.c:929): as good as absent
+            for (uint32_t d = 0; d <= KT_MAXD && !placed; ++d) {
+                uint32_t *w = reinterpret_cast<uint32_t *>(ktab + s * 4);
 #pragma unroll
-            for (int j = 0; j < 4 && !placed; ++j) {
-                if (ktab[s * 4 + j]) continue;
-                if (atomicCAS(ktab + s * 4 + j, 0ull, entry) == 0ull) { placed = true; if (kvals) kvals[s * 4 + j] = ix; }
+                for (uint32_t j = 0; j < 3 && !placed; ++j) {
+                    const uint32_t bit = 1u << (16u + j);
+                    if (w[7] & bit) continue;
+                    if (atomicOr(w + 7, bit) & bit) continue;      // somebody else took it
+                    w[j] = ix; w[3 + j] = (uint32_t)h;
+                    const uint32_t hi = (uint32_t)(h >> 32) & 0xFFFFu;
+                    if (j == 0) atomicOr(w + 6, hi); else if (j == 1) atomicOr(w + 6, hi << 16); else atomicOr(w + 7, hi);
+                    placed = true;
+                }
+                if (!placed && ++s == n_sectors) s = 0;
             }
-            if (!placed && ++s == n_sectors) s = 0;
+        } else {
+            const unsigned long long entry = (h << 16) | (unsigned long long)(0xFFFFu - (ix & 0xFFFFu));
+            if (ix >= 0xFFFEu) continue;                           // sentinel ids never pass ix < maxIX (itree.c:929)
+            for (uint32_t d = 0; d <= KT_MAXD && !placed; ++d) {
+#pragma unroll
+                for (int j = 0; j < 4 && !placed; ++j) {
+                    if (ktab[s * 4 + j]) continue;
+                    if (atomicCAS(ktab + s * 4 + j, 0ull, entry) == 0ull) placed = true;
+                }
+                if (!placed && ++s == n_sectors) s = 0;
+            }
         }
         if (!placed) atomicAdd(overflow, 1u);
     }
@@ -2038,27 +2084,27 @@ static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
     }
     if (db->use_table) {
         const uint64_t n = db->d.num_nodes;
-        // sector hash table at load <= 0.5 (4 entries per sector); grown if a record cannot be placed within KT_MAXD sectors
-        uint64_t sectors = n / 2 + 1;
+        // sector hash table at load <= 0.5 (4 entries per sector, 3 with uint32_t labels); grown if a record cannot be placed within KT_MAXD sectors
+        const uint32_t wide = db->d.ix_bytes == 4;
+        uint64_t sectors = wide ? n / 3 * 2 + 1 : n / 2 + 1;
         if (sectors < KT_MIN_SECTORS) sectors = KT_MIN_SECTORS;
         uint32_t *d_ovf;
         CK(cudaMalloc(&d_ovf, 4));
         for (int attempt = 0;; ++attempt) {
             cudaError_t e = cudaMalloc(&db->ktab, sectors * 32);
-            if (e == cudaSuccess && db->d.ix_bytes == 4) e = cudaMalloc(&db->kvals, sectors * 16);
             if (e == cudaSuccess) e = cudaMemset(db->ktab, 0, sectors * 32);
             if (e == cudaSuccess) e = cudaMemset(d_ovf, 0, 4);
             if (e != cudaSuccess) { cudaFree(d_ovf); CK(e); }
             DevDB dd = db->d;
-            unsigned long long *kt = (unsigned long long *)db->ktab; uint32_t *kv = (uint32_t *)db->kvals;
+            unsigned long long *kt = (unsigned long long *)db->ktab;
             launch_per_bin(n, [&](int g, unsigned blocks) {
                 switch (g) {
-                case 1: ktab_build_kernel<1><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
-                case 2: ktab_build_kernel<2><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
-                case 4: ktab_build_kernel<4><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
-                case 8: ktab_build_kernel<8><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
-                case 16: ktab_build_kernel<16><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
-                default: ktab_build_kernel<32><<<blocks, 256>>>(dd, kt, kv, sectors, d_ovf); break;
+                case 1: ktab_build_kernel<1><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
+                case 2: ktab_build_kernel<2><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
+                case 4: ktab_build_kernel<4><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
+                case 8: ktab_build_kernel<8><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
+                case 16: ktab_build_kernel<16><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
+                default: ktab_build_kernel<32><<<blocks, 256>>>(dd, kt, wide, sectors, d_ovf); break;
                 }
             });
             uint32_t ovf = 0;
@@ -2066,13 +2112,13 @@ static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
             if (e == cudaSuccess) e = cudaMemcpy(&ovf, d_ovf, 4, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { cudaFree(d_ovf); CK(e); }
             if (!ovf) break;
-            cudaFree(db->ktab); cudaFree(db->kvals); db->ktab = db->kvals = nullptr;
+            cudaFree(db->ktab); db->ktab = nullptr;
             if (attempt == 3) { cudaFree(d_ovf); utb_set_error("cannot build the lookup table (%u records unplaced)", ovf); return UTB_ERR_LIMIT; }
             sectors += sectors / 2;
         }
         cudaFree(d_ovf);
-        db->d.ktab = (const uint64_t *)db->ktab; db->d.kvals = (const uint32_t *)db->kvals; db->d.kt_sectors = sectors;
-        db->nb_ktab = sectors * 32; db->nb_kvals = db->kvals ? sectors * 16 : 0;
+        db->d.ktab = (const uint64_t *)db->ktab; db->d.kt_wide = wide; db->d.kt_sectors = sectors;
+        db->nb_ktab = sectors * 32;
         const char *bm = getenv("UTB_SIEVE");                      // 0 off, 1 always, default auto
         db->sieve_mode = bm ? (atoi(bm) == 0 ? 0 : atoi(bm) == 1 ? 1 : 2) : 2;
         if (db->sieve_mode) {
@@ -2103,7 +2149,7 @@ static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
         CK(cudaFree(db->recs)); CK(cudaFree(db->binix));           // the on-disk image is no longer needed
         db->recs = db->binix = nullptr; db->d.recs = nullptr; db->d.binix32 = nullptr; db->d.binix64 = nullptr;
         db->nb_recs = db->nb_binix = 0;
-        db->hbm_bytes = db->nb_ktab + db->nb_kvals + db->nb_sieve + fixed;
+        db->hbm_bytes = db->nb_ktab + db->nb_sieve + fixed;
     } else {
         // Reference probe sequence: the hot prefix table pinned in L2 -- reserve persisting lines for the
         // index so the record traffic does not evict it (applied per stream in utb_batch_create).
@@ -2123,7 +2169,7 @@ static int db_build_tables(utb_db *db, size_t nb_binix, size_t nb_recs) {
     if (getenv("UTB_STATS"))
         fprintf(stderr, "utree-b200: device %d: %s, %.2f GB resident (table %.2f GB, sieve %.2f GB)\n", db->device,
                 db->use_table ? "sector hash table" : "reference probe sequence", db->hbm_bytes / 1e9,
-                (db->nb_ktab + db->nb_kvals) / 1e9, db->nb_sieve / 1e9);
+                db->nb_ktab / 1e9, db->nb_sieve / 1e9);
     return UTB_OK;
 }
 
@@ -2139,7 +2185,7 @@ extern "C" int utb_db_clone(const utb_db *src, int device, utb_db **out) {
     if (!db) { utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     *db = *src;
     db->device = device;
-    db->binix = db->recs = db->blob = db->off = db->rank = db->by_rank = db->ktab = db->kvals = db->sieve = nullptr;
+    db->binix = db->recs = db->blob = db->off = db->rank = db->by_rank = db->ktab = db->sieve = nullptr;
     if (cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || db->sm_count < 1) { cudaGetLastError(); db->sm_count = 148; }
     int can = 0;
     if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
@@ -2149,7 +2195,7 @@ extern "C" int utb_db_clone(const utb_db *src, int device, utb_db **out) {
     struct { void **dst; void *from; size_t n; } parts[] = {
         {&db->binix, src->binix, src->nb_binix ? src->nb_binix + 64 : 0}, {&db->recs, src->recs, src->nb_recs ? src->nb_recs + 64 : 0},
         {&db->blob, src->blob, src->nb_blob}, {&db->off, src->off, src->nb_lab}, {&db->rank, src->rank, src->nb_lab},
-        {&db->by_rank, src->by_rank, src->nb_lab}, {&db->ktab, src->ktab, src->nb_ktab}, {&db->kvals, src->kvals, src->nb_kvals},
+        {&db->by_rank, src->by_rank, src->nb_lab}, {&db->ktab, src->ktab, src->nb_ktab},
         {&db->sieve, src->sieve, src->nb_sieve}};
     cudaError_t e = cudaSuccess;
     for (size_t i = 0; i < sizeof parts / sizeof parts[0] && e == cudaSuccess; ++i) {
@@ -2167,7 +2213,7 @@ extern "C" int utb_db_clone(const utb_db *src, int device, utb_db **out) {
     db->d.recs = (const uint8_t *)db->recs;
     db->d.blob = (const char *)db->blob; db->d.off = (const uint32_t *)db->off;
     db->d.rank = (const uint32_t *)db->rank; db->d.by_rank = (const uint32_t *)db->by_rank;
-    db->d.ktab = (const uint64_t *)db->ktab; db->d.kvals = (const uint32_t *)db->kvals; db->d.sieve = (const uint2 *)db->sieve;
+    db->d.ktab = (const uint64_t *)db->ktab; db->d.sieve = (const uint2 *)db->sieve;
     if (db->l2_window && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, db->l2_window_bytes) != cudaSuccess) { cudaGetLastError(); db->l2_window = 0; }
     *out = db;
     return UTB_OK;
@@ -2176,7 +2222,7 @@ extern "C" int utb_db_clone(const utb_db *src, int device, utb_db **out) {
 extern "C" void utb_db_free(utb_db *db) {
     if (!db) return;
     cudaSetDevice(db->device);
-    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob); cudaFree(db->ktab); cudaFree(db->kvals); cudaFree(db->sieve);
+    cudaFree(db->binix); cudaFree(db->recs); cudaFree(db->blob); cudaFree(db->ktab); cudaFree(db->sieve);
     cudaFree(db->off); cudaFree(db->rank); cudaFree(db->by_rank);
     free(db);
 }
@@ -2202,9 +2248,10 @@ static int vs_alloc(const utb_db *db, size_t max_bytes, vote_scratch *vs) {
     if (pool > VBIG_POOL_MAX) pool = VBIG_POOL_MAX;
     if (pool < 1) pool = 1;
     vs->vl.pool = (uint32_t)pool;
-    size_t split_bases = max_bytes / pool + 1;                     // no more than `pool` reads of a batch can be longer than that
-    if (split_bases < ((size_t)64 << 10)) split_bases = (size_t)64 << 10;
-    vs->vl.split_slots = 2ull * split_bases;
+    // entries (hits in list mode, lookup slots otherwise) beyond which a read is split across the grid; when more than
+    // `pool` reads of a batch qualify the rest are voted by one CTA each, as the shorter ones are
+    vs->vl.split_slots = (size_t)128 << 10;
+    (void)max_bytes;
     const char *e = getenv("UTB_VOTE_SPLIT_SLOTS");                // tests: a small threshold sends short "long" reads through the split path
     if (e && atoll(e) > 0) vs->vl.split_slots = (unsigned long long)atoll(e);
     vs->vl.sort_max = VB_SORT_MAX;
