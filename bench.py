@@ -71,6 +71,7 @@ CONFIGS = {
                   desc="small synthetic CTR (108 genomes x 0.4 Mb, complevel 2) vs 400k x 150bp reads, RC"),
 }
 SEED = 20260101
+ALL_CPUS = os.sched_getaffinity(0)
 CHUNK_BYTES = 1_900_000_000          # raw bytes of one resident batch (positions x 2 strands must fit 32 bits)
 
 
@@ -269,6 +270,50 @@ def chunks_of(off, limit=CHUNK_BYTES, max_reads=10_000_000):
     return out
 
 
+def bind_near_gpu(index):
+    """N > 1: run this rank (and so page-lock its host buffers) on the cores of the NUMA node its GPU hangs off, the way
+    one would start it under numactl.  Returns what it did, for the JSON line; any failure leaves the affinity alone."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}/"
+        node = int(open(base + "numa_node").read())
+        cpus = set()
+        for part in open(base + "local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return {"numa_node": node, "bound": False}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "bound": True, "cpus": len(cpus)}
+    except Exception as e:                                           # noqa: BLE001
+        return {"bound": False, "why": str(e)[:80]}
+
+
+def mem_interleave(on):
+    """Page placement of what this process allocates next: spread over all NUMA nodes (a buffer every GPU reads) or the
+    default again.  Best effort."""
+    try:
+        import ctypes, platform
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+        if nr is None:
+            return False
+        mask = 0
+        if on:
+            for part in open("/sys/devices/system/node/online").read().strip().split(","):
+                a, _, b = part.partition("-")
+                for n in range(int(a), int(b or a) + 1):
+                    mask |= 1 << n
+            if mask & (mask - 1) == 0:
+                return False
+        m = ctypes.c_ulong(mask)
+        return ctypes.CDLL(None, use_errno=True).syscall(nr, 3 if on else 0, ctypes.byref(m) if on else None, 65 if on else 0) == 0
+    except Exception:                                                # noqa: BLE001
+        return False
+
+
 def cli_run(exe, ctr_path, fasta, out, threads):
     t = time.time()
     p = subprocess.run([exe, ctr_path, fasta, out, str(threads), "RC"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
@@ -317,6 +362,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU fallback")
     torch.cuda.set_device(local)
     cpu_group = None
+    numa = bind_near_gpu(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         cpu_group = dist.new_group(backend="gloo")          # host-side waits that must not park a kernel on the GPUs
@@ -568,6 +614,8 @@ def main():
                    "hbm_bytes": hbm_bytes, "load_s": round(db_load_s, 1)},
             "hit_rate": round(hits / max(lookups, 1), 4), "lookups_per_read": round(lookups / n_reads, 2),
         }
+        if numa is not None:
+            line["host_affinity"] = dict(numa, note="each rank runs on the cores local to its GPU (rank 0 shown)")
         line.update(extra)
     searcher.destroy(); ctr.close()
     if world > 1:
@@ -634,7 +682,10 @@ def extra_legs(args, cfg, capi, searcher, ctr, ctr_path, reads_np, off, out_text
         log(f"e2e_pageable leg failed: {e}")
     if world > 1:
         try:    # ---- ONE searcher over all devices: strong scaling of one FASTA of world x the reads
+            os.sched_setaffinity(0, ALL_CPUS)                       # this leg drives every GPU from one process: all cores, input spread over the nodes
+            spread = mem_interleave(True)
             big, boff = make_reads(cfg, 0, n_reads * world, local, pin=True)
+            mem_interleave(False)
             s2 = capi.Searcher(ctr, devices=tuple(range(world)), host_threads=max(2, (os.cpu_count() or 2) // 2))
             n_out = None
             for _ in range(2):
@@ -647,7 +698,7 @@ def extra_legs(args, cfg, capi, searcher, ctr, ctr_path, reads_np, off, out_text
                 assert rc_ == 0 and nb == n_out
             dt = (time.time() - t) / k
             ex["single_process"] = {"value": round(n_reads * world / dt, 1), "unit": "reads/s", "ms_per_step": round(dt * 1e3, 1),
-                                    "n_devices": world, "reads": n_reads * world, "out_bytes": int(n_out),
+                                    "n_devices": world, "reads": n_reads * world, "out_bytes": int(n_out), "input_interleaved_over_numa_nodes": bool(spread),
                                     "how": "ONE utb_searcher over all devices (tables uploaded once, cloned over NVLink), one FASTA, "
                                            "ordered merge; the other ranks idle on the host"}
             s2.destroy()

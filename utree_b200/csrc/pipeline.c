@@ -29,6 +29,7 @@
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/vfs.h>
 #include <time.h>
 #include <unistd.h>
@@ -140,12 +141,39 @@ struct utb_searcher {
     uint32_t *tally;               /* its Hashes (itree.c:971) */
     char *arena; size_t arena_cap; /* page-locked output of utb_search_mem: the devices copy their text straight into it; valid until
                                     * the next search on this searcher or its destruction */
+    int spread;                    /* more than one physical GPU: page-locked buffers are interleaved over the NUMA nodes */
 };
 
 static double now_s(void) {
     struct timespec ts;
     clock_gettime(CLOCK_MONOTONIC, &ts);
     return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* A searcher over several GPUs: its page-locked buffers (batch staging, output arena) are read and written by all of
+ * them, so their pages are spread over the NUMA nodes instead of landing on the node of the thread that happened to
+ * allocate them (one socket's memory controllers would carry every GPU's DMA).  Best effort: a kernel that refuses
+ * set_mempolicy (seccomp) leaves the default placement. */
+static void mem_interleave(int on) {
+#ifdef SYS_set_mempolicy
+    unsigned long mask = 0;
+    if (on) {
+        FILE *f = fopen("/sys/devices/system/node/online", "r");
+        if (!f) return;
+        int a, b; char sep;
+        while (fscanf(f, "%d", &a) == 1) {
+            b = a;
+            if (fscanf(f, "%c", &sep) == 1 && sep == '-') { if (fscanf(f, "%d", &b) != 1) b = a; if (fscanf(f, "%c", &sep) != 1) sep = 0; }
+            for (int n = a; n <= b && n < 64; ++n) mask |= 1ul << n;
+            if (sep != ',') break;
+        }
+        fclose(f);
+        if (!(mask & (mask - 1))) return;                          /* one node: nothing to spread */
+    }
+    (void)syscall(SYS_set_mempolicy, on ? 3 /* MPOL_INTERLEAVE */ : 0 /* MPOL_DEFAULT */, on ? &mask : NULL, on ? 65ul : 0ul);
+#else
+    (void)on;
+#endif
 }
 
 int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
@@ -178,6 +206,8 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     if (!s->devices || !s->dbs || !s->slots) { utb_searcher_destroy(s); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
     /* one upload + table build (PCIe); a repeated device shares that handle, every further GPU gets the
      * finished tables by peer copy over NVLink */
+    for (int d = 1; d < n_devices; ++d) if (devices[d] != devices[0]) s->spread = 1;
+    { const char *sp = getenv("UTB_NUMA_SPREAD"); if (sp) s->spread = atoi(sp) != 0; }
     for (int d = 0; d < n_devices; ++d) {
         s->devices[d] = devices[d];
         int rc = UTB_OK, shared = -1;
@@ -190,8 +220,10 @@ int utb_searcher_create(const utb_ctr *ctr, const int *devices, int n_devices,
     for (int i = 0; i < s->n_slots; ++i) {
         slot_t *sl = &s->slots[i];
         sl->dev_index = i % n_devices;
+        if (s->spread) mem_interleave(1);
         int rc = utb_batch_create(s->dbs[sl->dev_index], s->batch_bytes, s->batch_reads, &sl->b);
         if (!rc) rc = utb_batch_prepare(sl->b, s->device_format, s->device_frame);   /* nothing is allocated inside a search */
+        if (s->spread) mem_interleave(0);
         if (rc) { utb_searcher_destroy(s); return rc; }
         sl->name_off = utb_batch_name_off(sl->b);                  /* pinned: the device formatter reads them too */
         sl->name_len = utb_batch_name_len(sl->b);
@@ -351,7 +383,10 @@ static int sink_reserve(sink_t *k, size_t upto) {
     size_t nc = s->arena_cap ? s->arena_cap + s->arena_cap / 2 : (k->hint > ((size_t)1 << 24) ? k->hint : (size_t)1 << 24);
     if (nc < upto) nc = upto + upto / 4;
     void *m = NULL;
-    if (utb_pinned_alloc(nc, &m)) { k->failed = 1; return -1; }
+    if (s->spread) mem_interleave(1);
+    int arc = utb_pinned_alloc(nc, &m);
+    if (s->spread) mem_interleave(0);
+    if (arc) { k->failed = 1; return -1; }
     if (s->arena) {
         for (int i = 0; i < s->n_slots; ++i) utb_batch_sync(s->slots[i].b);   /* copies still in flight into the old arena */
         memcpy(m, s->arena, k->off);
