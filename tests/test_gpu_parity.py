@@ -301,6 +301,19 @@ def test_cli_binary_matches_reference(ctrs, tmp_path, db_name, reads, out, rc):
     assert lines[-2] == f"Good finds: {n_out}"
 
 
+@pytest.mark.parametrize("variant", ["1", "2", "3", "4"])
+def test_cli_sieve_kernel_variants_agree(ctrs, tmp_path, variant):
+    """UTB_SV_VARIANT picks another (steps per tile, CTAs per SM) instantiation of the sieve kernel once per process;
+    every one must write the golden bytes (reads of 150 bp and the 64 kb queries, whose tiles run into the guard groups)."""
+    exe = os.path.join(ROOT, "bin", "utree-search_gg")
+    o = str(tmp_path / "cli.out")
+    for reads, out in (("toyA_reads.fa", "toyA_rc.out"), ("long_reads.fa", "long_rc.out"), ("edge_reads.fa", "edge_rc.out")):
+        p = subprocess.run([exe, ctrs["toyA"], gold(reads), o, "2", "RC"], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, UTB_SV_VARIANT=variant, UTB_SIEVE="1"))
+        assert p.returncode == 0, p.stderr
+        assert open(o, "rb").read() == open(gold(out), "rb").read(), (variant, reads)
+
+
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "utree-build_gg")), reason="oracle/_ref not built")
 @pytest.mark.parametrize("complevel", [0, 2])
 def test_synthetic_ctr_equals_reference_built_tree(built, tmp_path, complevel):

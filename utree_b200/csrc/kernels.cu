@@ -2477,11 +2477,15 @@ static int launch_stages(utb_batch *b, bool timed) {
                 const unsigned pb = wb < sms * MINB ? (wb ? wb : 1u) : sms * MINB; \
                 if (nstr == 2) sieve_kernel<2, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink); \
                 else sieve_kernel<1, U, MINB><<<pb, 256, 0, b->st>>>(d, b->d_pk, b->d_bad, b->d_pkr, n_pos, b->dims_dev ? b->dims_dev + 1 : nullptr, b->d_counters, b->d_qwords, b->d_qslots, b->d_qcount, b->q_cap, sink); } while (0)
-            switch (sv_variant) {                                   // measured on B200, 10 M x 150 bp: 8.62 / 8.83 / 10.47 / 10.54 ms
+            // measured on B200, 10 M x 150 bp (profiles/r02_sieve_variants.txt): U = 6 steps per tile at 3 CTAs per SM (80
+            // registers) 8.54 ms; (5, 3) 8.60; (4, 3) 8.81; (4, 4) 8.98 (64 registers: 16 of them spilled); (3, 4) 9.22;
+            // (4, 5) 9.85; (2, 5) 10.5; (6, 2) 9.66; (8, 2) 9.88 -- instructions per step, not occupancy, decide
+            switch (sv_variant) {
             case 1: SV_LAUNCH(4, 3); break;
-            case 2: SV_LAUNCH(2, 5); break;
+            case 2: SV_LAUNCH(4, 4); break;
             case 3: SV_LAUNCH(2, 6); break;
-            default: SV_LAUNCH(4, 4); break;
+            case 4: SV_LAUNCH(5, 3); break;
+            default: SV_LAUNCH(6, 3); break;
             }
 #undef SV_LAUNCH
             if (timed) CK(cudaEventRecord(b->ev[5], b->st));
