@@ -4,7 +4,7 @@
 # --set full capture of its hot kernels (both only after the plain run exited 0).  TAG names the outputs in gpurun_out/.
 mkdir -p gpurun_out
 T=${TAG:-r02}
-( time python -m pytest tests -m gpu -q --durations=6 ) > gpurun_out/${T}_gputests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/${T}_gputests.log
+[ -z "$SKIP_TESTS" ] && { ( time python -m pytest tests -m gpu -q --durations=6 ) > gpurun_out/${T}_gputests.log 2>&1; echo "gpu tests rc=$?"; tail -3 gpurun_out/${T}_gputests.log; }
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${T}_smoke.log 2>&1; echo "smoke rc=$?"
 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_l2s.json 2> gpurun_out/${T}_bench_l2s.err; rc=$?; echo "bench rc=$rc"; [ $rc -ne 0 ] && { tail -30 gpurun_out/${T}_bench_l2s.err; exit 1; }
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_reference_arm.json 2> gpurun_out/${T}_bench_reference_arm.err; echo "reference arm rc=$?"

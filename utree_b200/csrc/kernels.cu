@@ -25,7 +25,7 @@
 //
 // Kernels: nl_count / nl_index / frame_parse (XT_INITIATE_WS, itree.c:860-901),
 // pack_kernel (XT_WORD_SEARCH's 2-bit packing, itree.c:919-926), sieve_kernel
-// (membership pre-filter, one 16-byte fetch per position for both strands, one DRAM
+// (membership pre-filter, one 8-byte fetch per position for both strands, one DRAM
 // line per ~9 positions) and queue_lookup_kernel (XT_getIX32 + xtSuffixBS on the
 // survivors, itree.c:699-730), lookup_kernel (the same without pre-filter, or the
 // reference's exact probe sequence), vote_thread / vote_warp / vote_block (full
@@ -827,6 +827,28 @@ __device__ __forceinline__ uint32_t cutoff_of(uint32_t x) {   // itree.c:1044-10
     return c;
 }
 
+// itree.c:1060-1061 for one thread: the first t' >= t with s1[t'] == 0 || s1[t'] != s2[t'] || s1[t'] == ';', and the two
+// characters there.  Both strings start at a multiple of 8 bytes and are NUL-padded to the next one (the device blob,
+// the staged copy), and agree below t: eight characters per step from the same offset in both.
+__device__ __forceinline__ unsigned long long nz_bytes(unsigned long long v) {    // bit 7 of every nonzero byte
+    return (((v & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | v) & 0x8080808080808080ull;
+}
+__device__ __forceinline__ uint32_t scan_token(const char *s1, const char *s2, uint32_t t, char &a, char &b) {
+    uint32_t tb = t & ~7u;
+    unsigned long long keep = ~0ull << (8u * (t & 7u));
+    for (;;) {
+        const unsigned long long x1 = *reinterpret_cast<const unsigned long long *>(s1 + tb);
+        const unsigned long long x2 = *reinterpret_cast<const unsigned long long *>(s2 + tb);
+        const unsigned long long stop = ((nz_bytes(x1) & nz_bytes(x1 ^ 0x3B3B3B3B3B3B3B3Bull)) ^ 0x8080808080808080ull | nz_bytes(x1 ^ x2)) & keep;
+        if (stop) {
+            const uint32_t k = ((uint32_t)__ffsll((long long)stop) - 1u) >> 3;
+            a = (char)(x1 >> (8u * k)); b = (char)(x2 >> (8u * k));
+            return tb + k;
+        }
+        tb += 8u; keep = ~0ull;
+    }
+}
+
 // The aufbau walk, executed by one converged warp; every lane carries the same
 // scalar state, the character scans are done 32 bytes at a time with ballots.
 // T_lab/T_cnt: the distinct labels of the read in strcmp order with counts
@@ -1054,10 +1076,8 @@ __device__ __forceinline__ void walk_thread(const DevDB &db, const uint32_t *T_l
                 continue;
             }
             // itree.c:1060-1061: first td >= dv+1 with s1[td]==0 || s1[td]!=s2[td] || s1[td]==';'
-            uint32_t t = dv + 1u;
             char a, b;
-            for (;; ++t) { a = s1[t]; b = s2[t]; if (a == 0 || a != b || a == ';') break; }
-            td = t;
+            td = scan_token(s1, s2, dv + 1u, a, b);
             if (a == b) run += TC(z);                               // itree.c:1062
             else if ((!a && b == ';') ||
                      ((a == ';' || !a) && td > 0 && s1[td - 1] == '_')) {   // itree.c:1063
@@ -1255,9 +1275,8 @@ __device__ void walk_warp_staged(const VlStage *sg, const char *str, uint32_t ui
                 const char *s1 = str + S_off[z - 1], *s2 = str + S_off[z];
                 if (!s1[dv + (dv == EMPTY)]) cls = CLS_K;           // itree.c:1052
                 else {
-                    uint32_t t = dv + 1u;                           // itree.c:1060-1061
                     char a, b;
-                    for (;; ++t) { a = s1[t]; b = s2[t]; if (a == 0 || a != b || a == ';') break; }
+                    const uint32_t t = scan_token(s1, s2, dv + 1u, a, b);   // itree.c:1060-1061
                     tdz = t;
                     if (a == b) cls = CLS_S;                        // itree.c:1062
                     else if ((!a && b == ';') || ((a == ';' || !a) && t > 0 && s1[t - 1] == '_')) cls = CLS_O;   // itree.c:1063
@@ -1321,7 +1340,7 @@ __device__ bool vl_stage(const DevDB &db, const uint32_t *tlab, const uint32_t *
             if (m) { len = t0 + (uint32_t)__ffs(m); break; }
             t0 += 32u;
         }
-        if (lane == 0) sg->off[i + 1] = len;
+        if (lane == 0) sg->off[i + 1] = (len + 7u) & ~7u;          // staged like the blob: multiples of 8, NUL-padded
     }
     __syncthreads();
     if (wid == 0) {                                                // lengths -> offsets
@@ -1339,7 +1358,7 @@ __device__ bool vl_stage(const DevDB &db, const uint32_t *tlab, const uint32_t *
     if (sm.base + 32u > VL_STR_BYTES) return false;                // the walk reads up to 31 bytes past a NUL
     for (uint32_t i = wid; i < uix; i += VB_THREADS / 32) {
         const char *p = db.blob + __ldg(db.off + sg->lab[i]);
-        const uint32_t a = sg->off[i], len = sg->off[i + 1] - a;
+        const uint32_t a = sg->off[i], len = sg->off[i + 1] - a;       // the blob's own padding comes along
         for (uint32_t j = lane; j < len; j += 32u) str[a + j] = p[j];
     }
     __syncthreads();
@@ -1427,7 +1446,7 @@ vote_block_kernel(DevDB db, VoteIn in, utb_result *__restrict__ results,
                   VoteLong vl, unsigned long long *__restrict__ counters) {
     __shared__ VlSmem sm;
     __shared__ VlCache cache;
-    __shared__ char str[VL_STR_BYTES];
+    __shared__ __align__(8) char str[VL_STR_BYTES];
     __shared__ uint32_t s_nt, s_n, s_big, s_qi;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
     uint32_t *hist = vl.hist + (size_t)blockIdx.x * db.max_ix;
@@ -1493,7 +1512,7 @@ vote_big_count_kernel(DevDB db, VoteIn in, VoteLong vl) {
 __global__ void __launch_bounds__(VB_THREADS)
 vote_big_finish_kernel(DevDB db, VoteLong vl, utb_result *__restrict__ results, unsigned long long *__restrict__ counters) {
     __shared__ VlSmem sm;
-    __shared__ char str[VL_STR_BYTES];
+    __shared__ __align__(8) char str[VL_STR_BYTES];
     const uint32_t n_big = min(*vl.big_state, vl.pool);
     for (uint32_t bi = blockIdx.x; bi < n_big; bi += gridDim.x)
         vl_finish(db, vl.big_hist + (size_t)bi * db.max_ix, vl.big_tlab + (size_t)bi * db.max_ix, vl.big_tcnt + (size_t)bi * db.max_ix,
@@ -1665,8 +1684,15 @@ __device__ __forceinline__ uint32_t dec_digits(uint32_t v) {
     return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u :
            v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
 }
+// strlen of a label: the blob keeps every string at a multiple of 8 bytes, NUL-padded to the next (>= 1 NUL), so the
+// length is the string's span minus the NULs at the end of its last 8-byte word
+__device__ __forceinline__ uint32_t label_len(const DevDB &db, uint32_t label) {
+    const uint32_t a = __ldg(db.off + label), b = __ldg(db.off + label + 1);
+    const unsigned long long nz = nz_bytes(*reinterpret_cast<const unsigned long long *>(db.blob + b - 8u));
+    return b - a - 8u + (nz ? (uint32_t)(64 - __clzll((long long)nz)) >> 3 : 0u);
+}
 __device__ __forceinline__ uint32_t tax_len_of(const DevDB &db, const utb_result &v) {
-    uint32_t ll = __ldg(db.off + v.label + 1) - __ldg(db.off + v.label) - 1u;
+    uint32_t ll = label_len(db, v.label);
     if (v.kind == UTB_WALK) {
         if (v.cut == UTB_CUT_EMPTY) ll = 0;                        // dv == -1 (itree.c:1087)
         else if (v.cut != UTB_CUT_FULL && v.cut < ll) ll = v.cut;  // first dv bytes (itree.c:1088)
@@ -2029,20 +2055,38 @@ static int db_upload_impl(const utb_ctr *ctr, int device, utb_db *db) {
     if (cudaDeviceGetAttribute(&db->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || db->sm_count < 1) { cudaGetLastError(); db->sm_count = 148; }
     CK(cudaMalloc(&db->binix, nb_binix + 64));
     CK(cudaMalloc(&db->recs, nb_recs + 64));                       // +slack: itree.c:766
-    CK(cudaMalloc(&db->blob, ctr->blob_len + 64));
+    // the label strings, each at a multiple of 8 bytes and NUL-padded to the next one: the vote's walk compares two
+    // labels eight characters per step from the same offset in both (scan_token)
+    size_t blob8 = 0;
+    for (size_t i = 0; i < nl; ++i) blob8 += ((size_t)(ctr->off[i + 1] - ctr->off[i]) + 7) & ~(size_t)7;
+    if (blob8 + 64 >= ((size_t)1 << 32)) { utb_set_error("label strings exceed 4 GB"); return UTB_ERR_LIMIT; }
+    char *h_blob = (char *)calloc(blob8 + 64, 1);
+    uint32_t *h_off = (uint32_t *)malloc((nl + 1) * 4);
+    if (!h_blob || !h_off) { free(h_blob); free(h_off); utb_set_error("out of memory"); return UTB_ERR_NOMEM; }
+    {
+        size_t at = 0;
+        for (size_t i = 0; i < nl; ++i) {
+            const size_t l = ctr->off[i + 1] - ctr->off[i];
+            h_off[i] = (uint32_t)at;
+            memcpy(h_blob + at, ctr->blob + ctr->off[i], l);
+            at += (l + 7) & ~(size_t)7;
+        }
+        h_off[nl] = (uint32_t)at;
+    }
+    struct HostTmp { char *b; uint32_t *o; ~HostTmp() { free(b); free(o); } } host_tmp{h_blob, h_off};
+    CK(cudaMalloc(&db->blob, blob8 + 64));
     CK(cudaMalloc(&db->off, (nl + 1) * 4));
     CK(cudaMalloc(&db->rank, (nl + 1) * 4));
     CK(cudaMalloc(&db->by_rank, (nl + 1) * 4));
     CK(cudaMemset((char *)db->binix + nb_binix, 0, 64));
     CK(cudaMemset((char *)db->recs + nb_recs, 0, 64));
-    CK(cudaMemset(db->blob, 0, ctr->blob_len + 64));
     rc = upload_streamed(device, db->binix, ctr->binix_raw, nb_binix); if (rc) return rc;
     rc = upload_streamed(device, db->recs, ctr->recs, nb_recs); if (rc) return rc;
-    CK(cudaMemcpy(db->blob, ctr->blob, ctr->blob_len, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(db->off, ctr->off, (nl + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db->blob, h_blob, blob8 + 64, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(db->off, h_off, (nl + 1) * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db->rank, ctr->rank, nl * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(db->by_rank, ctr->by_rank, nl * 4, cudaMemcpyHostToDevice));
-    db->nb_binix = nb_binix; db->nb_recs = nb_recs; db->nb_blob = ctr->blob_len + 64; db->nb_lab = (nl + 1) * 4;
+    db->nb_binix = nb_binix; db->nb_recs = nb_recs; db->nb_blob = blob8 + 64; db->nb_lab = (nl + 1) * 4;
     db->d.binix32 = ctr->binix_bytes == 4 ? (const uint32_t *)db->binix : nullptr;
     db->d.binix64 = ctr->binix_bytes == 8 ? (const uint64_t *)db->binix : nullptr;
     db->d.recs = (const uint8_t *)db->recs;
