@@ -365,9 +365,10 @@ static int sink_reserve(sink_t *k, size_t upto) {
         if (!k->mapped || upto <= k->map_hi) return 0;
         /* move the window: [off rounded down to a page, at least SINK_WINDOW further); the file grows with it (sparse) */
         sink_unmap(k);
-        const size_t lo = k->off & ~(size_t)4095;
+        const size_t pg = (size_t)sysconf(_SC_PAGESIZE) - 1;       /* a mapping starts on a page of the file */
+        const size_t lo = k->off & ~pg;
         size_t hi = lo + SINK_WINDOW;
-        if (hi < upto) hi = (upto + 4095) & ~(size_t)4095;
+        if (hi < upto) hi = (upto + pg) & ~pg;
         if (hi > k->file_len) {
             struct statfs fs;                                      /* a store into a mapping of a full file system is a SIGBUS, not an error code */
             if (fstatfs(k->fd, &fs) || (size_t)fs.f_bavail * (size_t)fs.f_bsize < 2 * (hi - lo) || ftruncate(k->fd, (off_t)hi)) { k->mapped = 0; return 0; }
