@@ -4,7 +4,7 @@
 Default workload (BASELINE.json configs[1], "l2s"): a synthetic L2-scale CTR (5,000
 prokaryote-sized genomes, complevel 2, ~1.1 G records, ~8 GB) against 10 M synthetic
 150 bp reads per GPU with reverse complement.  A "step" is one pass of the hot path over
-the whole read set.  `--config l4 | long | u32` runs the other BASELINE configs the same
+the whole read set.  `--config toy | l4 | long | u32` runs the other BASELINE configs the same
 way (their lines are committed under profiles/).
 
   value     reads/s with the FASTA bytes already resident in HBM: device time of
@@ -67,6 +67,9 @@ CONFIGS = {
     # IXTYPE=uint32_t (SZ=9), > 65,536 labels, complevel 0 (dense sampling), 250 bp reads (BASELINE.json configs[4])
     "u32": dict(universe=(60, 11, 10, 10, 6000), complevel=0, ix_bytes=4, reads=10_000_000, read_len=250,
                 desc="uint32-label synthetic CTR (66000 genomes x 6 kb, 73500 labels, complevel 0) vs 10M x 250bp reads, RC"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    "toy": dict(universe=(2, 2, 5, 1, 1_000_000), complevel=2, ix_bytes=2, reads=100_000, read_len=150,
+                desc="toy CTR (20 synthetic genomes x 1 Mb, complevel 2) vs 100k x 150bp reads, RC"),
     "small": dict(universe=(4, 3, 3, 3, 400_000), complevel=2, ix_bytes=2, reads=400_000, read_len=150,
                   desc="small synthetic CTR (108 genomes x 0.4 Mb, complevel 2) vs 400k x 150bp reads, RC"),
 }
