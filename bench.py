@@ -383,7 +383,9 @@ def main():
         ctr_path, ctr_meta = ensure_ctr(args.config, cfg, local)
     n_reads = cfg["reads"]
     t = time.time()
-    reads_np, off = make_reads(cfg, rank * n_reads, n_reads, local, pin=True)
+    from utree_b200.shard import shard_range
+    lo_read, hi_read = shard_range(world * n_reads, rank, world)    # this rank's contiguous range of the job's reads
+    reads_np, off = make_reads(cfg, lo_read, hi_read - lo_read, local, pin=True)
     n_bases = int(off[-1]) - 13 * n_reads
     log(f"rank {rank}: {n_reads} reads ({reads_np.size / 1e9:.2f} GB FASTA, {n_bases / 1e9:.2f} G bases) in {time.time() - t:.1f} s")
 
