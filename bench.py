@@ -459,9 +459,11 @@ def main():
         rc_, ex, nbytes, st = searcher.search_mem(None, do_rc=True, ptr=ptr, n=reads_np.size, copy=False)
         assert rc_ == 0 and nbytes == out_len
         e2e_stats.append(st)
+    own_e2e_s = time.time() - t0                                   # this rank alone; the figure uses the time up to the barrier, i.e. the slowest rank
     barrier()
     e2e_s = time.time() - t0
     clocks = sampler.summary()
+    log(f"rank {rank}: e2e {own_e2e_s * 1e3 / args.steps:.1f} ms per step on its own ({ncpu} cores visible, {host_threads} host threads)")
 
     # ---- reduce over ranks: max time, sum of units -----------------------------------
     tt = torch.tensor([dev_s, e2e_s], dtype=torch.float64, device="cuda")
@@ -470,6 +472,11 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_s_max, e2e_s_max = tt.tolist()
+    per_rank_ms = [round(own_e2e_s * 1e3 / args.steps, 1)]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device="cuda") for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([own_e2e_s * 1e3 / args.steps], dtype=torch.float64, device="cuda"))
+        per_rank_ms = [round(float(g.item()), 1) for g in gathered]
     lookups_all, hits_all, launches_all, bases_all = cnt.tolist()
 
     # ---- extra legs (rank 0; the other ranks wait on the host) ----------------------------
@@ -609,7 +616,7 @@ def main():
             "ms_per_step": round(dev_s_max * 1e3 / args.steps, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload,
             "e2e": {"value": round(e2e_value, 1), "unit": "reads/s", "h2d_bytes_per_step": int(st["h2d_bytes"]),
-                    "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": round(e2e_s_max * 1e3 / args.steps, 1),
+                    "d2h_bytes_per_step": int(st["d2h_bytes"]), "ms_per_step": round(e2e_s_max * 1e3 / args.steps, 1), "per_rank_ms": per_rank_ms,
                     "bases_per_s": round(bases_all * args.steps / e2e_s_max, 1),
                     "api": "utb_search_mem (page-locked host FASTA buffer -> text in the searcher's page-locked arena, "
                            "allocated once by the warm-up steps)", "out_bytes_per_step": int(st["out_bytes"]),
